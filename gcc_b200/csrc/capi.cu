@@ -1,0 +1,41 @@
+// capi.cu -- status / error plumbing of the C ABI (include/gccb200.h).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace gccb {
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return GCCB_ERR_CUDA;
+  }
+  return GCCB_OK;
+}
+}  // namespace gccb
+
+extern "C" int gccb_version(void) { return GCCB_VERSION; }
+
+extern "C" const char* gccb_last_error(void) { return gccb::g_err; }
+
+extern "C" int gccb_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    gccb::set_last_error("gccb_arch: no CUDA device");
+    cudaGetLastError();
+    return GCCB_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return major * 10 + minor;
+}

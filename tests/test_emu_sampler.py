@@ -1,0 +1,60 @@
+"""CPU: sampler kernels (gcc_b200/csrc/sampler.cu) run under the fiber emulator and
+compared bit-for-bit with the oracle.  Kernel LOGIC only -- the real parity gate is
+tests/test_gpu_*.py on a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from emu_util import NpBatch, NpGraph, lib, ptr
+from gcc_b200.datasets import synthetic
+from oracle import rwr as orwr
+
+
+def _run(g, B, rw_hops, key, first=0, node_cap=None, edge_cap=None):
+    L = lib()
+    G = NpGraph(g, rw_hops, 0.8, key)
+    seeds = np.zeros(B, np.int64)
+    sids = np.zeros(B, np.int64)
+    assert L.gccb_draw_seeds(ptr(G.cdf), g.num_nodes, key, first, B, ptr(seeds), ptr(sids), None) == 0
+    want_seeds = orwr.draw_seeds(G.cdf, key, range(first, first + B))
+    assert np.array_equal(seeds, want_seeds) and np.array_equal(sids, np.arange(first, first + B))
+    want = orwr.rwr_batch(G.indptr, G.indices, key, sids, seeds, G.btable, G.rt,
+                          int(G.btable.max()) + 65, 1 << 16)
+    views = [[want[2 * i + v] for i in range(B)] for v in (0, 1)]
+    N = max(sum(s["n"] for s in v) for v in views)
+    E = max(sum(s["m"] for s in v) for v in views)
+    b = NpBatch(B, node_cap or N + 7, edge_cap or E + 11)
+    ws = np.zeros(L.gccb_sample_batch_workspace(B, int(G.btable.max())), np.uint8)
+    rc = L.gccb_sample_batch(C.byref(G.c), ptr(seeds), ptr(sids), C.byref(b.c), ptr(ws), ws.nbytes, None)
+    assert rc == 0, L.gccb_last_error()
+    return b, views, want
+
+
+@pytest.mark.parametrize("name,B,hops", [("er", 5, 24), ("star", 3, 16), ("cl", 4, 40)])
+def test_sampler_matches_oracle(name, B, hops):
+    g = {"er": lambda: synthetic.erdos_renyi(300, 1200, seed=2),
+         "star": lambda: synthetic.star_graph(40),
+         "cl": lambda: synthetic.chung_lu(2000, 12000, seed=3)}[name]()
+    b, views, want = _run(g, B, hops, key=0xABCDEF12345)
+    assert b.flags[0] == 0
+    for v in (0, 1):
+        got = b.view_graphs(v)
+        assert b.node_off[v, B] == sum(s["n"] for s in views[v])
+        assert b.edge_off[v, B] == sum(s["m"] for s in views[v])
+        for gi, (a, w) in enumerate(zip(got, views[v])):
+            assert np.array_equal(a["subv"], w["subv"]), (v, gi)
+            assert np.array_equal(a["indptr"], w["indptr"]), (v, gi)
+            assert np.array_equal(a["indices"], w["indices"]), (v, gi)
+            c = b.counters[v * B + gi]
+            assert (c[0], c[1], c[2], c[3]) == (w["n"], w["m"], w["steps"], w["sumdeg"])
+        n = b.node_off[v, B]
+        assert np.array_equal(b.sub_deg[v, :n], np.diff(b.indptr[v, :n + 1]))
+        assert np.array_equal(b.graph_id[v, :n], np.repeat(np.arange(B), np.diff(b.node_off[v])))
+
+
+def test_sampler_capacity_overflow_is_flagged_not_fatal():
+    g = synthetic.erdos_renyi(300, 1200, seed=2)
+    b, views, _ = _run(g, 4, 24, key=5, node_cap=20, edge_cap=10000)
+    assert b.flags[0] & 1
+    assert b.node_off[0, 4] == -1 or b.node_off[1, 4] == -1
