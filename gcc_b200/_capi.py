@@ -57,7 +57,7 @@ _PROTOS = {
                                    p, p, p]),
     "gccb_gin_backward_workspace": (C.c_size_t, [C.POINTER(GinCfg), C.c_int32, C.c_int32]),
     "gccb_gin_backward": (C.c_int, [C.POINTER(GinCfg), C.POINTER(Batch), C.c_int32, p, p, p, p,
-                                    p, C.c_size_t, p]),
+                                    C.c_uint64, C.c_uint64, C.c_int32, p, C.c_size_t, p]),
     "gccb_moco_logits": (C.c_int, [p, p, p, C.c_int32, C.c_int32, C.c_int32, C.c_float, p, p]),
     "gccb_moco_logits_backward": (C.c_int, [p, p, p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                             p, p]),
@@ -66,7 +66,7 @@ _PROTOS = {
     "gccb_infonce_fused": (C.c_int, [p, p, p, C.c_int32, C.c_int32, C.c_int32, C.c_float, p, p,
                                      p, C.c_size_t, p]),
     "gccb_moco_enqueue": (C.c_int, [p, p, C.c_int32, C.c_int32, C.c_int32, p, p]),
-    "gccb_e2e_nce": (C.c_int, [p, p, C.c_int32, C.c_int32, C.c_float, p, p, p, p]),
+    "gccb_e2e_nce": (C.c_int, [p, p, C.c_int32, C.c_int32, C.c_float, p, p, p, p, C.c_size_t, p]),
     "gccb_clip_adam_ema": (C.c_int, [p, p, p, p, p, C.c_int64, C.c_int64, p, C.c_float,
                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_float, p, p, p]),

@@ -1,0 +1,215 @@
+// gin_common.cuh -- layouts and tile helpers shared by the GIN forward / backward kernels.
+#pragma once
+#include "common.cuh"
+
+namespace gccb {
+
+#define GCCB_DINP 64          // padded width of the layer-0 input [pos | deg_emb | seed | 0..]
+#define GCCB_TILE_ROWS 64
+#define GCCB_KC 64            // K-chunk of the weight operand staged in shared memory
+#define GCCB_MAX_L 8
+
+struct GinDims {
+  int L, H, P, D, maxdeg, din;   // din = P + D + 1 (49)
+  int norm;
+  float bn_eps, bn_mom, norm_eps, drop_p;
+};
+
+__host__ __device__ __forceinline__ int gin_in_features(const GinDims& d, int l) { return l == 0 ? d.din : d.H; }
+__host__ __device__ __forceinline__ int gin_in_width(const GinDims& d, int l) { return l == 0 ? GCCB_DINP : d.H; }
+
+// byte offsets inside the activation stash of ONE view
+struct ActsLayout {
+  size_t x0;                                   // float [node_cap][64]
+  size_t a[GCCB_MAX_L], z1[GCCB_MAX_L], z2[GCCB_MAX_L], h[GCCB_MAX_L];
+  size_t stats;                                // double [L-1][3][2][H]  column sums / sums of squares
+  size_t pooled;                               // float [L][B][PW]
+  size_t score;                                // float [B][H]  (pre-normalisation)
+  size_t feat;                                 // float [B][H]
+  size_t total;
+  int PW;
+};
+
+inline ActsLayout make_acts_layout(const GinDims& d, int B, int node_cap) {
+  ActsLayout a;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  a.x0 = take((size_t)node_cap * GCCB_DINP * 4);
+  for (int l = 0; l < GCCB_MAX_L; ++l) a.a[l] = a.z1[l] = a.z2[l] = a.h[l] = 0;
+  for (int l = 0; l < d.L - 1; ++l) {
+    a.a[l] = take((size_t)node_cap * gin_in_width(d, l) * 4);
+    a.z1[l] = take((size_t)node_cap * d.H * 4);
+    a.z2[l] = take((size_t)node_cap * d.H * 4);
+    a.h[l] = take((size_t)node_cap * d.H * 4);
+  }
+  a.stats = take((size_t)(d.L - 1) * 3 * 2 * d.H * 8);
+  a.PW = d.H > GCCB_DINP ? d.H : GCCB_DINP;
+  a.pooled = take((size_t)d.L * B * a.PW * 4);
+  a.score = take((size_t)B * d.H * 4);
+  a.feat = take((size_t)B * d.H * 4);
+  a.total = off;
+  return a;
+}
+
+// flat parameter layout (floats); mirrors gccb_gin_layout_t
+inline void make_param_layout(const GinDims& d, gccb_gin_layout_t* o) {
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t r = off; off += n; return r; };
+  for (int l = 0; l < 8; ++l)
+    o->w1[l] = o->b1[l] = o->bn1_w[l] = o->bn1_b[l] = o->w2[l] = o->b2[l] = o->bna_w[l] = o->bna_b[l] =
+        o->bnb_w[l] = o->bnb_b[l] = o->wp[l] = o->bp[l] = -1;
+  for (int l = 0; l < d.L - 1; ++l) {
+    o->w1[l] = take((int64_t)d.H * gin_in_features(d, l));
+    o->b1[l] = take(d.H);
+    o->bn1_w[l] = take(d.H);
+    o->bn1_b[l] = take(d.H);
+    o->w2[l] = take((int64_t)d.H * d.H);
+    o->b2[l] = take(d.H);
+    o->bna_w[l] = take(d.H);
+    o->bna_b[l] = take(d.H);
+    o->bnb_w[l] = take(d.H);
+    o->bnb_b[l] = take(d.H);
+  }
+  for (int l = 0; l < d.L; ++l) {
+    o->wp[l] = take((int64_t)d.H * gin_in_features(d, l));
+    o->bp[l] = take(d.H);
+  }
+  o->emb = take((int64_t)(d.maxdeg + 1) * d.D);
+  o->total = off;
+  o->run_total = (int64_t)(d.L - 1) * 3 * 2 * d.H;
+}
+
+inline int dims_from_cfg(const gccb_gin_cfg_t* c, GinDims* d) {
+  if (!c) return GCCB_ERR_BADARG;
+  d->L = c->num_layers; d->H = c->hidden; d->P = c->pos_dim; d->D = c->deg_dim;
+  d->maxdeg = c->max_degree; d->din = c->pos_dim + c->deg_dim + 1; d->norm = c->norm;
+  d->bn_eps = c->bn_eps; d->bn_mom = c->bn_momentum; d->norm_eps = c->norm_eps; d->drop_p = c->dropout_p;
+  if (d->L < 2 || d->L > GCCB_MAX_L || (d->H != 32 && d->H != 64 && d->H != 128 && d->H != 256) ||
+      d->din > GCCB_DINP || d->P < 2 || d->P > 32 || d->D < 1 || d->maxdeg < 1) {
+    set_last_error("gin: unsupported configuration (L=%d H=%d pos=%d deg=%d): need 2<=L<=8, "
+                   "H in {32,64,128,256}, pos+deg+1<=64, pos<=32", d->L, d->H, d->P, d->D);
+    return GCCB_ERR_BADARG;
+  }
+  return GCCB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// BatchNorm coefficients from accumulated column sums (train mode) or running stats.
+//   sums: double [2][H] (sum, sum of squares) over N rows.
+//   out (shared memory): mean[H], invstd[H], sc[H] = gamma*invstd, sh[H] = beta - mean*sc
+// Block 0 optionally applies the running-statistics update (momentum, unbiased variance).
+__device__ __forceinline__ void bn_prepare(const double* __restrict__ sums, int N, int H,
+                                           const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, float eps,
+                                           float* mean_s, float* invstd_s, float* sc_s, float* sh_s,
+                                           float* __restrict__ running /* [2][H] or null */,
+                                           bool use_running, bool update_running, float momentum) {
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    double mean, var;
+    if (use_running) {
+      mean = running[c];
+      var = running[H + c];
+    } else {
+      double n = N > 0 ? (double)N : 1.0;
+      mean = sums[c] / n;
+      var = sums[H + c] / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      if (update_running && running && blockIdx.x == 0) {
+        double unb = N > 1 ? var * n / (n - 1.0) : var;
+        running[c] = (float)((1.0 - momentum) * running[c] + momentum * mean);
+        running[H + c] = (float)((1.0 - momentum) * running[H + c] + momentum * unb);
+      }
+    }
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma[c];
+    mean_s[c] = (float)mean;
+    invstd_s[c] = invstd;
+    sc_s[c] = g * invstd;
+    sh_s[c] = beta[c] - (float)mean * g * invstd;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 64-row tile GEMM: acc[4][CPT] += As[row][k] * Ws[k][col], K a multiple of 32.
+// 256 threads: ty = tid/16 owns rows ty*4..+3, tx = tid%16 owns NOUT/16 columns.
+template <int NOUT> struct TileCols {
+  static constexpr int CPT = NOUT / 16;
+  static constexpr int VEC = CPT < 4 ? CPT : 4;
+  __device__ static __forceinline__ int col(int tx, int c) { return (c / VEC) * (16 * VEC) + tx * VEC + (c % VEC); }
+};
+
+// Stage a K-chunk of the weight operand: Ws[kk][c] = getw(k0 + kk, c), kk < KC, c < NOUT.
+template <int NOUT, class GetW>
+__device__ __forceinline__ void stage_weights(float* Ws, int k0, int kc, GetW getw) {
+  constexpr int LDW = NOUT + 4;
+  for (int idx = threadIdx.x; idx < kc * NOUT; idx += blockDim.x) {
+    int kk = idx % kc, c = idx / kc;                 // consecutive threads -> consecutive k (coalesced in W rows)
+    Ws[kk * LDW + c] = getw(k0 + kk, c);
+  }
+}
+
+template <int NOUT>
+__device__ __forceinline__ void tile_mma(const float* As, int lda, int k0, int kc, const float* Ws,
+                                         float (&acc)[4][TileCols<NOUT>::CPT]) {
+  using TC = TileCols<NOUT>;
+  constexpr int LDW = NOUT + 4;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  for (int kk = 0; kk < kc; ++kk) {
+    float a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = As[(ty * 4 + i) * lda + k0 + kk];
+    float w[TC::CPT];
+#pragma unroll
+    for (int c = 0; c < TC::CPT; ++c) w[c] = Ws[kk * LDW + TC::col(tx, c)];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < TC::CPT; ++c) acc[i][c] = fmaf(a[i], w[c], acc[i][c]);
+  }
+}
+
+// Full tile GEMM over K with the weight operand streamed through shared memory in KC chunks.
+// Callers must __syncthreads() after filling As and may not touch Ws concurrently.
+template <int NOUT, class GetW>
+__device__ __forceinline__ void tile_gemm(const float* As, int lda, int K, float* Ws, GetW getw,
+                                          float (&acc)[4][TileCols<NOUT>::CPT]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < TileCols<NOUT>::CPT; ++c) acc[i][c] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += GCCB_KC) {
+    int kc = K - k0 < GCCB_KC ? K - k0 : GCCB_KC;
+    __syncthreads();                                   // previous chunk fully consumed
+    stage_weights<NOUT>(Ws, k0, kc, getw);
+    __syncthreads();
+    tile_mma<NOUT>(As, lda, k0, kc, Ws, acc);
+  }
+}
+
+// Column sums of a per-thread [4][CPT] tile fragment -> shared red[2][NOUT] (sum, sum sq),
+// then double atomics into `sums` [2][NOUT].  vals outside the valid rows must be zero.
+template <int NOUT>
+__device__ __forceinline__ void tile_colstats(const float (&v)[4][TileCols<NOUT>::CPT], float* red /*[2][16][NOUT]*/,
+                                              double* __restrict__ sums) {
+  using TC = TileCols<NOUT>;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int c = 0; c < TC::CPT; ++c) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s += v[i][c]; q = fmaf(v[i][c], v[i][c], q); }
+    red[(0 * 16 + ty) * NOUT + TC::col(tx, c)] = s;
+    red[(1 * 16 + ty) * NOUT + TC::col(tx, c)] = q;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * NOUT; idx += blockDim.x) {
+    int which = idx / NOUT, c = idx - which * NOUT;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) s += red[(which * 16 + t) * NOUT + c];
+    atomicAdd(&sums[which * NOUT + c], (double)s);
+  }
+  __syncthreads();
+}
+
+}  // namespace gccb

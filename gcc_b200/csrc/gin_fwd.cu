@@ -1,0 +1,461 @@
+// gin_fwd.cu -- GIN encoder forward for one view of a batch of ego-nets.
+//
+// Replaces GraphEncoder.forward (gcc/models/graph_encoder.py:132-200, gin branch) and
+// UnsupervisedGIN.forward (gcc/models/gin.py:213-232) including what DGL does inside:
+//   GINConv('sum', eps buffer = 0): rst = (1+eps)*h + sum_{u in N(v)} h_u ; apply_func(rst)
+//   SumPooling: per-graph segment sum.
+// Per GIN layer (gin.py:54-58, :107-116, :218-220):
+//   a  = h + sum_nbr h          (gather / segmented reduce, fused into GEMM1's A tile)
+//   z1 = a W1^T + b1            -> train-mode BatchNorm statistics in the epilogue
+//   x1 = relu(bn1(z1))          (applied on load of GEMM2's A tile)
+//   z2 = x1 W2^T + b2           -> statistics
+//   y  = relu(bn_a(z2))         -> statistics (needs the full-batch mean of y)
+//   h' = relu(bn_b(y))
+// Every "-> statistics" is a column reduction over all N rows of the view, i.e. a
+// grid-wide dependency; kernel boundaries provide it.  Round 1 uses fp32 SIMT tiles
+// (bit-level agreement with an fp32 reference matters more than tensor-pipe speed
+// at hidden=64, where the layer is bandwidth/launch bound -- see DESIGN.md).
+#include "gin_common.cuh"
+
+namespace gccb {
+
+// X0 = [pos | degree_embedding(clamp(deg)) | seed one-hot | 0]   graph_encoder.py:152-165
+__global__ void __launch_bounds__(256)
+gin_build_x0_kernel(GinDims d, const int32_t* __restrict__ node_off_v, int B,
+                    const float* __restrict__ pos, const int32_t* __restrict__ sub_deg,
+                    const int32_t* __restrict__ graph_id, const float* __restrict__ emb,
+                    float* __restrict__ x0) {
+  const int N = node_off_v[B];
+  const int total = N * GCCB_DINP;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int r = idx / GCCB_DINP, c = idx - r * GCCB_DINP;
+    float v = 0.f;
+    if (c < d.P) {
+      v = pos[(size_t)r * d.P + c];
+    } else if (c < d.P + d.D) {
+      int dg = sub_deg[r];
+      dg = dg < 0 ? 0 : (dg > d.maxdeg ? d.maxdeg : dg);
+      v = emb[(size_t)dg * d.D + (c - d.P)];
+    } else if (c == d.P + d.D) {
+      v = (r == node_off_v[graph_id[r]]) ? 1.0f : 0.f;     // seed = first row of its graph
+    }
+    x0[idx] = v;
+  }
+}
+
+// K1: a = h + sum_nbr h ; z1 = a W1^T + b1 ; column statistics of z1.
+template <int KIN, int H>
+__global__ void __launch_bounds__(256)
+gin_agg_gemm1_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_t* __restrict__ indptr,
+                     const int32_t* __restrict__ indices, const float* __restrict__ h,
+                     const float* __restrict__ W1, int in_features, const float* __restrict__ b1,
+                     float eps_gin, float* __restrict__ a_out, float* __restrict__ z1,
+                     double* __restrict__ sums) {
+  GCCB_DYN_SMEM(float, smem);
+  constexpr int LDA = KIN + 1;
+  float* As = smem;                          // [64][KIN+1]
+  float* Ws = As + GCCB_TILE_ROWS * LDA;     // [KC][H+4]
+  float* red = Ws + GCCB_KC * (H + 4);       // [2][16][H]
+  const int N = node_off_v[B];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;
+  using TC = TileCols<H>;
+  for (int tile = blockIdx.x; tile * GCCB_TILE_ROWS < N; tile += gridDim.x) {
+    const int row0 = tile * GCCB_TILE_ROWS;
+    __syncthreads();                                   // As free (previous tile consumed)
+    // gather / segmented reduce: one warp per row, lanes across the feature dimension
+    for (int rr = warp; rr < GCCB_TILE_ROWS; rr += 8) {
+      const int r = row0 + rr;
+      constexpr int PER = (KIN + 31) / 32;
+      float acc[PER];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) acc[j] = 0.f;
+      if (r < N) {
+        const int beg = indptr[r], end = indptr[r + 1];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          int c = lane + 32 * j;
+          if (c < KIN) acc[j] = (1.0f + eps_gin) * h[(size_t)r * KIN + c];
+        }
+        for (int e = beg; e < end; ++e) {
+          const int u = indices[e];
+#pragma unroll
+          for (int j = 0; j < PER; ++j) {
+            int c = lane + 32 * j;
+            if (c < KIN) acc[j] += h[(size_t)u * KIN + c];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        int c = lane + 32 * j;
+        if (c < KIN) {
+          As[rr * LDA + c] = acc[j];
+          if (r < N) a_out[(size_t)r * KIN + c] = acc[j];
+        }
+      }
+    }
+    __syncthreads();
+    float acc[4][TC::CPT];
+    tile_gemm<H>(As, LDA, KIN, Ws,
+                 [&](int k, int o) { return k < in_features ? W1[(size_t)o * in_features + k] : 0.f; }, acc);
+    float v[4][TC::CPT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + ty * 4 + i;
+#pragma unroll
+      for (int c = 0; c < TC::CPT; ++c) {
+        const int col = TC::col(tx, c);
+        float z = acc[i][c] + b1[col];
+        v[i][c] = r < N ? z : 0.f;
+        if (r < N) z1[(size_t)r * H + col] = z;
+      }
+    }
+    tile_colstats<H>(v, red, sums);
+  }
+}
+
+// K2: x1 = relu(bn1(z1)) ; z2 = x1 W2^T + b2 ; column statistics of z2.
+template <int H>
+__global__ void __launch_bounds__(256)
+gin_bn_gemm2_kernel(const int32_t* __restrict__ node_off_v, int B, const float* __restrict__ z1,
+                    const double* __restrict__ sums1, const float* __restrict__ g1,
+                    const float* __restrict__ be1, float bn_eps, float* __restrict__ running1,
+                    int use_running, int update_running, float momentum,
+                    const float* __restrict__ W2, const float* __restrict__ b2,
+                    float* __restrict__ z2, double* __restrict__ sums2) {
+  GCCB_DYN_SMEM(float, smem);
+  constexpr int LDA = H + 1;
+  float* As = smem;
+  float* Ws = As + GCCB_TILE_ROWS * LDA;
+  float* red = Ws + GCCB_KC * (H + 4);
+  float* coef = red + 2 * 16 * H;            // mean | invstd | sc | sh
+  const int N = node_off_v[B];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  using TC = TileCols<H>;
+  bn_prepare(sums1, N, H, g1, be1, bn_eps, coef, coef + H, coef + 2 * H, coef + 3 * H, running1,
+             use_running != 0, update_running != 0, momentum);
+  __syncthreads();
+  const float* sc = coef + 2 * H;
+  const float* sh = coef + 3 * H;
+  for (int tile = blockIdx.x; tile * GCCB_TILE_ROWS < N; tile += gridDim.x) {
+    const int row0 = tile * GCCB_TILE_ROWS;
+    __syncthreads();
+    for (int idx = tid; idx < GCCB_TILE_ROWS * H; idx += 256) {
+      int rr = idx / H, c = idx - rr * H;
+      int r = row0 + rr;
+      float x = 0.f;
+      if (r < N) x = fmaxf(fmaf(z1[(size_t)r * H + c], sc[c], sh[c]), 0.f);
+      As[rr * LDA + c] = x;
+    }
+    __syncthreads();
+    float acc[4][TC::CPT];
+    tile_gemm<H>(As, LDA, H, Ws, [&](int k, int o) { return W2[(size_t)o * H + k]; }, acc);
+    float v[4][TC::CPT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + ty * 4 + i;
+#pragma unroll
+      for (int c = 0; c < TC::CPT; ++c) {
+        const int col = TC::col(tx, c);
+        float z = acc[i][c] + b2[col];
+        v[i][c] = r < N ? z : 0.f;
+        if (r < N) z2[(size_t)r * H + col] = z;
+      }
+    }
+    tile_colstats<H>(v, red, sums2);
+  }
+}
+
+// K3: y = relu(bn_a(z2)); column statistics of y.   (elementwise + reduction)
+// K4 (mode 1): h' = relu(bn_b(y)) written out.
+// One kernel, two modes: mode 0 accumulates sums of y; mode 1 writes h'.
+template <int H>
+__global__ void __launch_bounds__(256)
+gin_bn_tail_kernel(int mode, const int32_t* __restrict__ node_off_v, int B,
+                   const float* __restrict__ z2, const double* __restrict__ sums_a,
+                   const float* __restrict__ ga, const float* __restrict__ bea,
+                   float* __restrict__ running_a, const double* __restrict__ sums_b_in,
+                   const float* __restrict__ gb, const float* __restrict__ beb,
+                   float* __restrict__ running_b, float bn_eps, int use_running, int update_running,
+                   float momentum, double* __restrict__ sums_b_out, float* __restrict__ h_out) {
+  __shared__ float coef_a[4 * H];
+  __shared__ float coef_b[4 * H];
+  __shared__ float red[2 * 8 * H];
+  const int N = node_off_v[B];
+  const int tid = threadIdx.x;
+  // BN_a running stats are updated by mode 0 only, BN_b's by mode 1 only (once each)
+  bn_prepare(sums_a, N, H, ga, bea, bn_eps, coef_a, coef_a + H, coef_a + 2 * H, coef_a + 3 * H,
+             running_a, use_running != 0, update_running != 0 && mode == 0, momentum);
+  if (mode == 1)
+    bn_prepare(sums_b_in, N, H, gb, beb, bn_eps, coef_b, coef_b + H, coef_b + 2 * H, coef_b + 3 * H,
+               running_b, use_running != 0, update_running != 0, momentum);
+  __syncthreads();
+  // thread -> fixed column c = tid % H, row lane = tid / H ; rows strided
+  constexpr int RPB = 256 / H > 0 ? 256 / H : 1;       // rows handled per pass (H <= 256)
+  const int c = tid % H, rl = tid / H;
+  const float sca = coef_a[2 * H + c], sha = coef_a[3 * H + c];
+  float s = 0.f, q = 0.f;
+  if (mode == 0) {
+    for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
+      float y = fmaxf(fmaf(z2[(size_t)r * H + c], sca, sha), 0.f);
+      s += y;
+      q = fmaf(y, y, q);
+    }
+    red[(0 * RPB + rl) * H + c] = s;
+    red[(RPB + rl) * H + c] = q;
+    __syncthreads();
+    for (int idx = tid; idx < 2 * H; idx += 256) {
+      int which = idx / H, cc = idx - which * H;
+      float t = 0.f;
+      for (int j = 0; j < RPB; ++j) t += red[(which * RPB + j) * H + cc];
+      atomicAdd(&sums_b_out[which * H + cc], (double)t);
+    }
+  } else {
+    const float scb = coef_b[2 * H + c], shb = coef_b[3 * H + c];
+    for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
+      float y = fmaxf(fmaf(z2[(size_t)r * H + c], sca, sha), 0.f);
+      h_out[(size_t)r * H + c] = fmaxf(fmaf(y, scb, shb), 0.f);
+    }
+  }
+}
+
+// K5: SumPooling per graph for every layer's representation, the prediction heads with
+// dropout, the layer sum and the final L2 normalisation (gin.py:222-232, graph_encoder.py:195-196).
+// grid = B (one CTA per graph), block = 256.
+template <int H>
+__global__ void __launch_bounds__(256)
+gin_pool_predict_kernel(GinDims d, const int32_t* __restrict__ node_off_v, int B,
+                        const float* __restrict__ x0, const float* const* __restrict__ h_layers,
+                        const float* __restrict__ params, const int64_t* __restrict__ wp_off,
+                        const int64_t* __restrict__ bp_off, int PW, uint64_t drop_key,
+                        uint64_t drop_step, int drop_layer_base, uint32_t keep_thresh,
+                        float* __restrict__ pooled, float* __restrict__ score_out,
+                        float* __restrict__ feat_out, float* __restrict__ pooled_user) {
+  constexpr int MAXW = H > GCCB_DINP ? H : GCCB_DINP;
+  __shared__ float part[4][MAXW];
+  __shared__ float pl[MAXW];
+  __shared__ float score[H];
+  __shared__ float red_s[8];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  if (node_off_v[B] < 0) return;
+  const int r0 = node_off_v[g], r1 = node_off_v[g + 1];
+  for (int o = tid; o < H; o += 256) score[o] = 0.f;
+  __syncthreads();
+  for (int l = 0; l < d.L; ++l) {
+    const int W = l == 0 ? GCCB_DINP : H;                 // stored width
+    const int inf = l == 0 ? d.din : H;                   // in_features of the head
+    const float* src = l == 0 ? x0 : h_layers[l - 1];
+    // segment sum: thread (c, rg) with c < W, rg in 0..RG-1
+    const int RG = 256 / W >= 4 ? 4 : (256 / W > 0 ? 256 / W : 1);
+    const int c = tid % W, rg = tid / W;
+    if (rg < RG) {
+      float s = 0.f;
+      for (int r = r0 + rg; r < r1; r += RG) s += src[(size_t)r * W + c];
+      part[rg][c] = s;
+    }
+    __syncthreads();
+    for (int cc = tid; cc < W; cc += 256) {
+      float s = 0.f;
+      for (int j = 0; j < RG; ++j) s += part[j][cc];
+      pl[cc] = s;
+      pooled[((size_t)l * B + g) * PW + cc] = s;
+      if (pooled_user && l > 0) pooled_user[((size_t)(l - 1) * B + g) * H + cc] = s;   // all_outputs[1:]
+    }
+    __syncthreads();
+    const float* Wp = params + wp_off[l];
+    const float* bp = params + bp_off[l];
+    for (int o = tid; o < H; o += 256) {
+      float s = bp[o];
+      for (int k = 0; k < inf; ++k) s = fmaf(pl[k], Wp[(size_t)o * inf + k], s);
+      if (drop_layer_base >= 0) {                          // Dropout(p) in train mode, Philox mask
+        const uint32_t e = (uint32_t)(g * H + o);
+        u32x4 w = philox_at(drop_key, drop_step, e >> 2, 0, (uint32_t)(drop_layer_base + l),
+                            GCCB_TAG_DROPOUT);
+        const uint32_t word = (e & 3u) == 0 ? w.x : (e & 3u) == 1 ? w.y : (e & 3u) == 2 ? w.z : w.w;
+        s = word < keep_thresh ? s / (1.0f - d.drop_p) : 0.f;
+      }
+      score[o] += s;
+    }
+    __syncthreads();
+  }
+  // F.normalize(x, p=2, dim=-1, eps): x / max(||x||, eps)
+  float ss = 0.f;
+  for (int o = tid; o < H; o += 256) ss = fmaf(score[o], score[o], ss);
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red_s[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int j = 0; j < 8; ++j) tot += red_s[j];
+  const float nrm = fmaxf(sqrtf(tot), d.norm_eps);
+  for (int o = tid; o < H; o += 256) {
+    score_out[(size_t)g * H + o] = score[o];
+    feat_out[(size_t)g * H + o] = d.norm ? score[o] / nrm : score[o];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int KIN, int H>
+static size_t smem_gemm() {
+  return ((size_t)GCCB_TILE_ROWS * (KIN + 1) + (size_t)GCCB_KC * (H + 4) + 2 * 16 * H + 4 * H) * sizeof(float);
+}
+
+struct FwdArgs {
+  GinDims d;
+  const gccb_batch_t* batch;
+  int view;
+  const float* pos;
+  const float* params;
+  gccb_gin_layout_t lay;
+  float* running;
+  int64_t* nbt;
+  int bn_train;
+  uint64_t drop_key, drop_step;
+  int drop_base;
+  char* acts;
+  ActsLayout al;
+  float* feat;
+  float* pooled_user;
+  const float** d_hptrs;    // device array [L-1] of layer outputs (lives in acts tail)
+  int64_t* d_offs;          // device array [2][8] wp/bp offsets
+  gccb_stream_t stream;
+};
+
+template <int H>
+static int run_forward(const FwdArgs& a) {
+  const GinDims& d = a.d;
+  const int B = a.batch->batch, cap = a.batch->node_cap;
+  const int32_t* node_off_v = a.batch->node_off + (size_t)a.view * (B + 1);
+  const int32_t* indptr = a.batch->indptr + (size_t)a.view * (cap + 1);
+  const int32_t* indices = a.batch->indices + (size_t)a.view * a.batch->edge_cap;
+  const int32_t* sub_deg = a.batch->sub_deg + (size_t)a.view * cap;
+  const int32_t* graph_id = a.batch->graph_id + (size_t)a.view * cap;
+  const float* pos_v = a.pos + (size_t)a.view * cap * d.P;
+  float* x0 = (float*)(a.acts + a.al.x0);
+  double* stats = (double*)(a.acts + a.al.stats);
+  const int tiles = (cap + GCCB_TILE_ROWS - 1) / GCCB_TILE_ROWS;
+  const int grid = tiles < 592 ? tiles : 592;            // 4 waves of 148 SMs at most
+  const int use_running = a.bn_train ? 0 : 1, upd = a.bn_train ? 1 : 0;
+  cudaMemsetAsync(stats, 0, (size_t)(d.L - 1) * 3 * 2 * H * sizeof(double), (cudaStream_t)a.stream);
+  GCCB_LAUNCH(gin_build_x0_kernel, grid, 256, 0, a.stream, d, node_off_v, B, pos_v, sub_deg, graph_id,
+              a.params + a.lay.emb, x0);
+  const float* hin = x0;
+  for (int l = 0; l < d.L - 1; ++l) {
+    float* a_l = (float*)(a.acts + a.al.a[l]);
+    float* z1 = (float*)(a.acts + a.al.z1[l]);
+    float* z2 = (float*)(a.acts + a.al.z2[l]);
+    float* hout = (float*)(a.acts + a.al.h[l]);
+    double* s1 = stats + (size_t)(l * 3 + 0) * 2 * H;
+    double* sa = stats + (size_t)(l * 3 + 1) * 2 * H;
+    double* sb = stats + (size_t)(l * 3 + 2) * 2 * H;
+    float* run1 = a.running ? a.running + (size_t)(l * 3 + 0) * 2 * H : nullptr;
+    float* runa = a.running ? a.running + (size_t)(l * 3 + 1) * 2 * H : nullptr;
+    float* runb = a.running ? a.running + (size_t)(l * 3 + 2) * 2 * H : nullptr;
+    const float* P = a.params;
+    if (l == 0) {
+      auto k = gin_agg_gemm1_kernel<GCCB_DINP, H>;
+      size_t sm = smem_gemm<GCCB_DINP, H>();
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, indptr, indices, hin, P + a.lay.w1[l], d.din,
+                  P + a.lay.b1[l], 0.0f, a_l, z1, s1);
+    } else {
+      auto k = gin_agg_gemm1_kernel<H, H>;
+      size_t sm = smem_gemm<H, H>();
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, indptr, indices, hin, P + a.lay.w1[l], H,
+                  P + a.lay.b1[l], 0.0f, a_l, z1, s1);
+    }
+    {
+      auto k = gin_bn_gemm2_kernel<H>;
+      size_t sm = smem_gemm<H, H>();
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, z1, s1, P + a.lay.bn1_w[l], P + a.lay.bn1_b[l],
+                  d.bn_eps, run1, use_running, upd, d.bn_mom, P + a.lay.w2[l], P + a.lay.b2[l], z2, sa);
+    }
+    auto kt = gin_bn_tail_kernel<H>;
+    GCCB_LAUNCH(kt, grid, 256, 0, a.stream, 0, node_off_v, B, z2, sa, P + a.lay.bna_w[l], P + a.lay.bna_b[l],
+                runa, sb, P + a.lay.bnb_w[l], P + a.lay.bnb_b[l], runb, d.bn_eps, use_running, upd,
+                d.bn_mom, sb, hout);
+    GCCB_LAUNCH(kt, grid, 256, 0, a.stream, 1, node_off_v, B, z2, sa, P + a.lay.bna_w[l], P + a.lay.bna_b[l],
+                runa, sb, P + a.lay.bnb_w[l], P + a.lay.bnb_b[l], runb, d.bn_eps, use_running, upd,
+                d.bn_mom, sb, hout);
+    hin = hout;
+  }
+  const uint32_t keep = (uint32_t)fmin((1.0 - (double)d.drop_p) * 4294967296.0, 4294967295.0);
+  auto kp = gin_pool_predict_kernel<H>;
+  GCCB_LAUNCH(kp, B, 256, 0, a.stream, d, node_off_v, B, x0, a.d_hptrs, a.params, a.d_offs, a.d_offs + 8,
+              a.al.PW, a.drop_key, a.drop_step, a.drop_base, keep, (float*)(a.acts + a.al.pooled),
+              (float*)(a.acts + a.al.score), a.feat, a.pooled_user);
+  return check_launch("gccb_gin_forward");
+}
+
+}  // namespace gccb
+
+using namespace gccb;
+
+extern "C" int gccb_gin_param_layout(const gccb_gin_cfg_t* cfg, gccb_gin_layout_t* out) {
+  GinDims d;
+  int rc = dims_from_cfg(cfg, &d);
+  if (rc) return rc;
+  if (!out) return GCCB_ERR_BADARG;
+  make_param_layout(d, out);
+  return GCCB_OK;
+}
+
+// the stash tail also holds two small device tables the pooling kernel reads
+static size_t acts_tables_bytes() { return 256 + 8 * sizeof(void*) + 16 * sizeof(int64_t); }
+
+extern "C" size_t gccb_gin_acts_bytes(const gccb_gin_cfg_t* cfg, int32_t batch, int32_t node_cap) {
+  GinDims d;
+  if (dims_from_cfg(cfg, &d)) return 0;
+  return make_acts_layout(d, batch, node_cap).total + acts_tables_bytes();
+}
+
+namespace gccb {
+// fills the device tables (layer-output pointers, head offsets) with a tiny kernel so that no
+// host->device copy (and no pinned staging) is needed and the call stays graph-capturable
+__global__ void gin_fill_tables_kernel(char* acts, ActsLayout al, gccb_gin_layout_t lay, int L,
+                                       const float** hptrs, int64_t* offs, int64_t* nbt) {
+  int t = threadIdx.x;
+  if (t < L - 1) hptrs[t] = (const float*)(acts + al.h[t]);
+  if (t < 8) { offs[t] = lay.wp[t]; offs[8 + t] = lay.bp[t]; }
+  if (nbt && t < 3 * (L - 1)) nbt[t] += 1;      // BatchNorm.num_batches_tracked (train mode)
+}
+}  // namespace gccb
+
+extern "C" int gccb_gin_forward(const gccb_gin_cfg_t* cfg, const gccb_batch_t* batch, int32_t view,
+                                const float* pos, const float* params, float* bn_running,
+                                int64_t* num_batches_tracked, int32_t bn_train, uint64_t dropout_key,
+                                uint64_t dropout_step, int32_t dropout_layer_base, void* acts,
+                                size_t acts_bytes, float* feat, float* pooled_out,
+                                gccb_stream_t stream) {
+  FwdArgs a;
+  int rc = dims_from_cfg(cfg, &a.d);
+  if (rc) return rc;
+  if (!batch || !pos || !params || !acts || !feat || view < 0 || view > 1 || (!bn_train && !bn_running)) {
+    set_last_error("gccb_gin_forward: bad argument");
+    return GCCB_ERR_BADARG;
+  }
+  a.al = make_acts_layout(a.d, batch->batch, batch->node_cap);
+  if (acts_bytes < a.al.total + acts_tables_bytes()) {
+    set_last_error("gccb_gin_forward: activation stash too small (%zu < %zu)", acts_bytes,
+                   a.al.total + acts_tables_bytes());
+    return GCCB_ERR_CAPACITY;
+  }
+  make_param_layout(a.d, &a.lay);
+  a.batch = batch; a.view = view; a.pos = pos; a.params = params; a.running = bn_running;
+  a.nbt = num_batches_tracked; a.bn_train = bn_train; a.drop_key = dropout_key; a.drop_step = dropout_step;
+  a.drop_base = dropout_layer_base; a.acts = (char*)acts; a.feat = feat; a.pooled_user = pooled_out;
+  a.stream = stream;
+  char* tail = (char*)acts + a.al.total;
+  a.d_hptrs = (const float**)tail;
+  a.d_offs = (int64_t*)(tail + 8 * sizeof(void*));
+  GCCB_LAUNCH(gin_fill_tables_kernel, 1, 32, 0, stream, (char*)acts, a.al, a.lay, a.d.L, a.d_hptrs, a.d_offs,
+              bn_train ? num_batches_tracked : (int64_t*)nullptr);
+  switch (a.d.H) {
+    case 32: return run_forward<32>(a);
+    case 64: return run_forward<64>(a);
+    case 128: return run_forward<128>(a);
+    default: return run_forward<256>(a);
+  }
+}

@@ -1,0 +1,389 @@
+// moco.cu -- contrastive head: MoCo queue logits, InfoNCE loss (separate and fused), enqueue,
+// and the E2E (in-batch negatives) head.
+//
+// Replaces (reference file:line):
+//   MemoryMoCo.forward logits [q.k | q.queue^T]/T           gcc/contrastive/memory_moco.py:33-44
+//   FIFO enqueue via index_copy_                            gcc/contrastive/memory_moco.py:55-61
+//   NCESoftmaxLoss / NCESoftmaxLossNS (CrossEntropy)        gcc/contrastive/criterions.py:12-17,27-33
+//   E2E logits feat_k @ feat_q^T / T                        train.py:397-401
+// The reference materialises the B x (K+1) logits (16 MiB at K=16384), clones the 4 MiB queue
+// every step (:36) and syncs the host (:30).  The fused kernel streams the queue once,
+// keeps an online softmax per row (running max / sum / sum_j p_j key_j, the attention
+// recurrence with V = K) and never writes logits; the unfused entry points exist so the
+// reference's module API (MemoryMoCo.forward returning `out`) stays drop-in.
+#include "common.cuh"
+
+namespace gccb {
+
+#define GCCB_NCE_RB 8          // query rows per CTA
+
+// out[i][0] = q_i.k_i/T ; out[i][1+j] = q_i.mem_j/T.   grid = (ceil(K/256), ceil(B/RB)), block 256
+__global__ void __launch_bounds__(256)
+moco_logits_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                   const float* __restrict__ mem, int B, int d, int K, float invT,
+                   float* __restrict__ out) {
+  GCCB_DYN_SMEM(float, qs);               // [RB][d]
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.y * GCCB_NCE_RB;
+  for (int idx = tid; idx < GCCB_NCE_RB * d; idx += 256) {
+    int i = i0 + idx / d;
+    qs[idx] = i < B ? q[(size_t)i * d + idx % d] : 0.f;
+  }
+  __syncthreads();
+  const int j = blockIdx.x * 256 + tid;
+  float acc[GCCB_NCE_RB];
+#pragma unroll
+  for (int r = 0; r < GCCB_NCE_RB; ++r) acc[r] = 0.f;
+  if (j < K) {
+    const float* mj = mem + (size_t)j * d;
+    for (int c = 0; c < d; ++c) {
+      const float m = mj[c];
+#pragma unroll
+      for (int r = 0; r < GCCB_NCE_RB; ++r) acc[r] = fmaf(qs[r * d + c], m, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < GCCB_NCE_RB; ++r)
+      if (i0 + r < B) out[(size_t)(i0 + r) * (K + 1) + 1 + j] = acc[r] * invT;
+  }
+  if (blockIdx.x == 0 && tid < GCCB_NCE_RB && i0 + tid < B) {      // positive logit
+    const int i = i0 + tid;
+    float s = 0.f;
+    for (int c = 0; c < d; ++c) s = fmaf(qs[tid * d + c], k[(size_t)i * d + c], s);
+    out[(size_t)i * (K + 1)] = s * invT;
+  }
+}
+
+// dq_i = (1/T) (dout[i][0] k_i + sum_j dout[i][1+j] mem_j).   grid = B, block 256
+__global__ void __launch_bounds__(256)
+moco_logits_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ k,
+                       const float* __restrict__ mem, int B, int d, int K, float invT,
+                       float* __restrict__ dq) {
+  GCCB_DYN_SMEM(float, part);             // [groups][d]
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const int groups = 256 / d > 0 ? 256 / d : 1;
+  const int c = tid % d, gidx = tid / d;
+  const float* drow = dout + (size_t)i * (K + 1);
+  float s = 0.f;
+  if (gidx < groups)
+    for (int j = gidx; j < K; j += groups) s = fmaf(drow[1 + j], mem[(size_t)j * d + c], s);
+  if (gidx < groups) part[gidx * d + c] = s;
+  __syncthreads();
+  for (int cc = tid; cc < d; cc += 256) {
+    float t = drow[0] * k[(size_t)i * d + cc];
+    for (int gi = 0; gi < groups; ++gi) t += part[gi * d + cc];
+    dq[(size_t)i * d + cc] = t * invT;
+  }
+}
+
+// Cross entropy of out[B][C] against label 0 (mode 0) or i (mode 1); optional dout.
+// grid = B, block 256.  loss accumulated with one atomic per row (caller zeroes).
+__global__ void __launch_bounds__(256)
+nce_loss_kernel(const float* __restrict__ out, int B, int C, int label_mode,
+                float* __restrict__ loss, float* __restrict__ dout) {
+  __shared__ float red_s[8];
+  __shared__ float bc[2];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const float* row = out + (size_t)i * C;
+  float mx = -3.0e38f;
+  for (int j = tid; j < C; j += 256) mx = fmaxf(mx, row[j]);
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) red_s[tid >> 5] = mx;
+  __syncthreads();
+  if (tid == 0) { float m = red_s[0]; for (int w = 1; w < 8; ++w) m = fmaxf(m, red_s[w]); bc[0] = m; }
+  __syncthreads();
+  mx = bc[0];
+  float s = 0.f;
+  for (int j = tid; j < C; j += 256) s += expf(row[j] - mx);
+  s = warp_sum(s);
+  __syncthreads();
+  if ((tid & 31) == 0) red_s[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red_s[w]; bc[1] = t; }
+  __syncthreads();
+  const float sum = bc[1];
+  const int label = label_mode == 0 ? 0 : i;
+  if (tid == 0) atomicAdd(loss, (logf(sum) + mx - row[label]) / (float)B);
+  if (dout) {
+    float* drow = dout + (size_t)i * C;
+    const float invB = 1.0f / (float)B;
+    for (int j = tid; j < C; j += 256) {
+      float p = expf(row[j] - mx) / sum;
+      drow[j] = (p - (j == label ? 1.0f : 0.f)) * invB;
+    }
+  }
+}
+
+// ---- fused InfoNCE -------------------------------------------------------------------------
+// partial record per (chunk, row): m, s, acc[d]  ->  stride d + 2 floats
+// grid = (nchunks, ceil(B/RB)), block 256; dyn smem: qs[RB][d] | ms[CK][d+1] | ps[RB][CK]
+__global__ void __launch_bounds__(256)
+infonce_partial_kernel(const float* __restrict__ q, const float* __restrict__ mem, int B, int d,
+                       int K, int CK, float invT, float* __restrict__ part) {
+  GCCB_DYN_SMEM(float, smem);
+  float* qs = smem;
+  float* ms = qs + GCCB_NCE_RB * d;
+  float* ps = ms + (size_t)CK * (d + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.y * GCCB_NCE_RB, j0 = blockIdx.x * CK;
+  const int nk = min(CK, K - j0);
+  for (int idx = tid; idx < GCCB_NCE_RB * d; idx += 256) {
+    int i = i0 + idx / d;
+    qs[idx] = i < B ? q[(size_t)i * d + idx % d] : 0.f;
+  }
+  for (int idx = tid; idx < CK * d; idx += 256) {
+    int j = idx / d, c = idx - j * d;
+    ms[j * (d + 1) + c] = j < nk ? mem[(size_t)(j0 + j) * d + c] : 0.f;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < GCCB_NCE_RB * CK; idx += 256) {
+    int r = idx / CK, j = idx - r * CK;
+    float s = 0.f;
+    for (int c = 0; c < d; ++c) s = fmaf(qs[r * d + c], ms[j * (d + 1) + c], s);
+    ps[idx] = j < nk ? s * invT : -3.0e38f;
+  }
+  __syncthreads();
+  // warp r owns row r: chunk max and sum of exp
+  {
+    const int r = warp;                                   // 8 warps == RB rows
+    float mx = -3.0e38f;
+    for (int j = lane; j < CK; j += 32) mx = fmaxf(mx, ps[r * CK + j]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int j = lane; j < CK; j += 32) {
+      float p = j < nk ? expf(ps[r * CK + j] - mx) : 0.f;
+      ps[r * CK + j] = p;
+      s += p;
+    }
+    s = warp_sum(s);
+    if (lane == 0 && i0 + r < B) {
+      float* rec = part + ((size_t)blockIdx.x * B + i0 + r) * (d + 2);
+      rec[0] = mx;
+      rec[1] = s;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < GCCB_NCE_RB * d; idx += 256) {
+    int r = idx / d, c = idx - r * d;
+    if (i0 + r >= B) continue;
+    float a = 0.f;
+    for (int j = 0; j < nk; ++j) a = fmaf(ps[r * CK + j], ms[j * (d + 1) + c], a);
+    part[((size_t)blockIdx.x * B + i0 + r) * (d + 2) + 2 + c] = a;
+  }
+}
+
+// merge partials with the positive logit; loss_i, dq_i; stats[0] += loss_i/B, stats[1] += l_pos/B
+// grid = B, block 128 (threads over d)
+__global__ void __launch_bounds__(128)
+infonce_merge_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                     const float* __restrict__ part, int B, int d, int nchunks, float invT,
+                     float* __restrict__ stats, float* __restrict__ dq) {
+  __shared__ float red_s[4];
+  __shared__ float bc[3];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  float s = 0.f;
+  for (int c = tid; c < d; c += 128) s = fmaf(q[(size_t)i * d + c], k[(size_t)i * d + c], s);
+  s = warp_sum(s);
+  if ((tid & 31) == 0) red_s[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    const float lpos = (red_s[0] + red_s[1] + red_s[2] + red_s[3]) * invT;
+    float M = lpos;
+    for (int ch = 0; ch < nchunks; ++ch) M = fmaxf(M, part[((size_t)ch * B + i) * (d + 2)]);
+    float S = expf(lpos - M);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const float* rec = part + ((size_t)ch * B + i) * (d + 2);
+      S += rec[1] * expf(rec[0] - M);
+    }
+    bc[0] = M; bc[1] = S; bc[2] = lpos;
+    atomicAdd(&stats[0], (logf(S) + M - lpos) / (float)B);
+    atomicAdd(&stats[1], lpos / (float)B);
+  }
+  __syncthreads();
+  const float M = bc[0], S = bc[1], lpos = bc[2];
+  const float scale = invT / (float)B;
+  for (int c = tid; c < d; c += 128) {
+    float a = (expf(lpos - M) / S - 1.0f) * k[(size_t)i * d + c];
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const float* rec = part + ((size_t)ch * B + i) * (d + 2);
+      a = fmaf(expf(rec[0] - M) / S, rec[2 + c], a);
+    }
+    dq[(size_t)i * d + c] = a * scale;
+  }
+}
+
+__global__ void moco_enqueue_kernel(float* __restrict__ mem, const float* __restrict__ k, int B, int d,
+                                    int K, const int64_t* __restrict__ index_dev) {
+  const int64_t base = *index_dev;
+  const int total = B * d;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int i = idx / d, c = idx - i * d;
+    int64_t row = (base + i) % K;                       // torch.fmod(arange(B) + index, K)
+    mem[(size_t)row * d + c] = k[idx];
+  }
+}
+__global__ void moco_advance_kernel(int64_t* index_dev, int B, int K) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *index_dev = (*index_dev + B) % K;
+}
+
+// ---- E2E head: out[i][j] = k_i . q_j / T, label i ------------------------------------------
+// pass 1 (grid B, block 256): logits row, softmax, dout row into workspace, loss / prob stats
+__global__ void __launch_bounds__(256)
+e2e_rows_kernel(const float* __restrict__ q, const float* __restrict__ k, int B, int d, float invT,
+                float* __restrict__ stats, float* __restrict__ dout) {
+  GCCB_DYN_SMEM(float, smem);            // ks[d] | row[B]
+  __shared__ float red_s[8];
+  __shared__ float bc[2];
+  float* ks = smem;
+  float* row = smem + d;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < d; c += 256) ks[c] = k[(size_t)i * d + c];
+  __syncthreads();
+  float mx = -3.0e38f;
+  for (int j = tid; j < B; j += 256) {
+    float s = 0.f;
+    for (int c = 0; c < d; ++c) s = fmaf(ks[c], q[(size_t)j * d + c], s);
+    s *= invT;
+    row[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) red_s[tid >> 5] = mx;
+  __syncthreads();
+  if (tid == 0) { float m = red_s[0]; for (int w = 1; w < 8; ++w) m = fmaxf(m, red_s[w]); bc[0] = m; }
+  __syncthreads();
+  mx = bc[0];
+  float s = 0.f;
+  for (int j = tid; j < B; j += 256) s += expf(row[j] - mx);
+  s = warp_sum(s);
+  __syncthreads();
+  if ((tid & 31) == 0) red_s[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red_s[w];
+    bc[1] = t;
+    atomicAdd(&stats[0], (logf(t) + mx - row[i]) / (float)B);
+    atomicAdd(&stats[1], row[i] / (float)B);
+  }
+  __syncthreads();
+  const float sum = bc[1], invB = 1.0f / (float)B;
+  for (int j = tid; j < B; j += 256)
+    dout[(size_t)i * B + j] = (expf(row[j] - mx) / sum - (j == i ? 1.0f : 0.f)) * invB;
+}
+// pass 2 (grid (B, 2), block 128): y=0: dk_i = invT sum_j dout[i][j] q_j ; y=1: dq_j = invT sum_i dout[i][j] k_i
+__global__ void __launch_bounds__(128)
+e2e_grads_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ dout,
+                 int B, int d, float invT, float* __restrict__ dq, float* __restrict__ dk) {
+  const int x = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < d; c += 128) {
+    float a = 0.f;
+    if (blockIdx.y == 0) {
+      for (int j = 0; j < B; ++j) a = fmaf(dout[(size_t)x * B + j], q[(size_t)j * d + c], a);
+      dk[(size_t)x * d + c] = a * invT;
+    } else {
+      for (int i = 0; i < B; ++i) a = fmaf(dout[(size_t)i * B + x], k[(size_t)i * d + c], a);
+      dq[(size_t)x * d + c] = a * invT;
+    }
+  }
+}
+
+static int infonce_ck(int d) { int ck = 16384 / d; return ck < 32 ? 32 : (ck > 256 ? 256 : ck); }
+
+}  // namespace gccb
+
+using namespace gccb;
+
+static int bad_head_args(const char* who, const void* a, const void* b, int B, int d, int K) {
+  if (!a || !b || B <= 0 || d <= 0 || d > 256 || K <= 0) {
+    set_last_error("%s: bad argument (need 0 < d <= 256)", who);
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" int gccb_moco_logits(const float* q, const float* k, const float* memory, int32_t B,
+                                int32_t d, int32_t K, float T, float* out, gccb_stream_t stream) {
+  if (bad_head_args("gccb_moco_logits", q, k, B, d, K) || !memory || !out) return GCCB_ERR_BADARG;
+  dim3 grid((K + 255) / 256, (B + GCCB_NCE_RB - 1) / GCCB_NCE_RB);
+  GCCB_LAUNCH(moco_logits_kernel, grid, 256, (size_t)GCCB_NCE_RB * d * 4, stream, q, k, memory, B, d, K,
+              1.0f / T, out);
+  return check_launch("gccb_moco_logits");
+}
+
+extern "C" int gccb_moco_logits_backward(const float* dout, const float* k, const float* memory,
+                                         int32_t B, int32_t d, int32_t K, float T, float* dq,
+                                         gccb_stream_t stream) {
+  if (bad_head_args("gccb_moco_logits_backward", dout, k, B, d, K) || !memory || !dq) return GCCB_ERR_BADARG;
+  GCCB_LAUNCH(moco_logits_bwd_kernel, B, 256, (size_t)256 * 4 + (size_t)d * 4, stream, dout, k, memory, B, d, K,
+              1.0f / T, dq);
+  return check_launch("gccb_moco_logits_backward");
+}
+
+extern "C" int gccb_nce_loss(const float* out, int32_t B, int32_t C, int32_t label_mode, float* loss,
+                             float* dout, gccb_stream_t stream) {
+  if (!out || !loss || B <= 0 || C <= 0 || (label_mode == 1 && C < B)) {
+    set_last_error("gccb_nce_loss: bad argument");
+    return GCCB_ERR_BADARG;
+  }
+  cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream);
+  GCCB_LAUNCH(nce_loss_kernel, B, 256, 0, stream, out, B, C, label_mode, loss, dout);
+  return check_launch("gccb_nce_loss");
+}
+
+extern "C" size_t gccb_infonce_workspace(int32_t B, int32_t d, int32_t K) {
+  int ck = infonce_ck(d);
+  size_t nch = (size_t)(K + ck - 1) / ck;
+  return nch * (size_t)B * (d + 2) * sizeof(float);
+}
+
+extern "C" int gccb_infonce_fused(const float* q, const float* k, const float* memory, int32_t B,
+                                  int32_t d, int32_t K, float T, float* stats, float* dq, void* workspace,
+                                  size_t workspace_bytes, gccb_stream_t stream) {
+  if (bad_head_args("gccb_infonce_fused", q, k, B, d, K) || !memory || !stats || !dq || !workspace)
+    return GCCB_ERR_BADARG;
+  if (workspace_bytes < gccb_infonce_workspace(B, d, K)) {
+    set_last_error("gccb_infonce_fused: workspace too small");
+    return GCCB_ERR_CAPACITY;
+  }
+  const int ck = infonce_ck(d);
+  const int nch = (K + ck - 1) / ck;
+  const size_t smem = ((size_t)GCCB_NCE_RB * d + (size_t)ck * (d + 1) + (size_t)GCCB_NCE_RB * ck) * 4;
+  auto kp = infonce_partial_kernel;
+  cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaMemsetAsync(stats, 0, 2 * sizeof(float), (cudaStream_t)stream);
+  dim3 grid(nch, (B + GCCB_NCE_RB - 1) / GCCB_NCE_RB);
+  GCCB_LAUNCH(kp, grid, 256, smem, stream, q, memory, B, d, K, ck, 1.0f / T, (float*)workspace);
+  GCCB_LAUNCH(infonce_merge_kernel, B, 128, 0, stream, q, k, (const float*)workspace, B, d, nch, 1.0f / T,
+              stats, dq);
+  return check_launch("gccb_infonce_fused");
+}
+
+extern "C" int gccb_moco_enqueue(float* memory, const float* k, int32_t B, int32_t d, int32_t K,
+                                 int64_t* index_dev, gccb_stream_t stream) {
+  if (!memory || !k || !index_dev || B <= 0 || d <= 0 || K <= 0) {
+    set_last_error("gccb_moco_enqueue: bad argument");
+    return GCCB_ERR_BADARG;
+  }
+  GCCB_LAUNCH(moco_enqueue_kernel, (B * d + 255) / 256, 256, 0, stream, memory, k, B, d, K,
+              (const int64_t*)index_dev);
+  GCCB_LAUNCH(moco_advance_kernel, 1, 32, 0, stream, index_dev, B, K);
+  return check_launch("gccb_moco_enqueue");
+}
+
+extern "C" int gccb_e2e_nce(const float* q, const float* k, int32_t B, int32_t d, float T, float* stats,
+                            float* dq, float* dk, void* workspace, size_t workspace_bytes,
+                            gccb_stream_t stream) {
+  if (bad_head_args("gccb_e2e_nce", q, k, B, d, 1) || !stats || !dq || !dk || !workspace) return GCCB_ERR_BADARG;
+  if (workspace_bytes < (size_t)B * B * sizeof(float)) {
+    set_last_error("gccb_e2e_nce: workspace needs B*B floats");
+    return GCCB_ERR_CAPACITY;
+  }
+  cudaMemsetAsync(stats, 0, 2 * sizeof(float), (cudaStream_t)stream);
+  const size_t smem = ((size_t)d + B) * 4;
+  auto k1 = e2e_rows_kernel;
+  cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  GCCB_LAUNCH(k1, B, 256, smem, stream, q, k, B, d, 1.0f / T, stats, (float*)workspace);
+  dim3 grid(B, 2);
+  GCCB_LAUNCH(e2e_grads_kernel, grid, 128, 0, stream, q, k, (const float*)workspace, B, d, 1.0f / T, dq, dk);
+  return check_launch("gccb_e2e_nce");
+}

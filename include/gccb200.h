@@ -160,10 +160,12 @@ int gccb_gin_forward(const gccb_gin_cfg_t* cfg, const gccb_batch_t* batch, int32
                      size_t acts_bytes, float* feat, float* pooled_out, gccb_stream_t stream);
 
 /* backward of ONE view (loss.backward(), train.py:408): grads += d loss / d params
- * (flat, same layout; caller zeroes before the first view).                             */
+ * (flat, same layout; caller zeroes before the first view).  The dropout arguments must
+ * repeat the forward's.                                                                 */
 size_t gccb_gin_backward_workspace(const gccb_gin_cfg_t* cfg, int32_t batch, int32_t node_cap);
 int gccb_gin_backward(const gccb_gin_cfg_t* cfg, const gccb_batch_t* batch, int32_t view,
                       const float* params, const void* acts, const float* dfeat, float* grads,
+                      uint64_t dropout_key, uint64_t dropout_step, int32_t dropout_layer_base,
                       void* workspace, size_t workspace_bytes, gccb_stream_t stream);
 
 /* ---- contrastive head ------------------------------------------------------------------ */
@@ -191,7 +193,8 @@ int gccb_moco_enqueue(float* memory, const float* k, int32_t B, int32_t d, int32
 /* E2E head (train.py:397-401, criterions.py:27-33): out = k q^T / T, CE vs arange;
  * returns loss, mean diagonal logit, dq and dk.                                          */
 int gccb_e2e_nce(const float* q, const float* k, int32_t B, int32_t d, float T, float* stats,
-                 float* dq, float* dk, gccb_stream_t stream);
+                 float* dq, float* dk, void* workspace /* B*B floats */, size_t workspace_bytes,
+                 gccb_stream_t stream);
 
 /* ---- optimiser ------------------------------------------------------------------------- */
 /* clip_grad_norm_ (train.py:340-347,409) + Adam with L2 weight decay (train.py:417,667-672)

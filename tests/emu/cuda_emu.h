@@ -97,8 +97,8 @@ struct Ctx {
 inline Ctx& C() { static Ctx c; return c; }
 }  // namespace emu
 
-static uint3 threadIdx, blockIdx;
-static dim3 blockDim, gridDim;
+inline uint3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
 static const int warpSize = 32;
 
 namespace emu {
