@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- subgraphs/sec of the MoCo pretraining step (BASELINE.json metric) on N x B200.
+
+  python bench.py --gpus 1 --steps 50 --warmup 5                  (N>1: launched by torchrun)
+  python bench.py --impl reference ...                            (CPU oracle arm, host cores)
+
+Workload (config.workload): BASELINE.json configs[1] = "C2": MoCo K=16384 m=0.999, 5-layer GIN
+hid=64, rw_hops=256 restart=0.8, batch 256 (per GPU: weak scaling, configs[2] at N>1), synthetic
+power-law Chung-Lu graph 1M nodes / 20M edges (CSR ~168 MB > the 126 MB L2, sampled at random).
+One step = sample -> induce -> positional features -> GIN q/k -> InfoNCE -> backward -> clip/Adam
+-> EMA -> enqueue = 2*B ego-subgraphs.  `value` has inputs resident in HBM; `e2e` drives the same
+step with host-side seeds (pinned -> H2D) and a loss read-back (D2H) inside the timed region.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "subgraphs/sec (MoCo pretrain step)"
+CONFIGS = {
+    # name: nodes, pairs, batch, K, layers, hidden, rw_hops
+    "c2": dict(nodes=1_000_000, pairs=20_000_000, batch=256, K=16384, layers=5, hidden=64, rw_hops=256),
+    "small": dict(nodes=50_000, pairs=500_000, batch=64, K=1024, layers=5, hidden=64, rw_hops=64),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def workload_name(cfg, n_gpus):
+    return ("MoCo K=%d m=0.999 T=0.07, %d-layer GIN hid=%d, rw_hops=%d restart=0.8, batch %d%s, "
+            "Chung-Lu power-law %d nodes / %d edges" % (
+                cfg["K"], cfg["layers"], cfg["hidden"], cfg["rw_hops"], cfg["batch"],
+                " per GPU" if n_gpus > 1 else "", cfg["nodes"], cfg["pairs"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (pynvml in a thread) -- the recipe's clocks line
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C walk/induce, the reference's own scipy eigsh call, torch-CPU model)
+def _cpu_worker(args):
+    """One DataLoader-worker-like task: sample + induce + positional features for a slice of the
+    batch (OMP/MKL threads = 1, like the reference's workers)."""
+    (indptr, indices, key, sample_ids, seeds, btable, rt, cap_n, cap_m, rng_seed) = args
+    import numpy as np
+    from oracle import posenc as opos
+    from oracle import rwr as orwr
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    t0 = time.perf_counter()
+    subs = orwr.rwr_batch(indptr, indices, key, sample_ids, seeds, btable, rt, cap_n, cap_m)
+    t1 = time.perf_counter()
+    rng = np.random.RandomState(rng_seed)
+    pos = [opos.posenc_reference_call(s["indptr"], s["indices"], s["n"], 32, rng=rng) for s in subs]
+    t2 = time.perf_counter()
+    return subs, pos, t1 - t0, t2 - t1
+
+
+_G = {}
+
+
+def _cpu_worker_shared(task):
+    a = _G["graph"]
+    return _cpu_worker((a[0], a[1]) + task)
+
+
+def cpu_arm(cfg, graph_np, steps, seconds_budget, cores=None):
+    """Times `steps` (or as many as fit in seconds_budget) full CPU steps.  Returns dict."""
+    import multiprocessing as mp
+    import numpy as np
+    import torch
+    from oracle import rwr as orwr
+    from oracle import step as ostep
+    from gcc_b200.models import layout as glayout
+    from oracle import model as om
+    cores = cores or os.cpu_count() or 1
+    indptr, indices = graph_np
+    B, L, H, K = cfg["batch"], cfg["layers"], cfg["hidden"], cfg["K"]
+    cdf = orwr.seed_cdf(indptr)
+    btable = orwr.budget_table(int(np.diff(indptr).max()), cfg["rw_hops"], 0.8)
+    rt = orwr.restart_threshold(0.8)
+    cap_n = int(btable.max()) + 65
+    _G["graph"] = (indptr, indices)
+    torch.manual_seed(0)
+    shapes = om.param_shapes(num_layers=L, hidden=H)
+    params = {}
+    for k, shp in shapes.items():
+        if k.endswith("running_var") or (k.endswith("weight") and len(shp) == 1):
+            params[k] = torch.ones(shp)
+        elif k.endswith("num_batches_tracked"):
+            params[k] = torch.zeros(shp, dtype=torch.long)
+        elif len(shp) == 2:
+            params[k] = torch.randn(shp) / math.sqrt(shp[1])
+        else:
+            params[k] = torch.zeros(shp)
+    state = dict(params=params, ema={k: v.clone() for k, v in params.items()},
+                 memory=torch.rand(K, H) * 0.4 - 0.2, index=0, adam_m={}, adam_v={}, adam_t=0)
+    ctx = mp.get_context("fork")
+    split = {"walk_induce": 0.0, "eigsh": 0.0, "collate": 0.0, "model": 0.0}
+    done, t_start = 0, time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        for st in range(steps):
+            sids = np.arange(st * B, (st + 1) * B, dtype=np.int64)
+            seeds = orwr.draw_seeds(cdf, 0, sids)
+            chunks = np.array_split(np.arange(B), cores)
+            tasks = [(0, sids[c], seeds[c], btable, rt, cap_n, 1 << 16, 1000 * st + i)
+                     for i, c in enumerate(chunks) if len(c)]
+            res = pool.map(_cpu_worker_shared, tasks)
+            split["walk_induce"] += max(r[2] for r in res)
+            split["eigsh"] += max(r[3] for r in res)
+            t0 = time.perf_counter()
+            views = [[], []]
+            posv = [[], []]
+            for subs, pos, _, _ in res:
+                for j, (s, p) in enumerate(zip(subs, pos)):
+                    views[j & 1].append(s)
+                    posv[j & 1].append(p)
+            batches = []
+            for v in (0, 1):
+                noff = np.concatenate([[0], np.cumsum([s["n"] for s in views[v]])])
+                eoff = np.concatenate([[0], np.cumsum([s["m"] for s in views[v]])])
+                ip = np.concatenate([eoff[i] + s["indptr"][:-1] for i, s in enumerate(views[v])] + [[eoff[-1]]])
+                ix = np.concatenate([noff[i] + s["indices"] for i, s in enumerate(views[v])])
+                seed = np.zeros(noff[-1], np.int64)
+                seed[noff[:-1]] = 1
+                batches.append(dict(indptr=ip, indices=ix, pos=np.concatenate(posv[v]), seed=seed,
+                                    sub_deg=np.concatenate([np.diff(s["indptr"]) for s in views[v]]),
+                                    node_off=noff))
+            t1 = time.perf_counter()
+            ostep.train_step(state, batches[0], batches[1], num_layers=L, moco=True, T=0.07, lr=0.005,
+                             dropout_key=1, step_index=st)
+            t2 = time.perf_counter()
+            split["collate"] += t1 - t0
+            split["model"] += t2 - t1
+            done += 1
+            if seconds_budget and time.perf_counter() - t_start > seconds_budget:
+                break
+    dt = time.perf_counter() - t_start
+    return dict(value=2 * B * done / dt, unit="subgraphs/sec", cores=cores, kind="port",
+                sample="%d full steps of %d pairs (C oracle walk+induce, the reference's scipy eigsh "
+                       "call, torch-CPU encoder/loss/Adam); DGL itself is absent" % (done, B),
+                steps=done, seconds=dt, ms_per_step=1e3 * dt / max(done, 1),
+                split_seconds={k: round(v, 3) for k, v in split.items()})
+
+
+# ------------------------------------------------------------------------------------------------
+def make_graph_device(cfg, device):
+    from gcc_b200.datasets import synthetic
+    return synthetic.chung_lu_device(cfg["nodes"], cfg["pairs"], 0.5, seed=0, device=device)
+
+
+def run_reference(args, cfg):
+    """--impl reference: the CPU path (oracle port; the reference's DGL path cannot run, DGL is
+    absent) on the host cores, same workload / metric.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from gcc_b200.datasets import synthetic
+    if torch.cuda.is_available():
+        g = make_graph_device(cfg, "cuda")
+        graph_np = (g.indptr.cpu().numpy(), g.indices.cpu().numpy())
+    else:
+        g = synthetic.chung_lu(cfg["nodes"], cfg["pairs"], 0.5, seed=0)
+        graph_np = (g.indptr, g.indices)
+    cpu_arm(cfg, graph_np, args.warmup, 0)                              # warm-up steps
+    r = cpu_arm(cfg, graph_np, args.steps, 240.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "subgraphs/sec",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, 1), "config": args.config},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "split_seconds")},
+            "e2e": {"value": r["value"], "unit": "subgraphs/sec", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args, cfg):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gcc_b200 import _lib
+    from gcc_b200.contrastive.memory_moco import MemoryMoCo
+    from gcc_b200.datasets.graph_dataset import LoadBalanceGraphDataset
+    from gcc_b200.engine import PretrainEngine
+    from gcc_b200.models import GraphEncoder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, L, H, K = cfg["batch"], cfg["layers"], cfg["hidden"], cfg["K"]
+    torch.manual_seed(0)
+    g = make_graph_device(cfg, dev)
+    ds = LoadBalanceGraphDataset(rw_hops=cfg["rw_hops"], restart_prob=0.8, positional_embedding_size=32,
+                                 dgl_graphs_file=g, num_samples=2000, num_workers=12, num_copies=6,
+                                 batch_size=B, seed=0, device=dev)
+
+    def mk():
+        return GraphEncoder(positional_embedding_size=32, max_node_freq=16, max_edge_freq=16, max_degree=512,
+                            freq_embedding_size=16, degree_embedding_size=16, output_dim=H, node_hidden_dim=H,
+                            edge_hidden_dim=H, num_layers=L, num_step_set2set=6, num_layer_set2set=3,
+                            norm=True, gnn_model="gin", degree_input=True)
+
+    model, ema = mk(), mk()
+    ema.load_state_dict(model.state_dict())                 # moment_update(model, model_ema, 0), train.py:623-624
+    model, ema = model.to(dev), ema.to(dev)
+    contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
+    eng = PretrainEngine(ds, model, ema, contrast, moco=True, rank=rank, world_size=world)
+    lib = _lib.get()
+    total_steps = 75000                                     # train.py defaults: 100 epochs x 750
+
+    def lr_at(step):
+        from gcc_b200.utils.misc import warmup_linear
+        return 0.005 * warmup_linear(step / total_steps, 0.1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        eng.step(lr=lr_at(eng.global_step))
+    barrier()
+    ds.buffers.check_flags()
+    # ---- timed region: K steps, inputs resident in HBM, no host sync inside -------------------
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    samp_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+                torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    cnt_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+    launches0 = lib.gccb_launch_count()
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        # same step as eng.step(), with events around the sampler and the eigensolver
+        samp_ev[i][0].record()
+        first = (eng.global_step * world + rank) * B
+        ds.sample_batch(first_sample=first, posenc=False)
+        samp_ev[i][1].record()
+        cnt_acc += ds.buffers.counters.double().sum(0)      # algorithmic-byte counters (device side)
+        _posenc(ds)
+        samp_ev[i][2].record()
+        _rest_of_step(eng, lr_at(eng.global_step))
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    launches = lib.gccb_launch_count() - launches0
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = 2.0 * B * world * args.steps / (ms_max / 1e3)
+    ds.buffers.check_flags()
+    stats = eng.read_stats()
+    samp_ms = sum(a.elapsed_time(b) for a, b, _ in samp_ev) / args.steps
+    eig_ms = sum(b.elapsed_time(c) for _, b, c in samp_ev) / args.steps
+    n_sum, m_sum, t_sum, deg_sum = [float(x) / args.steps for x in cnt_acc.tolist()]
+    # per view bytes = T*(8+4) + sum_{v in subv}(8 + 4 deg v) + 4*(2n + 1 + m)
+    alg_bytes = t_sum * 12 + (8 * n_sum + 4 * deg_sum) + 4 * (2 * n_sum + 2 * B + m_sum)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (samp_ms / 1e3) / 1e9
+    roofline = {"kernel": "sampler: rwr_walk_unique + batch_offsets + induce_fill (per step, 3 launches)",
+                "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_step": alg_bytes, "ms_per_launch_group": samp_ms,
+                "note": "latency-bound at 512 ego-nets/step (12 MB of traffic); see DESIGN.md"}
+    phases = {"sampler_ms": samp_ms, "eigensolver_ms": eig_ms,
+              "encoder_head_optim_ms": ms / args.steps - samp_ms - eig_ms}
+
+    # ---- e2e: host seeds (pinned) -> H2D each step, loss D2H each step ---------------------------
+    cdf_host = ds.graph.cdf.cpu().numpy()
+    rs = np.random.RandomState(1 + rank)
+    n_e2e = max(args.steps // 2, 5)
+    host_seeds = torch.from_numpy(np.searchsorted(cdf_host, rs.random_sample((n_e2e + 2, B)), side="right")
+                                  .clip(max=len(cdf_host) - 1).astype(np.int64)).pin_memory()
+    seeds_dev = torch.zeros(B, dtype=torch.int64, device=dev)
+    loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+    for i in range(2):
+        seeds_dev.copy_(host_seeds[i], non_blocking=True)
+        eng.step(lr=lr_at(eng.global_step), seeds=seeds_dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_e2e):
+        seeds_dev.copy_(host_seeds[2 + i], non_blocking=True)
+        eng.step(lr=lr_at(eng.global_step), seeds=seeds_dev)
+        loss_host.copy_(eng.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()           # the reference's .item() per step (train.py:420-422)
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = 2.0 * B * world * n_e2e / (float(t2.item()) / 1e3)
+
+    line = {"metric": METRIC, "value": value, "unit": "subgraphs/sec", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(cfg, world), "config": args.config,
+                       "global_batch_pairs": B * world, "subgraphs_per_step": 2 * B * world,
+                       "parallelism": "dp%d (CSR replicated, seeds sharded, one all-gather/step)" % world,
+                       "l2": "inputs larger than L2: %.0f MB CSR sampled at random; no explicit flush" % (
+                           ds.graph.nbytes / 1e6),
+                       "graph_nodes": ds.graph.num_nodes, "graph_nnz": int(ds.graph.indices.numel()),
+                       "max_degree": ds.graph.max_degree, "max_walk_budget": ds.graph.max_budget,
+                       "avg_nodes_per_egonet": n_sum / (2 * B), "avg_edges_per_egonet": m_sum / (2 * B)},
+            "pairs_per_sec": value / 2.0,
+            "e2e": {"value": e2e_value, "unit": "subgraphs/sec", "h2d_bytes_per_step": B * 8,
+                    "d2h_bytes_per_step": 16, "steps": n_e2e,
+                    "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step -> stats D2H + sync"},
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "clocks": clk, "roofline": roofline, "phases_ms": phases,
+            "loss": stats["loss"], "grad_norm": stats["grad_norm"]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        graph_np = (g.indptr.cpu().numpy(), g.indices.cpu().numpy())
+        cb = cpu_arm(cfg, graph_np, 10000, args.cpu_seconds)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "split_seconds")}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _posenc(ds):
+    import ctypes as C
+    from gcc_b200 import _lib
+    buf = ds.buffers
+    _lib.check(_lib.get().gccb_posenc(C.byref(buf.c), buf.pos_dim, 1, _lib.dptr(buf.pos), _lib.dptr(buf.eigvals),
+                                      _lib.dptr(buf.ws_posenc), buf.ws_posenc.numel(), _lib.stream_ptr()),
+               "gccb_posenc")
+
+
+def _rest_of_step(eng, lr):
+    """PretrainEngine.step() minus sampling/posenc (already issued with events around them)."""
+    eng.step(lr=lr, _presampled=True)
+
+
+def main():
+    args = parse()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,6 +5,9 @@
 #include "common.cuh"
 
 namespace gccb {
+#ifndef GCCB_EMU
+unsigned long long g_launch_count = 0;   // kernels enqueued by this library (bench.py: gpu_launches)
+#endif
 static thread_local char g_err[512] = "";
 
 void set_last_error(const char* fmt, ...) {
@@ -25,6 +28,14 @@ int check_launch(const char* what) {
 }  // namespace gccb
 
 extern "C" int gccb_version(void) { return GCCB_VERSION; }
+
+extern "C" unsigned long long gccb_launch_count(void) {
+#ifndef GCCB_EMU
+  return gccb::g_launch_count;
+#else
+  return 0;
+#endif
+}
 
 extern "C" const char* gccb_last_error(void) { return gccb::g_err; }
 

@@ -11,8 +11,9 @@
 #define GCCB_DYN_SMEM(type, name)                                   \
   extern __shared__ __align__(16) unsigned char name##_raw_smem[];  \
   type* name = reinterpret_cast<type*>(name##_raw_smem)
+namespace gccb { extern unsigned long long g_launch_count; }
 #define GCCB_LAUNCH(kern, grid, block, smem, stream, ...) \
-  kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+  (++gccb::g_launch_count, kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__))
 #endif
 
 #include "../../include/gccb200.h"

@@ -113,3 +113,40 @@ def disjoint_union(graphs, name="union"):
         eoff += int(g.indptr[-1])
     return CSRGraph(np.concatenate(indptrs), np.concatenate(indices).astype(np.int32),
                     off, name)
+
+
+def chung_lu_device(n=1_000_000, n_pairs=20_000_000, exponent=0.5, seed=0, device="cuda"):
+    """C2-size Chung-Lu graph generated ON the GPU with torch (setup, not the timed path): the
+    same construction as chung_lu()/from_pairs() -- sample endpoints ~ w, drop self loops,
+    symmetrise, de-duplicate, drop zero-degree vertices -- with tensors left on the device.
+    (torch's CUDA RNG stream differs from numpy's, so the edge set differs from chung_lu(seed).)"""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    w = (torch.arange(n, device=device, dtype=torch.float64) + 1.0) ** (-exponent)
+    cdf = torch.cumsum(w, 0)
+    cdf = cdf / cdf[-1]
+    keys = []
+    left, chunk = n_pairs, 1 << 24
+    while left > 0:
+        c = min(left, chunk)
+        src = torch.searchsorted(cdf, torch.rand(c, generator=gen, device=device, dtype=torch.float64), right=True).clamp_(max=n - 1)
+        dst = torch.searchsorted(cdf, torch.rand(c, generator=gen, device=device, dtype=torch.float64), right=True).clamp_(max=n - 1)
+        keep = src != dst
+        src, dst = src[keep], dst[keep]
+        keys.append(src * n + dst)
+        keys.append(dst * n + src)
+        left -= c
+    key = torch.unique(torch.cat(keys), sorted=True)
+    del keys
+    s, d = key // n, key % n
+    deg = torch.bincount(s, minlength=n)
+    alive = deg > 0
+    n2 = int(alive.sum())
+    if n2 != n:
+        remap = torch.cumsum(alive.long(), 0) - 1
+        d = remap[d]
+        deg = deg[alive]
+    indptr = torch.zeros(n2 + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=indptr[1:])
+    return CSRGraph(indptr, d.to(torch.int32), n2, "chunglu_dev_n%d_p%d" % (n, n_pairs))

@@ -1,0 +1,156 @@
+"""PretrainEngine: one MoCo / E2E pretraining step (train.py:378-434 + the DataLoader work that
+feeds it) as a fixed sequence of libgccb200 kernel launches with no host synchronisation:
+
+  draw seeds -> RWR walk / induce / batch -> positional features           (datasets/)
+  -> GIN forward q (model) and k (model_ema, BN in train mode, train.py:357-365)
+  -> fused InfoNCE (loss, dq; logits never materialised)                     (memory_moco.py, criterions.py)
+  -> GIN backward -> [all-gather of keys+grads when world > 1]
+  -> clip + Adam + momentum update on flat buffers (train.py:409-417,430-431)
+  -> FIFO enqueue of the keys (memory_moco.py:55-61)
+
+The module-level API (GraphEncoder.forward + autograd, MemoryMoCo.forward, NCESoftmaxLoss) runs
+the same kernels piecewise and stays drop-in for the reference's train_moco; this engine is what
+train.py / bench.py drive.  Scalars the reference reads with .item() every step (train.py:420-422)
+live in a device stats buffer read on demand.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from .datasets.data_util import BatchedSubgraphs
+
+
+class PretrainEngine:
+    def __init__(self, dataset, model, model_ema, contrast, moco=True, learning_rate=0.005,
+                 betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, clip_norm=1.0, alpha=0.999,
+                 nce_t=0.07, rank=0, world_size=1, process_group=None):
+        _lib.require_device()
+        self.lib = _lib.get()
+        self.ds, self.model, self.model_ema, self.contrast = dataset, model, model_ema, contrast
+        self.moco, self.lr0, self.betas, self.eps = moco, learning_rate, betas, eps
+        self.wd, self.clip, self.alpha, self.T = weight_decay, clip_norm, alpha, nce_t
+        self.rank, self.world, self.pg = rank, world_size, process_group
+        dev = model.flat_params.device
+        self.dev = dev
+        B, H, L = dataset.batch_size, model.cfg.hidden, model.cfg.num_layers
+        self.B, self.H, self.L = B, H, L
+        f32 = dict(dtype=torch.float32, device=dev)
+        n_live = model.n_live
+        self.grads = torch.zeros(n_live, **f32)
+        self.adam_m = torch.zeros(n_live, **f32)
+        self.adam_v = torch.zeros(n_live, **f32)
+        self.adam_t = 0
+        self.hyper = torch.zeros(4, **f32)
+        self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.stats = torch.zeros(4, **f32)            # loss, prob, grad_norm(pre-clip), unused
+        self.norm_ws = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.feat_q = torch.zeros(B, H, **f32)
+        self.feat_k = torch.zeros(B, H, **f32)
+        self.dq = torch.zeros(B, H, **f32)
+        self.dk = torch.zeros(B, H, **f32)
+        self.pooled = torch.zeros(max(L - 1, 1), B, H, **f32)
+        cap = dataset.node_cap
+        acts_bytes = self.lib.gccb_gin_acts_bytes(C.byref(model.cfg), B, cap)
+        self.acts_q = torch.empty(acts_bytes, dtype=torch.uint8, device=dev)
+        self.acts_k = torch.empty(acts_bytes, dtype=torch.uint8, device=dev)
+        self.bwd_ws = torch.empty(self.lib.gccb_gin_backward_workspace(C.byref(model.cfg), B, cap),
+                                  dtype=torch.uint8, device=dev)
+        K = contrast.queueSize
+        self.K = K
+        self.nce_ws = torch.empty(max(self.lib.gccb_infonce_workspace(B, H, K), B * B * 4, 8),
+                                  dtype=torch.uint8, device=dev)
+        self.index_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.index_dev.fill_(contrast.index)
+        self.global_step = 0
+        if world_size > 1:
+            self.payload = B * H + n_live + 4
+            self.send = torch.zeros(self.payload, **f32)
+            self.gathered = torch.zeros(world_size, self.payload, **f32)
+            if moco and K % (world_size * B) != 0:
+                raise ValueError("queue size must be a multiple of world_size*batch (identical queues)")
+        self.launches_per_step = None
+
+    # -------------------------------------------------------------------------------------------
+    def _hyper(self, lr):
+        self.adam_t += 1
+        b1, b2 = self.betas
+        self.hyper_host[0] = lr
+        self.hyper_host[1] = 1.0 - b1 ** self.adam_t
+        self.hyper_host[2] = math.sqrt(1.0 - b2 ** self.adam_t)
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+
+    def step(self, lr=None, seeds=None, _presampled=False):
+        """One optimisation step.  `seeds`: optional int64 CUDA tensor [B] (else drawn on device
+        from the Philox stream).  Returns nothing; read_stats() syncs."""
+        lib, st = self.lib, _lib.stream_ptr()
+        ds, model, ema = self.ds, self.model, self.model_ema
+        B, H, L = self.B, self.H, self.L
+        lr = self.lr0 if lr is None else lr
+        first = (self.global_step * self.world + self.rank) * B
+        buf = ds.buffers if _presampled else ds.sample_batch(first_sample=first, seeds=seeds)
+        gq, gk = BatchedSubgraphs(buf, 0), BatchedSubgraphs(buf, 1)
+        step = self.global_step
+        _, _, saved_q = model._run_forward(gq, True, drop_step=step, drop_base=0, acts=self.acts_q,
+                                           feat=self.feat_q, pooled=self.pooled, bn_train=True)
+        self.grads.zero_()
+        if self.moco:
+            ema._run_forward(gk, False, drop_step=0, drop_base=-1, acts=self.acts_k, feat=self.feat_k,
+                             pooled=self.pooled, bn_train=True)
+            _lib.check(lib.gccb_infonce_fused(_lib.dptr(self.feat_q), _lib.dptr(self.feat_k),
+                                              _lib.dptr(self.contrast.memory), B, H, self.K, self.T,
+                                              _lib.dptr(self.stats), _lib.dptr(self.dq),
+                                              _lib.dptr(self.nce_ws), self.nce_ws.numel(), st),
+                       "gccb_infonce_fused")
+            model._run_backward(gq, saved_q, self.dq, grads_flat=self.grads, ws=self.bwd_ws)
+        else:
+            _, _, saved_k = model._run_forward(gk, True, drop_step=step, drop_base=L, acts=self.acts_k,
+                                               feat=self.feat_k, pooled=self.pooled, bn_train=True)
+            _lib.check(lib.gccb_e2e_nce(_lib.dptr(self.feat_q), _lib.dptr(self.feat_k), B, H, self.T,
+                                        _lib.dptr(self.stats), _lib.dptr(self.dq), _lib.dptr(self.dk),
+                                        _lib.dptr(self.nce_ws), self.nce_ws.numel(), st), "gccb_e2e_nce")
+            model._run_backward(gq, saved_q, self.dq, grads_flat=self.grads, ws=self.bwd_ws)
+            model._run_backward(gk, saved_k, self.dk, grads_flat=self.grads, ws=self.bwd_ws)
+        grads, scale = self.grads, 1.0
+        if self.world > 1:
+            # the ONE collective of the step: keys + gradients + stats, then a fixed-rank-order sum
+            n_live = model.n_live
+            self.send[:B * H].copy_(self.feat_k.reshape(-1))
+            self.send[B * H:B * H + n_live].copy_(self.grads)
+            self.send[B * H + n_live:].copy_(self.stats)
+            torch.distributed.all_gather_into_tensor(self.gathered.reshape(-1), self.send, group=self.pg)
+            _lib.check(lib.gccb_sum_ranks(C.c_void_p(self.gathered.data_ptr() + 4 * B * H), self.world,
+                                          self.payload, n_live, _lib.dptr(self.grads), st), "gccb_sum_ranks")
+            scale = 1.0 / self.world
+        self._hyper(lr)
+        _lib.check(lib.gccb_clip_adam_ema(_lib.dptr(model.flat_params), _lib.dptr(grads),
+                                          _lib.dptr(self.adam_m), _lib.dptr(self.adam_v),
+                                          _lib.dptr(ema.flat_params) if self.moco else None,
+                                          model.n_live, model._n_all, _lib.dptr(self.hyper), self.betas[0],
+                                          self.betas[1], self.eps, self.wd, self.clip,
+                                          self.alpha if self.moco else -1.0, scale,
+                                          C.c_void_p(self.stats.data_ptr() + 8), _lib.dptr(self.norm_ws), st),
+                   "gccb_clip_adam_ema")
+        if self.moco:
+            if self.world > 1:
+                for r in range(self.world):     # rank order -> identical queues on every rank
+                    _lib.check(lib.gccb_moco_enqueue(_lib.dptr(self.contrast.memory),
+                                                     C.c_void_p(self.gathered.data_ptr() + 4 * r * self.payload),
+                                                     B, H, self.K, _lib.dptr(self.index_dev), st),
+                               "gccb_moco_enqueue")
+            else:
+                _lib.check(lib.gccb_moco_enqueue(_lib.dptr(self.contrast.memory), _lib.dptr(self.feat_k),
+                                                 B, H, self.K, _lib.dptr(self.index_dev), st),
+                           "gccb_moco_enqueue")
+            self.contrast.index = (self.contrast.index + B * self.world) % self.K
+        self.global_step += 1
+
+    def read_stats(self):
+        """Host sync: loss, prob (mean positive logit), pre-clip grad norm, batch sizes, flags."""
+        buf = self.ds.buffers
+        buf.check_flags()
+        s = self.stats.tolist()
+        sizes = buf.node_off[:, self.B].tolist() + buf.edge_off[:, self.B].tolist()
+        return dict(loss=s[0], prob=s[1], grad_norm=s[2], nodes_q=sizes[0], nodes_k=sizes[1],
+                    edges_q=sizes[2], edges_k=sizes[3])

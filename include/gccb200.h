@@ -48,6 +48,8 @@ int gccb_version(void);
 /* compute capability (major*10+minor) of the current device, or a negative status */
 int gccb_arch(void);
 const char* gccb_last_error(void);
+/* number of kernels this library has enqueued so far in this process (host counter) */
+unsigned long long gccb_launch_count(void);
 
 /* ---- parent graph + sampler constants (host struct, device pointers inside) -------- */
 typedef struct {
@@ -120,7 +122,7 @@ int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t normalize, f
 /* ---- GIN encoder ----------------------------------------------------------------------
  * Replaces GraphEncoder.forward / UnsupervisedGIN.forward (graph_encoder.py:132-200,
  * gin.py:213-232) incl. DGL GINConv('sum', eps buffer = 0) and SumPooling.
- * Parameters live in ONE flat fp32 buffer; gccb_gin_param_offsets() gives the layout
+ * Parameters live in ONE flat fp32 buffer; gccb_gin_param_layout gives the layout
  * (the Python module maps the reference's state_dict keys onto slices of it).          */
 typedef struct {
   int32_t num_layers;  /* L (GIN layers = L-1, prediction heads = L)  train.py:79 */
