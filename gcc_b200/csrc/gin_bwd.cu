@@ -13,7 +13,7 @@
 
 namespace gccb {
 
-#define GCCB_WG_CHUNKS 32     // row chunks of the weight-gradient split-K
+#define GCCB_WG_CHUNKS 256    // row chunks of the weight-gradient split-K (>= one wave of CTAs)
 
 struct BwdLayout {            // byte offsets in the backward workspace
   size_t dh, g1, dz2, da, red, dS, dpool, part, total;

@@ -7,38 +7,55 @@
 // k <= 0 -> zeros.  The reference runs ARPACK (scipy eigsh, float64, random v0)
 // per ego-net on a CPU worker: ~2.8 ms each, the dominant cost of its pipeline.
 //
-// Method (B200): one CTA per ego-net, the dense matrix G = L + 2I (SPD, spectrum
-// in [1,3]) lives in shared memory, column-major.  One-sided (Hestenes) Jacobi
-// orthogonalises the columns of G with plane rotations applied on the right;
-// because G is symmetric positive definite the converged columns are
-// lambda_j' * v_j, so eigenvectors are the normalised columns and no separate
-// V matrix is stored (n <= 232 fits in 227 KB).  A warp owns one column pair per
-// step of a round-robin tournament (n/2 disjoint pairs per round), dot products
-// by shuffle reduction, rotations in registers.  Degenerate spectra (ego-nets are
-// star-like) are handled exactly: Jacobi returns an orthonormal basis of every
-// eigenspace.  Ego-nets are binned by size into three launches (shared memory
-// 17 KB / 66 KB / 218 KB) through device-built work lists.
+// Two device solvers, one CTA per ego-net, chosen by size through device-built work lists:
+//
+//  (1) n <= 64: dense one-sided (Hestenes) Jacobi.  G = L + 2I (SPD, spectrum in [1,3]) lives in
+//      shared memory, column-major; plane rotations applied on the right orthogonalise its
+//      columns; because G is symmetric positive definite the converged columns are
+//      lambda_j' v_j, so the eigenvectors are the normalised columns and no V matrix is stored.
+//      A warp owns one column pair per step of a round-robin tournament; dot products by
+//      shuffle reduction, rotations in registers.
+//
+//  (2) n > 64: Chebyshev-filtered subspace iteration (ChFSI) on a block of 48 vectors, any n.
+//      Ego-nets are star-like: their spectra have one huge degenerate cluster, so a degree-4/8
+//      Chebyshev filter on [-1, cut] followed by Rayleigh-Ritz converges in ~3 outer iterations
+//      (measured on the C2 workload).  Per iteration: 8 sparse products with the sub-CSR (fused
+//      three-term recurrence), CGS2 re-orthonormalisation, H = Q^T L Q, the 48x48 Ritz problem
+//      solved by solver (1) in shared memory, X = Q W, residual check.  The n x 48 blocks live in
+//      an L2-resident workspace (2 blocks per ego-net), so shared memory does not bound n and
+//      8 CTAs fit per SM.  Cost is O(n * 48^2) instead of the O(n^3) of a dense solve.
+//
+// Both return an orthonormal basis of every eigenspace (degenerate clusters included), Ritz
+// values as Rayleigh quotients, a deterministic sign (largest-|.| component positive) and are
+// deterministic run to run (no floating-point atomics on the results).
 #include "common.cuh"
 
 namespace gccb {
 
-#define GCCB_EIG_NMAX 232
+#define GCCB_EIG_SMALL 64          // largest n solved by the dense Jacobi kernel
 #define GCCB_EIG_MAXSWEEP 14
 #define GCCB_EIG_TOL 1.0e-6f
+#define GCCB_CF_B 48               // ChFSI block size (>= pos_dim 32 + guard vectors)
+#define GCCB_CF_DEG0 4              // Chebyshev degree of the first outer iteration (random block:
+                                   // keep it numerically full rank for fp32 Gram-Schmidt)
+#define GCCB_CF_DEG 8              // degree of the later iterations (gain T_8(3) ~ 7e5 < 1/eps_fp32)
+#define GCCB_CF_NSM 160            // blocks of ego-nets up to this size live in shared memory
+#define GCCB_CF_MAXIT 16
+#define GCCB_CF_TOL 4.0e-5f        // max residual ||L x - theta x|| over the wanted pairs
+#define GCCB_CF_STAG 1.5e-4f       // accepted when the residual stagnates below this (fp32 floor)
+#define GCCB_CF_HEAVY 32           // rows with more neighbours are processed warp-cooperatively
+#define GCCB_CF_MAXHEAVY 128
 
-// class 0: n <= 64, class 1: n <= 128, class 2: n <= NMAX, class 3: larger (unsupported)
-__device__ __forceinline__ int eig_class(int n) {
-  return n <= 64 ? 0 : n <= 128 ? 1 : n <= GCCB_EIG_NMAX ? 2 : 3;
-}
+// class 0: n <= 64 (dense Jacobi), class 1: ChFSI with shared-memory blocks, class 2: ChFSI, L2 blocks
+__device__ __forceinline__ int eig_class(int n) { return n <= GCCB_EIG_SMALL ? 0 : n <= GCCB_CF_NSM ? 1 : 2; }
 
 // Work lists: worklist[c][i] = slot.  One CTA, deterministic order.  grid = 1, block = 256.
 __global__ void __launch_bounds__(256)
 posenc_classify_kernel(const int64_t* __restrict__ counters, const int32_t* __restrict__ node_off,
-                       int B, int32_t* __restrict__ worklist, int32_t* __restrict__ counts,
-                       int32_t* __restrict__ flags) {
+                       int B, int32_t* __restrict__ worklist, int32_t* __restrict__ counts) {
   __shared__ int scan_scratch[33];
   const int tid = threadIdx.x;
-  int base[4] = {0, 0, 0, 0};
+  int base[3] = {0, 0, 0};
   for (int s0 = 0; s0 < 2 * B; s0 += 256) {
     int slot = s0 + tid;
     int cls = -1;
@@ -47,85 +64,24 @@ posenc_classify_kernel(const int64_t* __restrict__ counters, const int32_t* __re
       if (node_off[view * (B + 1) + B] >= 0) cls = eig_class((int)counters[(size_t)slot * 4]);
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 3; ++c) {
       int tot;
       int ex = block_scan_excl(cls == c ? 1 : 0, scan_scratch, &tot);
       if (cls == c) worklist[(size_t)c * 2 * B + base[c] + ex] = slot;
       base[c] += tot;
     }
   }
-  if (tid < 4) counts[tid] = base[tid];
-  if (tid == 0 && base[3] > 0) atomicOr(flags, (int)GCCB_FLAG_EIG_TOOBIG);
+  if (tid == 0) { counts[0] = base[0]; counts[1] = base[1]; counts[2] = base[2]; }
 }
 
-// zero rows of ego-nets the eigensolver cannot take (class 3) so no garbage reaches the encoder
-__global__ void posenc_zero_big_kernel(const int32_t* __restrict__ worklist,
-                                       const int32_t* __restrict__ counts, int B, int node_cap,
-                                       const int32_t* __restrict__ node_off, int pos_dim,
-                                       float* __restrict__ pos, float* __restrict__ eigvals) {
-  if ((int)blockIdx.x >= counts[3]) return;
-  const int slot = worklist[(size_t)3 * 2 * B + blockIdx.x];
-  const int view = slot / B, g = slot - view * B;
-  const int noff = node_off[view * (B + 1) + g], n = node_off[view * (B + 1) + g + 1] - noff;
-  float* out = pos + ((size_t)view * node_cap + noff) * pos_dim;
-  for (int i = threadIdx.x; i < n * pos_dim; i += blockDim.x) out[i] = 0.f;
-  if (eigvals)
-    for (int i = threadIdx.x; i < pos_dim; i += blockDim.x) eigvals[(size_t)slot * pos_dim + i] = 0.f;
-}
-
-// One-sided Jacobi eigensolver + feature write.  NR = ceil(nmax / 32) rows per lane.
+// ------------------------------------------------------------------------------------------------
+// One-sided Jacobi on the n x n column-major matrix G (leading dimension ld) in shared memory:
+// orthogonalises the columns in place; on return nrm[j] = ||g_j||.  Returns the number of
+// sweeps used (== GCCB_EIG_MAXSWEEP means not converged).  NR = ceil(nmax/32) rows per lane.
 template <int NR, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts,
-                     int cls, int B, int node_cap, int edge_cap,
-                     const int32_t* __restrict__ node_off, const int32_t* __restrict__ b_indptr,
-                     const int32_t* __restrict__ b_indices, const int32_t* __restrict__ sub_deg,
-                     int pos_dim, int normalize, float* __restrict__ pos,
-                     float* __restrict__ eigvals, int32_t* __restrict__ flags) {
-  GCCB_DYN_SMEM(float, smem);
-  __shared__ int sel[32];
-  __shared__ float sgn[32];
-  if ((int)blockIdx.x >= counts[cls]) return;
-  const int slot = worklist[(size_t)cls * 2 * B + blockIdx.x];
-  const int view = slot / B, g = slot - view * B;
-  const int noff = node_off[view * (B + 1) + g];
-  const int n = node_off[view * (B + 1) + g + 1] - noff;
+__device__ __forceinline__ int jacobi_onesided(float* G, float* nrm, int n, int ld) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = THREADS / 32;
-  const int k = min(n - 2, pos_dim);
-  float* out = pos + ((size_t)view * node_cap + noff) * pos_dim;
-  if (k <= 0) {                                        // data_util.py:243-244
-    for (int i = tid; i < n * pos_dim; i += THREADS) out[i] = 0.f;
-    if (eigvals)
-      for (int i = tid; i < pos_dim; i += THREADS) eigvals[(size_t)slot * pos_dim + i] = 0.f;
-    return;
-  }
-  const int ld = n;
-  float* G = smem;                 // [n][ld] column-major: G[col * ld + row]
-  float* nrm = G + (size_t)n * ld; // [n] squared column norms
-  float* dinv = nrm + n;           // [n] D^-1/2
-  const int32_t* v_indptr = b_indptr + (size_t)view * (node_cap + 1);
-  const int32_t* v_indices = b_indices + (size_t)view * edge_cap;
-  const int32_t* v_deg = sub_deg + (size_t)view * node_cap;
-
-  for (int i = tid; i < n * ld; i += THREADS) G[i] = 0.f;
-  for (int i = tid; i < n; i += THREADS) {
-    int d = v_deg[noff + i];
-    dinv[i] = 1.0f / sqrtf((float)(d < 1 ? 1 : d));   // in_degrees().clip(1) ** -0.5
-  }
-  __syncthreads();
-  for (int i = warp; i < n; i += NW) {                 // row i <- its in-neighbours j
-    const int beg = v_indptr[noff + i], end = v_indptr[noff + i + 1];
-    const float di = dinv[i];
-    for (int e = beg + lane; e < end; e += 32) {
-      int j = v_indices[e] - noff;
-      atomicAdd(&G[(size_t)j * ld + i], di * dinv[j]);
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < n; i += THREADS) G[(size_t)i * ld + i] += 2.0f;
-  __syncthreads();
-
   const int m = n + (n & 1);                            // tournament size (even)
   int sweep = 0;
   for (; sweep < GCCB_EIG_MAXSWEEP; ++sweep) {
@@ -183,11 +139,7 @@ posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __rest
     }
     if (!__syncthreads_or(rotated)) break;
   }
-  if (sweep == GCCB_EIG_MAXSWEEP && tid == 0) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
-
-  // eigenvalue of column j = ||g_j|| - 2; rank columns, keep the k largest, ascending
-  float* mu = nrm;                                      // reuse: mu[j] = ||g_j||
-  for (int p = warp; p < n; p += NW) {
+  for (int p = warp; p < n; p += NW) {                  // final norms: nrm[j] = ||g_j||
     float s = 0.f;
 #pragma unroll
     for (int jj = 0; jj < NR; ++jj) {
@@ -196,67 +148,118 @@ posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __rest
       s = fmaf(x, x, s);
     }
     s = warp_sum(s);
-    if (lane == 0) mu[p] = sqrtf(s);
+    if (lane == 0) nrm[p] = sqrtf(s);
   }
   __syncthreads();
-  for (int j = tid; j < n; j += THREADS) {
-    const float mj = mu[j];
-    int rank = 0;
-    for (int i = 0; i < n; ++i) {
-      float mi = mu[i];
-      rank += (mi > mj) || (mi == mj && i < j);
+  return sweep;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Cyclic two-sided Jacobi for a small symmetric matrix in shared memory (m <= 64): A (m x m,
+// column-major, leading dimension LD, odd LD -> conflict-free) is diagonalised, V accumulates the
+// eigenvectors (columns).  Round-robin ordering: the m/2 disjoint rotations of a round are each
+// derived by ONE thread from three scalars (no dot products, no shuffles), then the whole block
+// applies them -- columns of A and V, then rows of A.  A must have a positive diagonal (callers
+// pass L + 2I or H + 2I): the skip test is relative to sqrt(a_pp a_qq).  Returns sweeps used.
+template <int THREADS, class T>
+__device__ __forceinline__ int jacobi_twosided(T* A, T* V, T* cs /*[64]*/, int* pq /*[32]*/, int m, int LD) {
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < m * m; idx += THREADS) {
+    const int j = idx / m, i = idx - j * m;
+    V[j * LD + i] = i == j ? (T)1 : (T)0;
+  }
+  const int mm = m + (m & 1), half = mm >> 1;
+  __syncthreads();
+  int sweep = 0;
+  for (; sweep < GCCB_EIG_MAXSWEEP; ++sweep) {
+    int rotated = 0;
+    for (int r = 0; r < mm - 1; ++r) {
+      if (tid < half) {
+        int p, q;
+        if (tid == 0) { p = mm - 1; q = r; }
+        else { p = (r + tid) % (mm - 1); q = (r + mm - 1 - tid) % (mm - 1); }
+        if (p > q) { int t = p; p = q; q = t; }
+        T c = (T)1, s = (T)0;
+        if (q < m) {
+          const T app = A[p * LD + p], aqq = A[q * LD + q], apq = A[q * LD + p];
+          const T tol = sizeof(T) == 8 ? (T)1e-14 : (T)2.0e-7;
+          if (fabs(apq) > tol * sqrt(fabs(app * aqq))) {
+            const T zeta = (aqq - app) / ((T)2 * apq);
+            const T t = (zeta >= (T)0 ? (T)1 : (T)-1) / (fabs(zeta) + sqrt((T)1 + zeta * zeta));
+            c = (T)1 / sqrt((T)1 + t * t);
+            s = c * t;
+            rotated = 1;
+          }
+        } else {
+          p = q = -1;                                  // bye
+        }
+        cs[2 * tid] = c; cs[2 * tid + 1] = s; pq[tid] = (p & 0xffff) | (q << 16);
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J      (item = pair, row)
+      for (int item = tid; item < half * m; item += THREADS) {
+        const int pr = item / m, i = item - pr * m;
+        const int code = pq[pr];
+        const int q = code >> 16;
+        if (q < 0) continue;
+        const int p = code & 0xffff;
+        const T c = cs[2 * pr], s = cs[2 * pr + 1];
+        if (s == (T)0) continue;
+        T x = A[p * LD + i], y = A[q * LD + i];
+        A[p * LD + i] = c * x - s * y;
+        A[q * LD + i] = s * x + c * y;
+        x = V[p * LD + i]; y = V[q * LD + i];
+        V[p * LD + i] = c * x - s * y;
+        V[q * LD + i] = s * x + c * y;
+      }
+      __syncthreads();
+      // rows: A <- J^T A                 (item = pair, column)
+      for (int item = tid; item < half * m; item += THREADS) {
+        const int pr = item / m, j = item - pr * m;
+        const int code = pq[pr];
+        const int q = code >> 16;
+        if (q < 0) continue;
+        const int p = code & 0xffff;
+        const T c = cs[2 * pr], s = cs[2 * pr + 1];
+        if (s == (T)0) continue;
+        const T x = A[j * LD + p], y = A[j * LD + q];
+        A[j * LD + p] = c * x - s * y;
+        A[j * LD + q] = s * x + c * y;
+      }
+      __syncthreads();
     }
-    if (rank < k) sel[k - 1 - rank] = j;                // ascending: slot k-1 = largest
+    if (!__syncthreads_or(rotated)) break;
   }
-  __syncthreads();
+  return sweep;
+}
+
+// Shared epilogue: write pos rows from k unit eigenvectors.
+//   vec(c, r): component r of the eigenvector for output column c (ascending eigenvalue order)
+template <class VecFn>
+__device__ __forceinline__ void write_features(int n, int k, int pos_dim, int normalize, float* sgn /*[32] smem*/,
+                                               float* __restrict__ out, VecFn vec) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
   // deterministic sign: the largest-|.| component (lowest row on ties) is positive
   for (int c = warp; c < k; c += NW) {
-    const float* col = G + (size_t)sel[c] * ld;
-    float best = -1.f; int brow = 0x7fffffff;
+    float best = -1.f, bval = 0.f; int brow = 0x7fffffff;
     for (int r = lane; r < n; r += 32) {
-      float a = fabsf(col[r]);
-      if (a > best) { best = a; brow = r; }
+      float x = vec(c, r), a = fabsf(x);
+      if (a > best) { best = a; brow = r; bval = x; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       float ob = __shfl_xor_sync(0xffffffffu, best, o);
       int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-      if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+      float ov = __shfl_xor_sync(0xffffffffu, bval, o);
+      if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; bval = ov; }
     }
-    if (lane == 0) sgn[c] = col[brow] < 0.f ? -1.0f : 1.0f;
+    if (lane == 0) sgn[c] = bval < 0.f ? -1.0f : 1.0f;
   }
   __syncthreads();
-  if (eigvals) {
-    // eigenvalues as Rayleigh quotients v^T L v against the ORIGINAL sparse matrix: the
-    // column norms carry the accumulated rounding of ~n rotations per sweep (~1e-5), the
-    // Rayleigh quotient is second-order accurate in the eigenvector error.
-    for (int c = warp; c < pos_dim; c += NW) {
-      float acc = 0.f;
-      if (c < k) {
-        const float* col = G + (size_t)sel[c] * ld;
-        for (int i = lane; i < n; i += 32) {
-          const int beg = v_indptr[noff + i], end = v_indptr[noff + i + 1];
-          float rowacc = 0.f;
-          for (int e = beg; e < end; ++e) {
-            int j = v_indices[e] - noff;
-            rowacc = fmaf(dinv[j], col[j], rowacc);
-          }
-          acc = fmaf(col[i] * dinv[i], rowacc, acc);
-        }
-        acc = warp_sum(acc);
-        const float m2 = mu[sel[c]];
-        acc = acc / (m2 * m2);
-      }
-      if (lane == 0) eigvals[(size_t)slot * pos_dim + c] = acc;
-    }
-  }
-  // rows: lane c holds component c of node r (pos_dim <= 32)
-  for (int r = warp; r < n; r += NW) {
+  for (int r = warp; r < n; r += NW) {                  // lane c holds component c of node r
     float u = 0.f;
-    if (lane < k) {
-      const int j = sel[lane];
-      u = sgn[lane] * G[(size_t)j * ld + r] / mu[j];
-    }
+    if (lane < k) u = sgn[lane] * vec(lane, r);
     if (normalize) {                                    // sklearn normalize(norm="l2")
       float ss = warp_sum(u * u);
       if (ss > 0.f) u = u / sqrtf(ss);
@@ -265,16 +268,419 @@ posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __rest
   }
 }
 
-static size_t eig_smem_bytes(int nmax) { return ((size_t)nmax * nmax + 2 * (size_t)nmax) * sizeof(float); }
+// ---- solver (1): dense two-sided Jacobi, n <= 64 ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts,
+                     int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
+                     const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
+                     const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
+                     float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags) {
+  // float64 like the reference's eigsh call (data_util.py:245): with close eigenvalues (paths,
+  // rings) an fp32 rotation sequence loses eigenVECTOR accuracy as eps * rotations / gap
+  constexpr int LD = GCCB_EIG_SMALL + 1;
+  GCCB_DYN_SMEM(double, dsm);
+  double* G = dsm;                          // [64][65]
+  double* V = dsm + GCCB_EIG_SMALL * LD;    // [64][65]
+  __shared__ float dinv[GCCB_EIG_SMALL];
+  __shared__ double cs[64];
+  __shared__ int pq[32];
+  __shared__ int sel[32];
+  __shared__ float sgn[32];
+  if ((int)blockIdx.x >= counts[0]) return;
+  const int slot = worklist[blockIdx.x];
+  const int view = slot / B, g = slot - view * B;
+  const int noff = node_off[view * (B + 1) + g];
+  const int n = node_off[view * (B + 1) + g + 1] - noff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = min(n - 2, pos_dim);
+  float* out = pos + ((size_t)view * node_cap + noff) * pos_dim;
+  if (k <= 0) {                                        // data_util.py:243-244
+    for (int i = tid; i < n * pos_dim; i += 256) out[i] = 0.f;
+    if (eigvals)
+      for (int i = tid; i < pos_dim; i += 256) eigvals[(size_t)slot * pos_dim + i] = 0.f;
+    return;
+  }
+  const int32_t* v_indptr = b_indptr + (size_t)view * (node_cap + 1);
+  const int32_t* v_indices = b_indices + (size_t)view * edge_cap;
+  const int32_t* v_deg = sub_deg + (size_t)view * node_cap;
+  for (int i = tid; i < n * LD; i += 256) G[i] = 0.0;
+  for (int i = tid; i < n; i += 256) {
+    int d = v_deg[noff + i];
+    dinv[i] = 1.0f / sqrtf((float)(d < 1 ? 1 : d));   // in_degrees().clip(1) ** -0.5
+  }
+  __syncthreads();
+  for (int i = warp; i < n; i += 8) {                  // row i <- its in-neighbours j
+    const int beg = v_indptr[noff + i], end = v_indptr[noff + i + 1];
+    const float di = dinv[i];
+    for (int e = beg + lane; e < end; e += 32) {
+      int j = v_indices[e] - noff;
+      atomicAdd(&G[j * LD + i], (double)(di * dinv[j]));   // same fp32 weights as the ChFSI path
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) G[i * LD + i] += 2.0;            // G = L + 2I, positive diagonal
+  __syncthreads();
+  const int sweeps = jacobi_twosided<256, double>(G, V, cs, pq, n, LD);
+  if (sweeps == GCCB_EIG_MAXSWEEP && tid == 0) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
+  // eigenvalue j = G[j][j] - 2; rank, keep the k largest, ascending
+  for (int j = tid; j < n; j += 256) {
+    const double mj = G[j * LD + j];
+    int rank = 0;
+    for (int i = 0; i < n; ++i) {
+      double mi = G[i * LD + i];
+      rank += (mi > mj) || (mi == mj && i < j);
+    }
+    if (rank < k) sel[k - 1 - rank] = j;                // ascending: slot k-1 = largest
+  }
+  __syncthreads();
+  if (eigvals) {
+    // eigenvalues as Rayleigh quotients v^T L v against the ORIGINAL sparse matrix (the rotated
+    // diagonal carries the accumulated rounding of all rotations, ~1e-6..1e-5)
+    for (int c = warp; c < pos_dim; c += 8) {
+      float acc = 0.f;
+      if (c < k) {
+        const double* col = V + sel[c] * LD;
+        for (int i = lane; i < n; i += 32) {
+          const int beg = v_indptr[noff + i], end = v_indptr[noff + i + 1];
+          float rowacc = 0.f;
+          for (int e = beg; e < end; ++e) {
+            int j = v_indices[e] - noff;
+            rowacc = fmaf(dinv[j], (float)col[j], rowacc);
+          }
+          acc = fmaf((float)col[i] * dinv[i], rowacc, acc);
+        }
+        acc = warp_sum(acc);
+      }
+      if (lane == 0) eigvals[(size_t)slot * pos_dim + c] = acc;
+    }
+  }
+  const double* Vc = V;
+  const int* selc = sel;
+  write_features(n, k, pos_dim, normalize, sgn, out, [&](int c, int r) { return (float)Vc[selc[c] * LD + r]; });
+}
+
+// ---- solver (2): Chebyshev-filtered subspace iteration, any n > 64 -------------------------------
+struct SubCsr {
+  const int32_t* indptr;   // view-local, index with noff + r
+  const int32_t* indices;
+  const float* dinv;       // [n] for this ego-net
+  int noff, n;
+};
+
+// dst[c][r] = alpha * (sum_{j in N(r)} w_rj src[c][j] - cen * src[c][r]) - beta * dst[c][r]
+// (beta == 0: dst is write-only).  Blocks are column-major n x 48.  Rows with more than
+// `thresh` neighbours are listed in heavy[] and processed by whole warps.
+__device__ __forceinline__ void spmm_cheb(const SubCsr& S, const float* __restrict__ src, float* __restrict__ dst,
+                                          float alpha, float cen, float beta, const int* heavy, int nheavy,
+                                          int thresh) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+  const int n = S.n;
+  constexpr int CG = 8;                                  // columns per work item
+  const int items = n * (GCCB_CF_B / CG);
+  for (int it = tid; it < items; it += blockDim.x) {
+    const int r = it % n, c0 = (it / n) * CG;
+    const int beg = S.indptr[S.noff + r], end = S.indptr[S.noff + r + 1];
+    if (end - beg > thresh) continue;                    // heavy row: handled below
+    float acc[CG];
+#pragma unroll
+    for (int cc = 0; cc < CG; ++cc) acc[cc] = 0.f;
+    const float dr = S.dinv[r];
+    for (int e = beg; e < end; ++e) {
+      const int j = S.indices[e] - S.noff;
+      const float w = dr * S.dinv[j];
+#pragma unroll
+      for (int cc = 0; cc < CG; ++cc) acc[cc] = fmaf(w, src[(size_t)(c0 + cc) * n + j], acc[cc]);
+    }
+#pragma unroll
+    for (int cc = 0; cc < CG; ++cc) {
+      const size_t o = (size_t)(c0 + cc) * n + r;
+      float v = alpha * (acc[cc] - cen * src[o]);
+      if (beta != 0.f) v -= beta * dst[o];
+      dst[o] = v;
+    }
+  }
+  for (int h = 0; h < nheavy; ++h) {
+    const int r = heavy[h];
+    const int beg = S.indptr[S.noff + r], end = S.indptr[S.noff + r + 1];
+    const float dr = S.dinv[r];
+    // two columns per pass: independent accumulators hide the gather latency
+    for (int c = warp * 2; c < GCCB_CF_B; c += NW * 2) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int e = beg + lane; e < end; e += 32) {
+        const int j = S.indices[e] - S.noff;
+        const float w = dr * S.dinv[j];
+        a0 = fmaf(w, src[(size_t)c * n + j], a0);
+        a1 = fmaf(w, src[(size_t)(c + 1) * n + j], a1);
+      }
+      a0 = warp_sum(a0);
+      a1 = warp_sum(a1);
+      if (lane < 2) {
+        const size_t o = (size_t)(c + lane) * n + r;
+        float v = alpha * ((lane == 0 ? a0 : a1) - cen * src[o]);
+        if (beta != 0.f) v -= beta * dst[o];
+        dst[o] = v;
+      }
+    }
+  }
+}
+
+// SMEM_BLOCKS: the two n x 48 blocks live in dynamic shared memory (n <= GCCB_CF_NSM) instead of
+// the L2-resident workspace.  cls selects the work list.
+template <bool SMEM_BLOCKS>
+__global__ void __launch_bounds__(256)
+posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts, int cls,
+                    int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
+                    const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
+                    const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
+                    float* __restrict__ blocks /* [2][2*node_cap*48] */, float* __restrict__ dinv_g /* [2*node_cap] */,
+                    float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags) {
+  constexpr int CB = GCCB_CF_B, LD = CB + 1;
+  GCCB_DYN_SMEM(float, dynsm);
+  __shared__ float Gs[CB * LD];            // Ritz problem
+  __shared__ float Ws[CB * LD];            // its eigenvectors
+  __shared__ float tile[2][32][CB + 1];    // Q / Z row chunks for H = Q^T Z
+  __shared__ float rdot[CB];
+  __shared__ float theta[CB];
+  __shared__ float cs[64];
+  __shared__ int pq[32];
+  __shared__ int perm[CB];
+  __shared__ int heavy[GCCB_CF_MAXHEAVY];
+  __shared__ int s_nheavy;
+  __shared__ float s_red[8];
+  __shared__ float s_bc[2];
+  __shared__ float sgn[32];
+  if ((int)blockIdx.x >= counts[cls]) return;
+  const int slot = worklist[(size_t)cls * 2 * B + blockIdx.x];
+  const int view = slot / B, g = slot - view * B;
+  const int noff = node_off[view * (B + 1) + g];
+  const int n = node_off[view * (B + 1) + g + 1] - noff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = min(n - 2, pos_dim);                    // n > 64 -> k = pos_dim
+  float* out = pos + ((size_t)view * node_cap + noff) * pos_dim;
+  float* dinv = dinv_g + (size_t)view * node_cap + noff;
+  SubCsr S;
+  S.indptr = b_indptr + (size_t)view * (node_cap + 1);
+  S.indices = b_indices + (size_t)view * edge_cap;
+  S.dinv = dinv;
+  S.noff = noff; S.n = n;
+  const int32_t* v_deg = sub_deg + (size_t)view * node_cap;
+  float* X;
+  float* Y;
+  if (SMEM_BLOCKS) {
+    X = dynsm;
+    Y = dynsm + (size_t)n * CB;
+  } else {
+    X = blocks + ((size_t)view * node_cap + noff) * CB;                // n x CB, column-major
+    Y = X + (size_t)2 * node_cap * CB;
+  }
+  if (tid == 0) s_nheavy = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    int d = v_deg[noff + i];
+    dinv[i] = 1.0f / sqrtf((float)(d < 1 ? 1 : d));
+    if (d > GCCB_CF_HEAVY) {
+      int h = atomicAdd(&s_nheavy, 1);
+      if (h < GCCB_CF_MAXHEAVY) heavy[h] = i;
+    }
+  }
+  // start block: counter-based pseudo-random entries in (-1, 1) (deterministic)
+  for (int i = tid; i < n * CB; i += 256) {
+    u32x4 w = philox4x32_10((uint32_t)i, (uint32_t)n, 0x51ED270Bu, 3u, 0xC0FFEEu, 0x5EEDu);
+    X[i] = (float)(int32_t)w.x * (1.0f / 2147483648.0f);
+  }
+  __syncthreads();
+  int nheavy = s_nheavy, thresh = GCCB_CF_HEAVY;
+  if (nheavy > GCCB_CF_MAXHEAVY) { nheavy = 0; thresh = 0x7fffffff; }   // list overflow: all rows serial
+  float cut = 0.0f;                                     // the filter suppresses [-1, cut]
+  float prev_worst = 3.0e38f;
+  bool converged = false;
+  for (int iter = 0; iter < GCCB_CF_MAXIT && !converged; ++iter) {
+    // ---- Chebyshev filter on [-1, cut] (scaled three-term recurrence) -----------------------------
+    {
+      const int deg = iter == 0 ? GCCB_CF_DEG0 : GCCB_CF_DEG;
+      const float e = (cut + 1.0f) * 0.5f, cen = (cut - 1.0f) * 0.5f;
+      float sigma = e / (1.0f - cen);
+      const float sigma1 = sigma;
+      spmm_cheb(S, X, Y, sigma1 / e, cen, 0.f, heavy, nheavy, thresh);            // Y1
+      __syncthreads();
+      float* cur = Y; float* prev = X;
+      for (int i = 2; i <= deg; ++i) {
+        const float sigma2 = 1.0f / (2.0f / sigma1 - sigma);
+        spmm_cheb(S, cur, prev, 2.0f * sigma2 / e, cen, sigma * sigma2, heavy, nheavy, thresh);  // overwrites prev
+        __syncthreads();
+        float* t = cur; cur = prev; prev = t;
+        sigma = sigma2;
+      }
+      X = cur; Y = prev;                                 // filtered block in X, Y is scratch
+    }
+    // ---- CGS2: orthonormalise the columns of X in place -------------------------------------------
+    for (int j = 0; j < CB; ++j) {
+      float* yj = X + (size_t)j * n;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int i = warp; i < j; i += 8) {
+          const float* qi = X + (size_t)i * n;
+          float s = 0.f;
+          for (int r = lane; r < n; r += 32) s = fmaf(qi[r], yj[r], s);
+          s = warp_sum(s);
+          if (lane == 0) rdot[i] = s;
+        }
+        __syncthreads();
+        for (int r = tid; r < n; r += 256) {
+          float v0 = yj[r], v1 = 0.f;                   // two chains: halves the FMA dependency depth
+          int i = 0;
+          for (; i + 1 < j; i += 2) {
+            v0 = fmaf(-rdot[i], X[(size_t)i * n + r], v0);
+            v1 = fmaf(-rdot[i + 1], X[(size_t)(i + 1) * n + r], v1);
+          }
+          if (i < j) v0 = fmaf(-rdot[i], X[(size_t)i * n + r], v0);
+          yj[r] = v0 + v1;
+        }
+        __syncthreads();
+      }
+      float s = 0.f;
+      for (int r = tid; r < n; r += 256) s = fmaf(yj[r], yj[r], s);
+      s = warp_sum(s);
+      if (lane == 0) s_red[warp] = s;
+      __syncthreads();
+      if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        s_bc[0] = t > 1e-30f ? 1.0f / sqrtf(t) : 0.f;
+      }
+      __syncthreads();
+      const float inv = s_bc[0];
+      for (int r = tid; r < n; r += 256) yj[r] *= inv;
+      __syncthreads();
+    }
+    // ---- Z = L Q (into Y), H = Q^T Z ----------------------------------------------------------------
+    spmm_cheb(S, X, Y, 1.0f, 0.f, 0.f, heavy, nheavy, thresh);
+    __syncthreads();
+    {
+      const int ti = tid >> 4, tj = tid & 15;            // 16 x 16 threads, 3 x 3 outputs each
+      float acc[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 3; ++b2) acc[a][b2] = 0.f;
+      for (int r0 = 0; r0 < n; r0 += 32) {
+        for (int idx = tid; idx < 32 * CB; idx += 256) {
+          const int c = idx >> 5, rr = idx & 31;
+          const int r = r0 + rr;
+          tile[0][rr][c] = r < n ? X[(size_t)c * n + r] : 0.f;
+          tile[1][rr][c] = r < n ? Y[(size_t)c * n + r] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          float qa[3], zb[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { qa[a] = tile[0][rr][ti * 3 + a]; zb[a] = tile[1][rr][tj * 3 + a]; }
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < 3; ++b2) acc[a][b2] = fmaf(qa[a], zb[b2], acc[a][b2]);
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 3; ++b2) Gs[(tj * 3 + b2) * LD + ti * 3 + a] = acc[a][b2];
+      __syncthreads();
+      for (int idx = tid; idx < CB * CB; idx += 256) {  // G = sym(H) + 2 I, column-major
+        const int i = idx / CB, j = idx - i * CB;
+        if (i < j) {
+          float v = 0.5f * (Gs[j * LD + i] + Gs[i * LD + j]);
+          Gs[j * LD + i] = v;
+          Gs[i * LD + j] = v;
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < CB; i += 256) Gs[i * LD + i] += 2.0f;
+      __syncthreads();
+    }
+    // ---- 48 x 48 Ritz problem: two-sided Jacobi, eigenvectors in Ws --------------------------------
+    jacobi_twosided<256, float>(Gs, Ws, cs, pq, CB, LD);
+    for (int j = tid; j < CB; j += 256) {
+      const float mj = Gs[j * LD + j];
+      int rank = 0;
+      for (int i = 0; i < CB; ++i) {
+        float mi = Gs[i * LD + i];
+        rank += (mi > mj) || (mi == mj && i < j);
+      }
+      perm[rank] = j;                                   // descending: perm[0] = largest
+    }
+    __syncthreads();
+    // ---- X <- Q W[:, perm]: one warp per row, lanes over output columns, in place -----------------
+    for (int r = warp; r < n; r += 8) {
+      const float* w0 = Ws + perm[lane] * LD;
+      const float* w1 = Ws + perm[lane < 16 ? 32 + lane : 0] * LD;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < CB; ++i) {
+        const float q = X[(size_t)i * n + r];            // broadcast load
+        a0 = fmaf(q, w0[i], a0);
+        a1 = fmaf(q, w1[i], a1);
+      }
+      __syncwarp();                                      // all lanes have read row r before it is overwritten
+      X[(size_t)lane * n + r] = a0;
+      if (lane < 16) X[(size_t)(32 + lane) * n + r] = a1;
+    }
+    __syncthreads();
+    // ---- residuals of the wanted pairs: theta_c = x_c . L x_c ; ||L x_c - theta_c x_c|| -----------
+    spmm_cheb(S, X, Y, 1.0f, 0.f, 0.f, heavy, nheavy, thresh);          // Y = L X
+    __syncthreads();
+    float worst = 0.f;
+    for (int c = warp; c < CB; c += 8) {
+      const float* xc = X + (size_t)c * n;
+      const float* ax = Y + (size_t)c * n;
+      float th = 0.f;
+      for (int r = lane; r < n; r += 32) th = fmaf(xc[r], ax[r], th);
+      th = warp_sum(th);
+      float rs = 0.f;
+      for (int r = lane; r < n; r += 32) { float d = ax[r] - th * xc[r]; rs = fmaf(d, d, rs); }
+      rs = warp_sum(rs);
+      if (lane == 0) theta[c] = th;
+      if (c < k) worst = fmaxf(worst, sqrtf(rs));
+    }
+    if (lane == 0) s_red[warp] = worst;
+    __syncthreads();
+    if (tid == 0) {
+      float w = 0.f;
+      for (int i = 0; i < 8; ++i) w = fmaxf(w, s_red[i]);
+      s_bc[0] = w;
+      float lo = theta[0];
+      for (int i = 1; i < CB; ++i) lo = fminf(lo, theta[i]);
+      s_bc[1] = lo;
+    }
+    __syncthreads();
+    const float w_all = s_bc[0];
+    // converged, or stagnating at the fp32 noise floor of the Rayleigh-Ritz residual
+    converged = (w_all < GCCB_CF_TOL) || (w_all < GCCB_CF_STAG && w_all > 0.5f * prev_worst);
+    prev_worst = w_all;
+    cut = fminf(fmaxf(s_bc[1], -0.9f), 0.95f);          // smallest Ritz value of the block
+    __syncthreads();
+  }
+  if (!converged && tid == 0) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
+  // columns 0..k-1 of X hold the k largest Ritz pairs in DESCENDING order; emit ascending
+  // (data_util.py: eigsh(which='LA') returns ascending eigenvalues)
+  if (eigvals)
+    for (int c = tid; c < pos_dim; c += 256) eigvals[(size_t)slot * pos_dim + c] = c < k ? theta[k - 1 - c] : 0.f;
+  const float* Xf = X;
+  write_features(n, k, pos_dim, normalize, sgn, out,
+                 [&](int c, int r) { return Xf[(size_t)(k - 1 - c) * n + r]; });
+}
 
 }  // namespace gccb
 
 using namespace gccb;
 
-// workspace: worklist[4][2B] ints | counts[4] ints
+// workspace: worklist[3][2B] ints | counts[3] ints | pad | dinv[2*node_cap] | blocks[2][2*node_cap*48] floats
+static size_t posenc_ws_ints(int B) { return (((size_t)3 * 2 * B + 3) + 63) & ~(size_t)63; }
+
 extern "C" size_t gccb_posenc_workspace(int32_t batch, int32_t node_cap) {
-  (void)node_cap;
-  return ((size_t)4 * 2 * batch + 4) * sizeof(int32_t);
+  return posenc_ws_ints(batch) * sizeof(int32_t) +
+         ((size_t)2 * node_cap + (size_t)2 * 2 * node_cap * GCCB_CF_B) * sizeof(float);
 }
 
 extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t normalize,
@@ -290,26 +696,26 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
     return GCCB_ERR_CAPACITY;
   }
   int32_t* worklist = (int32_t*)workspace;
-  int32_t* counts = worklist + (size_t)4 * 2 * B;
-  GCCB_LAUNCH(posenc_classify_kernel, 1, 256, 0, stream, batch->counters, batch->node_off, B,
-              worklist, counts, batch->flags);
-  auto k2 = posenc_jacobi_kernel<8, 1024>;
-  auto k1 = posenc_jacobi_kernel<4, 512>;
-  auto k0 = posenc_jacobi_kernel<2, 256>;
-  const size_t s2 = eig_smem_bytes(GCCB_EIG_NMAX), s1 = eig_smem_bytes(128), s0 = eig_smem_bytes(64);
-  cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
-  cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
-  // largest matrices first: they are the tail of the step
-  GCCB_LAUNCH(k2, 2 * B, 1024, s2, stream, worklist, counts, 2, B, batch->node_cap,
-              batch->edge_cap, batch->node_off, batch->indptr, batch->indices, batch->sub_deg,
-              pos_dim, normalize, pos, eigvals, batch->flags);
-  GCCB_LAUNCH(k1, 2 * B, 512, s1, stream, worklist, counts, 1, B, batch->node_cap,
-              batch->edge_cap, batch->node_off, batch->indptr, batch->indices, batch->sub_deg,
-              pos_dim, normalize, pos, eigvals, batch->flags);
-  GCCB_LAUNCH(k0, 2 * B, 256, s0, stream, worklist, counts, 0, B, batch->node_cap,
-              batch->edge_cap, batch->node_off, batch->indptr, batch->indices, batch->sub_deg,
-              pos_dim, normalize, pos, eigvals, batch->flags);
-  GCCB_LAUNCH(posenc_zero_big_kernel, 2 * B, 256, 0, stream, worklist, counts, B,
-              batch->node_cap, batch->node_off, pos_dim, pos, eigvals);
+  int32_t* counts = worklist + (size_t)3 * 2 * B;
+  float* dinv = (float*)((int32_t*)workspace + posenc_ws_ints(B));
+  float* blocks = dinv + (size_t)2 * batch->node_cap;
+  GCCB_LAUNCH(posenc_classify_kernel, 1, 256, 0, stream, batch->counters, batch->node_off, B, worklist, counts);
+  // the large ego-nets first: they are the tail of the step
+  auto kbig = posenc_chfsi_kernel<false>;
+  auto kmid = posenc_chfsi_kernel<true>;
+  const size_t smid = (size_t)2 * GCCB_CF_NSM * GCCB_CF_B * sizeof(float);
+  cudaFuncSetAttribute(kmid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smid);
+  GCCB_LAUNCH(kbig, 2 * B, 256, 0, stream, worklist, counts, 2, B, batch->node_cap, batch->edge_cap,
+              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
+              pos, eigvals, batch->flags);
+  GCCB_LAUNCH(kmid, 2 * B, 256, smid, stream, worklist, counts, 1, B, batch->node_cap, batch->edge_cap,
+              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
+              pos, eigvals, batch->flags);
+  auto ksmall = posenc_jacobi_kernel;
+  const size_t ssmall = (size_t)2 * GCCB_EIG_SMALL * (GCCB_EIG_SMALL + 1) * sizeof(double);
+  cudaFuncSetAttribute(ksmall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmall);
+  GCCB_LAUNCH(ksmall, 2 * B, 256, ssmall, stream, worklist, counts, B, batch->node_cap, batch->edge_cap,
+              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, pos, eigvals,
+              batch->flags);
   return check_launch("gccb_posenc");
 }

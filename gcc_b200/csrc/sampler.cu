@@ -47,6 +47,19 @@ __device__ __forceinline__ int local_id(const int* keys, int n, int seed, int u)
   return (lo < n && keys[lo] == u) ? lo : -1;
 }
 
+// neighbour lists are ascending (gccb_graph_t contract): membership of u in adj(v) by bisection
+__device__ __forceinline__ bool adj_find(const int32_t* __restrict__ indices, int64_t beg, int64_t end, int u) {
+  const int64_t stop = end;
+  while (beg < end) {
+    int64_t mid = (beg + end) >> 1;
+    if (indices[mid] < u) beg = mid + 1; else end = mid;
+  }
+  return beg < stop && indices[beg] == u;
+}
+// A hub row (parent degree >> ego-net size) is not streamed: each ego-net vertex is looked up in the
+// hub's sorted neighbour list instead (n log deg probes instead of deg reads).
+#define GCCB_REVERSE_FACTOR 16
+
 // Pass 1: walk + sort/unique + induced-degree count.  grid = 2B, block = 256.
 // dyn smem: keys[P] ints, P = pow2 >= max_budget + HOPCAP.
 __global__ void __launch_bounds__(256)
@@ -162,9 +175,13 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
     const int64_t v = keys[i];
     const int64_t beg = indptr[v], end = indptr[v + 1];
     int cnt = 0;
-    for (int64_t e = beg + lane; e < end; e += 32) {
-      int u = indices[e];
-      cnt += local_id(keys, n, seed, u) >= 0;
+    if (end - beg > (int64_t)GCCB_REVERSE_FACTOR * n) {
+      for (int j = lane; j < n; j += 32) cnt += adj_find(indices, beg, end, keys[j]);
+    } else {
+      for (int64_t e = beg + lane; e < end; e += 32) {
+        int u = indices[e];
+        cnt += local_id(keys, n, seed, u) >= 0;
+      }
     }
     cnt = warp_sum_i(cnt);
     if (lane == 0) {
@@ -271,6 +288,25 @@ induce_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
     const int64_t v = keys[i];
     const int64_t beg = indptr[v], end = indptr[v + 1];
     int wpos = v_indptr[noff + i];
+    if (end - beg > (int64_t)GCCB_REVERSE_FACTOR * n) {
+      // candidates in ascending parent id = the order a scan of adj(v) would meet them:
+      // keys[1..n) is ascending, the seed (local id 0) is spliced in at its rank sr
+      int lo = 1, hi = n;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < seed) lo = mid + 1; else hi = mid; }
+      const int sr = lo - 1;                             // number of non-seed keys below the seed
+      for (int t0 = 0; t0 < n; t0 += 32) {
+        const int t = t0 + lane;
+        int j = -1;
+        if (t < n) {
+          const int loc = t < sr ? t + 1 : (t == sr ? 0 : t);
+          if (adj_find(indices, beg, end, keys[loc])) j = loc;
+        }
+        unsigned hit = __ballot_sync(0xffffffffu, j >= 0);
+        if (j >= 0) v_indices[wpos + __popc(hit & ((1u << lane) - 1u))] = noff + j;
+        wpos += __popc(hit);
+      }
+      continue;
+    }
     for (int64_t e0 = beg; e0 < end; e0 += 32) {
       int64_t e = e0 + lane;
       int j = -1;

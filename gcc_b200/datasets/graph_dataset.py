@@ -119,12 +119,22 @@ class BatchBuffers:
                              self.counters.data_ptr(), self.flags.data_ptr())
 
     def check_flags(self):
-        """Host sync: raise on any device-side failure flag."""
+        """Host sync: raise on any device-side failure flag.  Eigensolver non-convergence is not
+        fatal (the reference itself falls back to zeros after 10 ARPACK retries,
+        data_util.py:249-257): it is counted and reported once."""
         f = int(self.flags.item())
         if f:
             self.flags.zero_()
-            raise _lib.GccbError("device flags: " + "; ".join(
-                n for b, n in _capi.FLAG_NAMES.items() if f & b))
+            if f & _capi.FLAG_EIG_NOCONV:
+                self.eig_noconv_events = getattr(self, "eig_noconv_events", 0) + 1
+                if self.eig_noconv_events == 1:
+                    import warnings
+                    warnings.warn("gcc_b200: an ego-net eigensolve hit its iteration limit "
+                                  "(residual above 1.5e-4); features kept as is")
+                f &= ~_capi.FLAG_EIG_NOCONV
+            if f:
+                raise _lib.GccbError("device flags: " + "; ".join(
+                    n for b, n in _capi.FLAG_NAMES.items() if f & b))
 
 
 class LoadBalanceGraphDataset(torch.utils.data.IterableDataset):

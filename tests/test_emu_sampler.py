@@ -31,11 +31,13 @@ def _run(g, B, rw_hops, key, first=0, node_cap=None, edge_cap=None):
     return b, views, want
 
 
-@pytest.mark.parametrize("name,B,hops", [("er", 5, 24), ("star", 3, 16), ("cl", 4, 40)])
+@pytest.mark.parametrize("name,B,hops", [("er", 5, 24), ("star", 3, 16), ("cl", 4, 40), ("hub", 4, 16)])
 def test_sampler_matches_oracle(name, B, hops):
     g = {"er": lambda: synthetic.erdos_renyi(300, 1200, seed=2),
          "star": lambda: synthetic.star_graph(40),
-         "cl": lambda: synthetic.chung_lu(2000, 12000, seed=3)}[name]()
+         "cl": lambda: synthetic.chung_lu(2000, 12000, seed=3),
+         # hub degree >> ego-net size: exercises the reverse-probe induction path
+         "hub": lambda: synthetic.chung_lu(6000, 60000, exponent=0.9, seed=5)}[name]()
     b, views, want = _run(g, B, hops, key=0xABCDEF12345)
     assert b.flags[0] == 0
     for v in (0, 1):

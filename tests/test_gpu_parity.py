@@ -369,12 +369,25 @@ def test_engine_step_matches_oracle_and_learns():
     assert np.isclose(s["grad_norm"], r["grad_norm"], rtol=2e-3)
     fq = eng.feat_q.cpu().numpy()
     assert np.allclose(fq, r["feat_q"].numpy(), rtol=1e-3, atol=1e-4)
+    # raw (pre-clip) gradients of the flat buffer against autograd's
+    gflat = eng.grads.cpu().numpy()
+    for k, (off, shape) in model._slices.items():
+        if "mlp.linears" in k and k.endswith("bias"):
+            continue                                    # exactly-zero true gradient (feeds a BatchNorm)
+        got = gflat[off:off + int(np.prod(shape))].reshape(shape)
+        want = r["grads"][k].numpy() if k in r["grads"] else np.zeros(shape)
+        scale = max(np.abs(want).max(), 1e-6)
+        assert np.allclose(got, want, rtol=5e-3, atol=2e-3 * scale), (k, np.abs(got - want).max(), scale)
+    # weights after the first Adam step: update = lr * g/(|g|+eps) is sign-like, so entries whose
+    # gradient is ~eps-sized are ill-conditioned in the reference too; require agreement elsewhere
     sd1 = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
     for k, v in state["params"].items():
         if ("mlp.linears" in k and k.endswith("bias")) or (k.endswith("running_mean") and "apply_func" in k) \
                 or k.endswith("num_batches_tracked") or k.endswith(".eps"):
             continue
-        assert np.allclose(sd1[k], v.numpy(), rtol=2e-3, atol=5e-5), (k, np.abs(sd1[k] - v.numpy()).max())
+        diff = np.abs(sd1[k] - v.numpy())
+        assert diff.max() <= 2 * 0.005 + 1e-6, (k, diff.max())
+        assert (diff > 5e-5).mean() < 0.02, (k, (diff > 5e-5).mean())
     assert np.allclose(contrast.memory.cpu().numpy(), state["memory"].numpy(), atol=1e-4)
     losses = [s["loss"]]
     for i in range(30):
