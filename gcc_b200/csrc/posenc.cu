@@ -39,15 +39,16 @@ namespace gccb {
 #define GCCB_CF_DEG0 4              // Chebyshev degree of the first outer iteration (random block:
                                    // keep it numerically full rank for fp32 Gram-Schmidt)
 #define GCCB_CF_DEG 8              // degree of the later iterations (gain T_8(3) ~ 7e5 < 1/eps_fp32)
-#define GCCB_CF_NSM 160            // blocks of ego-nets up to this size live in shared memory
+#define GCCB_CF_NSM_A 96            // shared-memory block classes: n <= 96 (3 CTAs/SM) and
+#define GCCB_CF_NSM 160            //   n <= 160 (2 CTAs/SM); larger ego-nets use the L2 workspace
 #define GCCB_CF_MAXIT 16
 #define GCCB_CF_TOL 4.0e-5f        // max residual ||L x - theta x|| over the wanted pairs
 #define GCCB_CF_STAG 1.5e-4f       // accepted when the residual stagnates below this (fp32 floor)
-#define GCCB_CF_HEAVY 32           // rows with more neighbours are processed warp-cooperatively
-#define GCCB_CF_MAXHEAVY 128
 
-// class 0: n <= 64 (dense Jacobi), class 1: ChFSI with shared-memory blocks, class 2: ChFSI, L2 blocks
-__device__ __forceinline__ int eig_class(int n) { return n <= GCCB_EIG_SMALL ? 0 : n <= GCCB_CF_NSM ? 1 : 2; }
+// class 0: n <= 64 (dense Jacobi); 1, 2: ChFSI with shared-memory blocks; 3: ChFSI with L2 blocks
+__device__ __forceinline__ int eig_class(int n) {
+  return n <= GCCB_EIG_SMALL ? 0 : n <= GCCB_CF_NSM_A ? 1 : n <= GCCB_CF_NSM ? 2 : 3;
+}
 
 // Work lists: worklist[c][i] = slot.  One CTA, deterministic order.  grid = 1, block = 256.
 __global__ void __launch_bounds__(256)
@@ -55,7 +56,7 @@ posenc_classify_kernel(const int64_t* __restrict__ counters, const int32_t* __re
                        int B, int32_t* __restrict__ worklist, int32_t* __restrict__ counts) {
   __shared__ int scan_scratch[33];
   const int tid = threadIdx.x;
-  int base[3] = {0, 0, 0};
+  int base[4] = {0, 0, 0, 0};
   for (int s0 = 0; s0 < 2 * B; s0 += 256) {
     int slot = s0 + tid;
     int cls = -1;
@@ -64,14 +65,14 @@ posenc_classify_kernel(const int64_t* __restrict__ counters, const int32_t* __re
       if (node_off[view * (B + 1) + B] >= 0) cls = eig_class((int)counters[(size_t)slot * 4]);
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 4; ++c) {
       int tot;
       int ex = block_scan_excl(cls == c ? 1 : 0, scan_scratch, &tot);
       if (cls == c) worklist[(size_t)c * 2 * B + base[c] + ex] = slot;
       base[c] += tot;
     }
   }
-  if (tid == 0) { counts[0] = base[0]; counts[1] = base[1]; counts[2] = base[2]; }
+  if (tid < 4) counts[tid] = base[tid];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -360,6 +361,8 @@ posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __rest
 }
 
 // ---- solver (2): Chebyshev-filtered subspace iteration, any n > 64 -------------------------------
+// Blocks are ROW-major n x 48 (leading dimension ld): a neighbour gather reads one contiguous row,
+// so the sparse products are warp-per-row with lanes across the 48 columns (any degree, coalesced).
 struct SubCsr {
   const int32_t* indptr;   // view-local, index with noff + r
   const int32_t* indices;
@@ -367,67 +370,72 @@ struct SubCsr {
   int noff, n;
 };
 
-// dst[c][r] = alpha * (sum_{j in N(r)} w_rj src[c][j] - cen * src[c][r]) - beta * dst[c][r]
-// (beta == 0: dst is write-only).  Blocks are column-major n x 48.  Rows with more than
-// `thresh` neighbours are listed in heavy[] and processed by whole warps.
+// dst[r][c] = alpha * (sum_{j in N(r)} w_rj src[j][c] - cen * src[r][c]) - beta * dst[r][c]
+// (beta == 0: dst is write-only).  One warp per row; lane owns columns lane and 32 + lane.
 __device__ __forceinline__ void spmm_cheb(const SubCsr& S, const float* __restrict__ src, float* __restrict__ dst,
-                                          float alpha, float cen, float beta, const int* heavy, int nheavy,
-                                          int thresh) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
-  const int n = S.n;
-  constexpr int CG = 8;                                  // columns per work item
-  const int items = n * (GCCB_CF_B / CG);
-  for (int it = tid; it < items; it += blockDim.x) {
-    const int r = it % n, c0 = (it / n) * CG;
-    const int beg = S.indptr[S.noff + r], end = S.indptr[S.noff + r + 1];
-    if (end - beg > thresh) continue;                    // heavy row: handled below
-    float acc[CG];
-#pragma unroll
-    for (int cc = 0; cc < CG; ++cc) acc[cc] = 0.f;
-    const float dr = S.dinv[r];
-    for (int e = beg; e < end; ++e) {
-      const int j = S.indices[e] - S.noff;
-      const float w = dr * S.dinv[j];
-#pragma unroll
-      for (int cc = 0; cc < CG; ++cc) acc[cc] = fmaf(w, src[(size_t)(c0 + cc) * n + j], acc[cc]);
-    }
-#pragma unroll
-    for (int cc = 0; cc < CG; ++cc) {
-      const size_t o = (size_t)(c0 + cc) * n + r;
-      float v = alpha * (acc[cc] - cen * src[o]);
-      if (beta != 0.f) v -= beta * dst[o];
-      dst[o] = v;
-    }
-  }
-  for (int h = 0; h < nheavy; ++h) {
-    const int r = heavy[h];
+                                          int ld, float alpha, float cen, float beta) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const bool hi = lane < GCCB_CF_B - 32;
+  for (int r = warp; r < S.n; r += nw) {
     const int beg = S.indptr[S.noff + r], end = S.indptr[S.noff + r + 1];
     const float dr = S.dinv[r];
-    // two columns per pass: independent accumulators hide the gather latency
-    for (int c = warp * 2; c < GCCB_CF_B; c += NW * 2) {
-      float a0 = 0.f, a1 = 0.f;
-      for (int e = beg + lane; e < end; e += 32) {
-        const int j = S.indices[e] - S.noff;
-        const float w = dr * S.dinv[j];
-        a0 = fmaf(w, src[(size_t)c * n + j], a0);
-        a1 = fmaf(w, src[(size_t)(c + 1) * n + j], a1);
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    int e = beg;
+    for (; e + 1 < end; e += 2) {                         // two edges in flight
+      const int j0 = S.indices[e] - S.noff, j1 = S.indices[e + 1] - S.noff;
+      const float w0 = dr * S.dinv[j0], w1 = dr * S.dinv[j1];
+      a0 = fmaf(w0, src[(size_t)j0 * ld + lane], a0);
+      b0 = fmaf(w1, src[(size_t)j1 * ld + lane], b0);
+      if (hi) {
+        a1 = fmaf(w0, src[(size_t)j0 * ld + 32 + lane], a1);
+        b1 = fmaf(w1, src[(size_t)j1 * ld + 32 + lane], b1);
       }
-      a0 = warp_sum(a0);
-      a1 = warp_sum(a1);
-      if (lane < 2) {
-        const size_t o = (size_t)(c + lane) * n + r;
-        float v = alpha * ((lane == 0 ? a0 : a1) - cen * src[o]);
-        if (beta != 0.f) v -= beta * dst[o];
-        dst[o] = v;
-      }
+    }
+    if (e < end) {
+      const int j0 = S.indices[e] - S.noff;
+      const float w0 = dr * S.dinv[j0];
+      a0 = fmaf(w0, src[(size_t)j0 * ld + lane], a0);
+      if (hi) a1 = fmaf(w0, src[(size_t)j0 * ld + 32 + lane], a1);
+    }
+    a0 += b0; a1 += b1;
+    const size_t o = (size_t)r * ld + lane;
+    float v = alpha * (a0 - cen * src[o]);
+    if (beta != 0.f) v -= beta * dst[o];
+    dst[o] = v;
+    if (hi) {
+      float v1 = alpha * (a1 - cen * src[o + 32]);
+      if (beta != 0.f) v1 -= beta * dst[o + 32];
+      dst[o + 32] = v1;
     }
   }
 }
 
-// SMEM_BLOCKS: the two n x 48 blocks live in dynamic shared memory (n <= GCCB_CF_NSM) instead of
-// the L2-resident workspace.  cls selects the work list.
-template <bool SMEM_BLOCKS>
-__global__ void __launch_bounds__(256)
+// Per-column reduction helper: every warp accumulates (lane -> columns lane, 32+lane) over its rows,
+// partial sums go through part[32][48] and end up in out[48].  Ends with a barrier.
+template <class RowFn>
+__device__ __forceinline__ void column_sums(int n, float* part /*[32][48]*/, float* out /*[48]*/, RowFn f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const bool hi = lane < GCCB_CF_B - 32;
+  float a0 = 0.f, a1 = 0.f;
+  for (int r = warp; r < n; r += nw) {
+    a0 += f(r, lane);
+    if (hi) a1 += f(r, 32 + lane);
+  }
+  part[warp * GCCB_CF_B + lane] = a0;
+  if (hi) part[warp * GCCB_CF_B + 32 + lane] = a1;
+  __syncthreads();
+  for (int c = threadIdx.x; c < GCCB_CF_B; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += part[w * GCCB_CF_B + c];
+    out[c] = s;
+  }
+  __syncthreads();
+}
+
+// SMEM_BLOCKS: the two n x 48 blocks live in dynamic shared memory (ld = 49, conflict-free) instead
+// of the L2-resident workspace (ld = 48).  cls selects the work list; blockDim.x = 256 or 1024.
+template <bool SMEM_BLOCKS, int NT>
+__global__ void __launch_bounds__(NT)
 posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts, int cls,
                     int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
                     const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
@@ -436,25 +444,27 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
                     float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags) {
   constexpr int CB = GCCB_CF_B, LD = CB + 1;
   GCCB_DYN_SMEM(float, dynsm);
-  __shared__ float Gs[CB * LD];            // Ritz problem
-  __shared__ float Ws[CB * LD];            // its eigenvectors
-  __shared__ float tile[2][32][CB + 1];    // Q / Z row chunks for H = Q^T Z
+  __shared__ float Gs[CB * LD];                   // Ritz problem
+  __shared__ float WT[32 * (CB + 1) * 2];         // union: Ritz vectors Ws[CB*LD] | tiles [2][32][CB+1]
+  __shared__ float part[32 * CB];
   __shared__ float rdot[CB];
   __shared__ float theta[CB];
+  __shared__ float resid[CB];
   __shared__ float cs[64];
   __shared__ int pq[32];
   __shared__ int perm[CB];
-  __shared__ int heavy[GCCB_CF_MAXHEAVY];
-  __shared__ int s_nheavy;
-  __shared__ float s_red[8];
   __shared__ float s_bc[2];
   __shared__ float sgn[32];
+  float* Ws = WT;
+  float (*tile)[32][CB + 1] = reinterpret_cast<float (*)[32][CB + 1]>(WT);
   if ((int)blockIdx.x >= counts[cls]) return;
   const int slot = worklist[(size_t)cls * 2 * B + blockIdx.x];
   const int view = slot / B, g = slot - view * B;
   const int noff = node_off[view * (B + 1) + g];
   const int n = node_off[view * (B + 1) + g + 1] - noff;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+  const bool hi = lane < CB - 32;
   const int k = min(n - 2, pos_dim);                    // n > 64 -> k = pos_dim
   float* out = pos + ((size_t)view * node_cap + noff) * pos_dim;
   float* dinv = dinv_g + (size_t)view * node_cap + noff;
@@ -464,33 +474,26 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
   S.dinv = dinv;
   S.noff = noff; S.n = n;
   const int32_t* v_deg = sub_deg + (size_t)view * node_cap;
+  const int ld = SMEM_BLOCKS ? LD : CB;
   float* X;
   float* Y;
   if (SMEM_BLOCKS) {
     X = dynsm;
-    Y = dynsm + (size_t)n * CB;
+    Y = dynsm + (size_t)n * LD;
   } else {
-    X = blocks + ((size_t)view * node_cap + noff) * CB;                // n x CB, column-major
+    X = blocks + ((size_t)view * node_cap + noff) * CB;                // n x CB, row-major
     Y = X + (size_t)2 * node_cap * CB;
   }
-  if (tid == 0) s_nheavy = 0;
-  __syncthreads();
-  for (int i = tid; i < n; i += 256) {
+  for (int i = tid; i < n; i += NT) {
     int d = v_deg[noff + i];
     dinv[i] = 1.0f / sqrtf((float)(d < 1 ? 1 : d));
-    if (d > GCCB_CF_HEAVY) {
-      int h = atomicAdd(&s_nheavy, 1);
-      if (h < GCCB_CF_MAXHEAVY) heavy[h] = i;
-    }
   }
   // start block: counter-based pseudo-random entries in (-1, 1) (deterministic)
-  for (int i = tid; i < n * CB; i += 256) {
+  for (int i = tid; i < n * CB; i += NT) {
     u32x4 w = philox4x32_10((uint32_t)i, (uint32_t)n, 0x51ED270Bu, 3u, 0xC0FFEEu, 0x5EEDu);
-    X[i] = (float)(int32_t)w.x * (1.0f / 2147483648.0f);
+    X[(size_t)(i / CB) * ld + (i % CB)] = (float)(int32_t)w.x * (1.0f / 2147483648.0f);
   }
   __syncthreads();
-  int nheavy = s_nheavy, thresh = GCCB_CF_HEAVY;
-  if (nheavy > GCCB_CF_MAXHEAVY) { nheavy = 0; thresh = 0x7fffffff; }   // list overflow: all rows serial
   float cut = 0.0f;                                     // the filter suppresses [-1, cut]
   float prev_worst = 3.0e38f;
   bool converged = false;
@@ -501,93 +504,92 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
       const float e = (cut + 1.0f) * 0.5f, cen = (cut - 1.0f) * 0.5f;
       float sigma = e / (1.0f - cen);
       const float sigma1 = sigma;
-      spmm_cheb(S, X, Y, sigma1 / e, cen, 0.f, heavy, nheavy, thresh);            // Y1
+      spmm_cheb(S, X, Y, ld, sigma1 / e, cen, 0.f);                           // Y1
       __syncthreads();
       float* cur = Y; float* prev = X;
       for (int i = 2; i <= deg; ++i) {
         const float sigma2 = 1.0f / (2.0f / sigma1 - sigma);
-        spmm_cheb(S, cur, prev, 2.0f * sigma2 / e, cen, sigma * sigma2, heavy, nheavy, thresh);  // overwrites prev
+        spmm_cheb(S, cur, prev, ld, 2.0f * sigma2 / e, cen, sigma * sigma2);   // overwrites prev
         __syncthreads();
         float* t = cur; cur = prev; prev = t;
         sigma = sigma2;
       }
       X = cur; Y = prev;                                 // filtered block in X, Y is scratch
     }
-    // ---- CGS2: orthonormalise the columns of X in place -------------------------------------------
+    // ---- CGS2: orthonormalise the columns of X in place (row-major: all dots of a column at once)
     for (int j = 0; j < CB; ++j) {
-      float* yj = X + (size_t)j * n;
       for (int pass = 0; pass < 2; ++pass) {
-        for (int i = warp; i < j; i += 8) {
-          const float* qi = X + (size_t)i * n;
-          float s = 0.f;
-          for (int r = lane; r < n; r += 32) s = fmaf(qi[r], yj[r], s);
-          s = warp_sum(s);
-          if (lane == 0) rdot[i] = s;
-        }
-        __syncthreads();
-        for (int r = tid; r < n; r += 256) {
-          float v0 = yj[r], v1 = 0.f;                   // two chains: halves the FMA dependency depth
+        const float* Xc = X;
+        column_sums(n, part, rdot, [&](int r, int c) { return Xc[(size_t)r * ld + c] * Xc[(size_t)r * ld + j]; });
+        for (int r = tid; r < n; r += NT) {
+          float* row = X + (size_t)r * ld;
+          float v0 = row[j], v1 = 0.f;
           int i = 0;
           for (; i + 1 < j; i += 2) {
-            v0 = fmaf(-rdot[i], X[(size_t)i * n + r], v0);
-            v1 = fmaf(-rdot[i + 1], X[(size_t)(i + 1) * n + r], v1);
+            v0 = fmaf(-rdot[i], row[i], v0);
+            v1 = fmaf(-rdot[i + 1], row[i + 1], v1);
           }
-          if (i < j) v0 = fmaf(-rdot[i], X[(size_t)i * n + r], v0);
-          yj[r] = v0 + v1;
+          if (i < j) v0 = fmaf(-rdot[i], row[i], v0);
+          row[j] = v0 + v1;
         }
         __syncthreads();
       }
+      // normalise column j: the pass-2 dot of column j with itself is stale, recompute
       float s = 0.f;
-      for (int r = tid; r < n; r += 256) s = fmaf(yj[r], yj[r], s);
+      for (int r = tid; r < n; r += NT) { float v = X[(size_t)r * ld + j]; s = fmaf(v, v, s); }
       s = warp_sum(s);
-      if (lane == 0) s_red[warp] = s;
+      if (lane == 0) part[warp] = s;
       __syncthreads();
       if (tid == 0) {
         float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += s_red[w];
+        for (int w = 0; w < NW; ++w) t += part[w];
         s_bc[0] = t > 1e-30f ? 1.0f / sqrtf(t) : 0.f;
       }
       __syncthreads();
       const float inv = s_bc[0];
-      for (int r = tid; r < n; r += 256) yj[r] *= inv;
+      for (int r = tid; r < n; r += NT) X[(size_t)r * ld + j] *= inv;
       __syncthreads();
     }
     // ---- Z = L Q (into Y), H = Q^T Z ----------------------------------------------------------------
-    spmm_cheb(S, X, Y, 1.0f, 0.f, 0.f, heavy, nheavy, thresh);
+    spmm_cheb(S, X, Y, ld, 1.0f, 0.f, 0.f);
     __syncthreads();
     {
-      const int ti = tid >> 4, tj = tid & 15;            // 16 x 16 threads, 3 x 3 outputs each
+      const int ti = (tid & 255) >> 4, tj = tid & 15;    // first 256 threads: 16 x 16, 3 x 3 outputs each
       float acc[3][3];
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b2 = 0; b2 < 3; ++b2) acc[a][b2] = 0.f;
       for (int r0 = 0; r0 < n; r0 += 32) {
-        for (int idx = tid; idx < 32 * CB; idx += 256) {
-          const int c = idx >> 5, rr = idx & 31;
+        for (int idx = tid; idx < 32 * CB; idx += NT) {
+          const int rr = idx / CB, c = idx - rr * CB;
           const int r = r0 + rr;
-          tile[0][rr][c] = r < n ? X[(size_t)c * n + r] : 0.f;
-          tile[1][rr][c] = r < n ? Y[(size_t)c * n + r] : 0.f;
+          tile[0][rr][c] = r < n ? X[(size_t)r * ld + c] : 0.f;
+          tile[1][rr][c] = r < n ? Y[(size_t)r * ld + c] : 0.f;
         }
         __syncthreads();
+        if (tid < 256) {
 #pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          float qa[3], zb[3];
+          for (int rr = 0; rr < 32; ++rr) {
+            float qa[3], zb[3];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) { qa[a] = tile[0][rr][ti * 3 + a]; zb[a] = tile[1][rr][tj * 3 + a]; }
+            for (int a = 0; a < 3; ++a) { qa[a] = tile[0][rr][ti * 3 + a]; zb[a] = tile[1][rr][tj * 3 + a]; }
 #pragma unroll
-          for (int a = 0; a < 3; ++a)
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int b2 = 0; b2 < 3; ++b2) acc[a][b2] = fmaf(qa[a], zb[b2], acc[a][b2]);
+              for (int b2 = 0; b2 < 3; ++b2) acc[a][b2] = fmaf(qa[a], zb[b2], acc[a][b2]);
+          }
         }
         __syncthreads();
       }
+      if (tid < 256) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int b2 = 0; b2 < 3; ++b2) Gs[(tj * 3 + b2) * LD + ti * 3 + a] = acc[a][b2];
+          for (int b2 = 0; b2 < 3; ++b2) Gs[(tj * 3 + b2) * LD + ti * 3 + a] = acc[a][b2];
+      }
       __syncthreads();
-      for (int idx = tid; idx < CB * CB; idx += 256) {  // G = sym(H) + 2 I, column-major
+      for (int idx = tid; idx < CB * CB; idx += NT) {   // G = sym(H) + 2 I, column-major
         const int i = idx / CB, j = idx - i * CB;
         if (i < j) {
           float v = 0.5f * (Gs[j * LD + i] + Gs[i * LD + j]);
@@ -596,12 +598,12 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
         }
       }
       __syncthreads();
-      for (int i = tid; i < CB; i += 256) Gs[i * LD + i] += 2.0f;
+      for (int i = tid; i < CB; i += NT) Gs[i * LD + i] += 2.0f;
       __syncthreads();
     }
-    // ---- 48 x 48 Ritz problem: two-sided Jacobi, eigenvectors in Ws --------------------------------
-    jacobi_twosided<256, float>(Gs, Ws, cs, pq, CB, LD);
-    for (int j = tid; j < CB; j += 256) {
+    // ---- 48 x 48 Ritz problem: two-sided Jacobi, eigenvectors in Ws (tiles are dead now) ----------
+    jacobi_twosided<NT, float>(Gs, Ws, cs, pq, CB, LD);
+    for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
       int rank = 0;
       for (int i = 0; i < CB; ++i) {
@@ -612,45 +614,38 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
     }
     __syncthreads();
     // ---- X <- Q W[:, perm]: one warp per row, lanes over output columns, in place -----------------
-    for (int r = warp; r < n; r += 8) {
+    for (int r = warp; r < n; r += NW) {
       const float* w0 = Ws + perm[lane] * LD;
-      const float* w1 = Ws + perm[lane < 16 ? 32 + lane : 0] * LD;
+      const float* w1 = Ws + perm[hi ? 32 + lane : 0] * LD;
+      const float* row = X + (size_t)r * ld;
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll 8
       for (int i = 0; i < CB; ++i) {
-        const float q = X[(size_t)i * n + r];            // broadcast load
+        const float q = row[i];                          // broadcast
         a0 = fmaf(q, w0[i], a0);
         a1 = fmaf(q, w1[i], a1);
       }
       __syncwarp();                                      // all lanes have read row r before it is overwritten
-      X[(size_t)lane * n + r] = a0;
-      if (lane < 16) X[(size_t)(32 + lane) * n + r] = a1;
+      X[(size_t)r * ld + lane] = a0;
+      if (hi) X[(size_t)r * ld + 32 + lane] = a1;
     }
     __syncthreads();
     // ---- residuals of the wanted pairs: theta_c = x_c . L x_c ; ||L x_c - theta_c x_c|| -----------
-    spmm_cheb(S, X, Y, 1.0f, 0.f, 0.f, heavy, nheavy, thresh);          // Y = L X
+    spmm_cheb(S, X, Y, ld, 1.0f, 0.f, 0.f);              // Y = L X
     __syncthreads();
-    float worst = 0.f;
-    for (int c = warp; c < CB; c += 8) {
-      const float* xc = X + (size_t)c * n;
-      const float* ax = Y + (size_t)c * n;
-      float th = 0.f;
-      for (int r = lane; r < n; r += 32) th = fmaf(xc[r], ax[r], th);
-      th = warp_sum(th);
-      float rs = 0.f;
-      for (int r = lane; r < n; r += 32) { float d = ax[r] - th * xc[r]; rs = fmaf(d, d, rs); }
-      rs = warp_sum(rs);
-      if (lane == 0) theta[c] = th;
-      if (c < k) worst = fmaxf(worst, sqrtf(rs));
+    {
+      const float* Xc = X; const float* Yc = Y;
+      column_sums(n, part, theta, [&](int r, int c) { return Xc[(size_t)r * ld + c] * Yc[(size_t)r * ld + c]; });
+      column_sums(n, part, resid, [&](int r, int c) {
+        float d = Yc[(size_t)r * ld + c] - theta[c] * Xc[(size_t)r * ld + c];
+        return d * d;
+      });
     }
-    if (lane == 0) s_red[warp] = worst;
-    __syncthreads();
     if (tid == 0) {
-      float w = 0.f;
-      for (int i = 0; i < 8; ++i) w = fmaxf(w, s_red[i]);
-      s_bc[0] = w;
-      float lo = theta[0];
+      float w = 0.f, lo = theta[0];
+      for (int c = 0; c < k; ++c) w = fmaxf(w, resid[c]);
       for (int i = 1; i < CB; ++i) lo = fminf(lo, theta[i]);
+      s_bc[0] = sqrtf(w);
       s_bc[1] = lo;
     }
     __syncthreads();
@@ -665,18 +660,18 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
   // columns 0..k-1 of X hold the k largest Ritz pairs in DESCENDING order; emit ascending
   // (data_util.py: eigsh(which='LA') returns ascending eigenvalues)
   if (eigvals)
-    for (int c = tid; c < pos_dim; c += 256) eigvals[(size_t)slot * pos_dim + c] = c < k ? theta[k - 1 - c] : 0.f;
+    for (int c = tid; c < pos_dim; c += NT) eigvals[(size_t)slot * pos_dim + c] = c < k ? theta[k - 1 - c] : 0.f;
   const float* Xf = X;
   write_features(n, k, pos_dim, normalize, sgn, out,
-                 [&](int c, int r) { return Xf[(size_t)(k - 1 - c) * n + r]; });
+                 [&](int c, int r) { return Xf[(size_t)r * ld + (k - 1 - c)]; });
 }
 
 }  // namespace gccb
 
 using namespace gccb;
 
-// workspace: worklist[3][2B] ints | counts[3] ints | pad | dinv[2*node_cap] | blocks[2][2*node_cap*48] floats
-static size_t posenc_ws_ints(int B) { return (((size_t)3 * 2 * B + 3) + 63) & ~(size_t)63; }
+// workspace: worklist[4][2B] ints | counts[4] ints | pad | dinv[2*node_cap] | blocks[2][2*node_cap*48] floats
+static size_t posenc_ws_ints(int B) { return (((size_t)4 * 2 * B + 4) + 63) & ~(size_t)63; }
 
 extern "C" size_t gccb_posenc_workspace(int32_t batch, int32_t node_cap) {
   return posenc_ws_ints(batch) * sizeof(int32_t) +
@@ -696,26 +691,54 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
     return GCCB_ERR_CAPACITY;
   }
   int32_t* worklist = (int32_t*)workspace;
-  int32_t* counts = worklist + (size_t)3 * 2 * B;
+  int32_t* counts = worklist + (size_t)4 * 2 * B;
   float* dinv = (float*)((int32_t*)workspace + posenc_ws_ints(B));
   float* blocks = dinv + (size_t)2 * batch->node_cap;
   GCCB_LAUNCH(posenc_classify_kernel, 1, 256, 0, stream, batch->counters, batch->node_off, B, worklist, counts);
-  // the large ego-nets first: they are the tail of the step
-  auto kbig = posenc_chfsi_kernel<false>;
-  auto kmid = posenc_chfsi_kernel<true>;
-  const size_t smid = (size_t)2 * GCCB_CF_NSM * GCCB_CF_B * sizeof(float);
-  cudaFuncSetAttribute(kmid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smid);
-  GCCB_LAUNCH(kbig, 2 * B, 256, 0, stream, worklist, counts, 2, B, batch->node_cap, batch->edge_cap,
-              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
-              pos, eigvals, batch->flags);
-  GCCB_LAUNCH(kmid, 2 * B, 256, smid, stream, worklist, counts, 1, B, batch->node_cap, batch->edge_cap,
-              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
-              pos, eigvals, batch->flags);
+  auto kbig = posenc_chfsi_kernel<false, 1024>;
+  auto kmid = posenc_chfsi_kernel<true, 256>;
   auto ksmall = posenc_jacobi_kernel;
+  const size_t s_a = (size_t)2 * GCCB_CF_NSM_A * (GCCB_CF_B + 1) * sizeof(float);
+  const size_t s_b = (size_t)2 * GCCB_CF_NSM * (GCCB_CF_B + 1) * sizeof(float);
   const size_t ssmall = (size_t)2 * GCCB_EIG_SMALL * (GCCB_EIG_SMALL + 1) * sizeof(double);
+  cudaFuncSetAttribute(kmid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_b);
   cudaFuncSetAttribute(ksmall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmall);
-  GCCB_LAUNCH(ksmall, 2 * B, 256, ssmall, stream, worklist, counts, B, batch->node_cap, batch->edge_cap,
+  // The four size classes are independent: fork them over side streams (event fork/join, legal
+  // inside CUDA-graph capture) so that the few long-running large ego-nets overlap the many small ones.
+#ifndef GCCB_EMU
+  static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  if (!side[0]) {
+    for (int i = 0; i < 3; ++i) {
+      cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+  }
+  cudaStream_t main_s = (cudaStream_t)stream;
+  cudaEventRecord(ev_fork, main_s);
+  for (int i = 0; i < 3; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
+  gccb_stream_t s_big = side[0], s_mid2 = side[1], s_small = side[2], s_mid1 = stream;
+#else
+  gccb_stream_t s_big = stream, s_mid2 = stream, s_small = stream, s_mid1 = stream;
+#endif
+  GCCB_LAUNCH(kbig, 2 * B, 1024, 0, s_big, worklist, counts, 3, B, batch->node_cap, batch->edge_cap,
+              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
+              pos, eigvals, batch->flags);
+  GCCB_LAUNCH(kmid, 2 * B, 256, s_b, s_mid2, worklist, counts, 2, B, batch->node_cap, batch->edge_cap,
+              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
+              pos, eigvals, batch->flags);
+  GCCB_LAUNCH(kmid, 2 * B, 256, s_a, s_mid1, worklist, counts, 1, B, batch->node_cap, batch->edge_cap,
+              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
+              pos, eigvals, batch->flags);
+  GCCB_LAUNCH(ksmall, 2 * B, 256, ssmall, s_small, worklist, counts, B, batch->node_cap, batch->edge_cap,
               batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, pos, eigvals,
               batch->flags);
+#ifndef GCCB_EMU
+  for (int i = 0; i < 3; ++i) {
+    cudaEventRecord(ev_join[i], side[i]);
+    cudaStreamWaitEvent(main_s, ev_join[i], 0);
+  }
+#endif
   return check_launch("gccb_posenc");
 }

@@ -62,17 +62,20 @@ def test_jacobi_spectral_parity_small_and_degenerate():
 
 
 def test_jacobi_size_classes_and_normalisation():
-    g1 = synthetic.erdos_renyi(100, 260, seed=7)          # n > 64: Chebyshev-filtered subspace iteration
+    g1 = synthetic.erdos_renyi(90, 240, seed=7)           # 64 < n <= 96: Chebyshev-filtered subspace iteration
     g2 = synthetic.star_graph(90)                         # extreme degeneracy (eigenvalue 0 x 89)
-    views = [[_sub(g1)], [_sub(g2)]]
-    assert 64 < g1.num_nodes and 64 < g2.num_nodes
+    g3 = synthetic.erdos_renyi(150, 420, seed=9)          # 96 < n <= 160: second shared-memory class
+    views = [[_sub(g1), _sub(g3)], [_sub(g2), _sub(synthetic.path_graph(30))]]
+    assert 64 < g1.num_nodes <= 96 < g3.num_nodes <= 160 and 64 < g2.num_nodes
     b, pos, eig = _posenc(views, normalize=0)
     assert b.flags[0] == 0
     for v in (0, 1):
-        _check_spectral(views[v][0], pos[v, :views[v][0]["n"]], eig[v])
+        for gi, sub in enumerate(views[v]):
+            a, z = b.node_off[v, gi], b.node_off[v, gi + 1]
+            _check_spectral(sub, pos[v, a:z], eig[v * b.B + gi])
     b, posn, _ = _posenc(views, normalize=1)
     for v in (0, 1):
-        n = views[v][0]["n"]
+        n = b.node_off[v, b.B]
         assert np.allclose(np.linalg.norm(posn[v, :n], axis=1), 1.0, atol=1e-5)
         raw = pos[v, :n]
         want = raw / np.linalg.norm(raw, axis=1, keepdims=True)
