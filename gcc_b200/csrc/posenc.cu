@@ -40,14 +40,18 @@ namespace gccb {
                                    // keep it numerically full rank for fp32 Gram-Schmidt)
 #define GCCB_CF_DEG 8              // degree of the later iterations (gain T_8(3) ~ 7e5 < 1/eps_fp32)
 #define GCCB_CF_NSM_A 96            // shared-memory block classes: n <= 96 (3 CTAs/SM) and
-#define GCCB_CF_NSM 160            //   n <= 160 (2 CTAs/SM); larger ego-nets use the L2 workspace
-#define GCCB_CF_MAXIT 16
+#define GCCB_CF_NSM 160            //   n <= 160 (2 CTAs/SM),
+#define GCCB_CF_NSM_C 480          //   n <= 480 (1 CTA of 1024 threads per SM);
+#define GCCB_CF_NSM_D 1000         //   n <= 1000: one block in shared memory (MODE 2); larger: L2 workspace
+#define GCCB_CF_MAXIT 8
 #define GCCB_CF_TOL 4.0e-5f        // max residual ||L x - theta x|| over the wanted pairs
-#define GCCB_CF_STAG 1.5e-4f       // accepted when the residual stagnates below this (fp32 floor)
+#define GCCB_CF_STAG 1.0e-3f       // accepted when the residual stops halving below this: ego-nets whose
+                                   // near-degenerate cluster is wider than the block stall at its spread
 
-// class 0: n <= 64 (dense Jacobi); 1, 2: ChFSI with shared-memory blocks; 3: ChFSI with L2 blocks
+// class 0: n <= 64 (dense Jacobi); 1, 2, 3: ChFSI with shared-memory blocks; 4: ChFSI with L2 blocks
 __device__ __forceinline__ int eig_class(int n) {
-  return n <= GCCB_EIG_SMALL ? 0 : n <= GCCB_CF_NSM_A ? 1 : n <= GCCB_CF_NSM ? 2 : 3;
+  return n <= GCCB_EIG_SMALL ? 0 : n <= GCCB_CF_NSM_A ? 1 : n <= GCCB_CF_NSM ? 2 : n <= GCCB_CF_NSM_C ? 3 :
+         n <= GCCB_CF_NSM_D ? 4 : 5;
 }
 
 // Work lists: worklist[c][i] = slot.  One CTA, deterministic order.  grid = 1, block = 256.
@@ -56,7 +60,7 @@ posenc_classify_kernel(const int64_t* __restrict__ counters, const int32_t* __re
                        int B, int32_t* __restrict__ worklist, int32_t* __restrict__ counts) {
   __shared__ int scan_scratch[33];
   const int tid = threadIdx.x;
-  int base[4] = {0, 0, 0, 0};
+  int base[6] = {0, 0, 0, 0, 0, 0};
   for (int s0 = 0; s0 < 2 * B; s0 += 256) {
     int slot = s0 + tid;
     int cls = -1;
@@ -65,14 +69,14 @@ posenc_classify_kernel(const int64_t* __restrict__ counters, const int32_t* __re
       if (node_off[view * (B + 1) + B] >= 0) cls = eig_class((int)counters[(size_t)slot * 4]);
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 6; ++c) {
       int tot;
       int ex = block_scan_excl(cls == c ? 1 : 0, scan_scratch, &tot);
       if (cls == c) worklist[(size_t)c * 2 * B + base[c] + ex] = slot;
       base[c] += tot;
     }
   }
-  if (tid < 4) counts[tid] = base[tid];
+  if (tid < 6) counts[tid] = base[tid];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -269,22 +273,20 @@ __device__ __forceinline__ void write_features(int n, int k, int pos_dim, int no
   }
 }
 
-// ---- solver (1): dense two-sided Jacobi, n <= 64 ---------------------------------------------------
+// ---- solver (1): dense one-sided Jacobi, n <= 64 ---------------------------------------------------
+// (one-sided on the SPD matrix L + 2I keeps eigenVECTOR accuracy for close eigenvalues -- paths,
+// rings -- where an fp32 two-sided rotation sequence loses it as eps * rotations / gap; fp64 would
+// too be accurate but runs at a small fraction of the fp32 rate on this part)
 __global__ void __launch_bounds__(256)
 posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts,
                      int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
                      const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
                      const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
-                     float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags) {
-  // float64 like the reference's eigsh call (data_util.py:245): with close eigenvalues (paths,
-  // rings) an fp32 rotation sequence loses eigenVECTOR accuracy as eps * rotations / gap
-  constexpr int LD = GCCB_EIG_SMALL + 1;
-  GCCB_DYN_SMEM(double, dsm);
-  double* G = dsm;                          // [64][65]
-  double* V = dsm + GCCB_EIG_SMALL * LD;    // [64][65]
+                     float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags,
+                     int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res) {
+  __shared__ float G[GCCB_EIG_SMALL * GCCB_EIG_SMALL];
+  __shared__ float nrm[GCCB_EIG_SMALL];
   __shared__ float dinv[GCCB_EIG_SMALL];
-  __shared__ double cs[64];
-  __shared__ int pq[32];
   __shared__ int sel[32];
   __shared__ float sgn[32];
   if ((int)blockIdx.x >= counts[0]) return;
@@ -301,10 +303,11 @@ posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __rest
       for (int i = tid; i < pos_dim; i += 256) eigvals[(size_t)slot * pos_dim + i] = 0.f;
     return;
   }
+  const int ld = n;
   const int32_t* v_indptr = b_indptr + (size_t)view * (node_cap + 1);
   const int32_t* v_indices = b_indices + (size_t)view * edge_cap;
   const int32_t* v_deg = sub_deg + (size_t)view * node_cap;
-  for (int i = tid; i < n * LD; i += 256) G[i] = 0.0;
+  for (int i = tid; i < n * ld; i += 256) G[i] = 0.f;
   for (int i = tid; i < n; i += 256) {
     int d = v_deg[noff + i];
     dinv[i] = 1.0f / sqrtf((float)(d < 1 ? 1 : d));   // in_degrees().clip(1) ** -0.5
@@ -315,49 +318,54 @@ posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __rest
     const float di = dinv[i];
     for (int e = beg + lane; e < end; e += 32) {
       int j = v_indices[e] - noff;
-      atomicAdd(&G[j * LD + i], (double)(di * dinv[j]));   // same fp32 weights as the ChFSI path
+      atomicAdd(&G[(size_t)j * ld + i], di * dinv[j]);  // shared-memory adds of exact products
     }
   }
   __syncthreads();
-  for (int i = tid; i < n; i += 256) G[i * LD + i] += 2.0;            // G = L + 2I, positive diagonal
+  for (int i = tid; i < n; i += 256) G[(size_t)i * ld + i] += 2.0f;
   __syncthreads();
-  const int sweeps = jacobi_twosided<256, double>(G, V, cs, pq, n, LD);
+  const int sweeps = jacobi_onesided<2, 256>(G, nrm, n, ld);
   if (sweeps == GCCB_EIG_MAXSWEEP && tid == 0) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
-  // eigenvalue j = G[j][j] - 2; rank, keep the k largest, ascending
+  if (tid == 0) { dbg_iters[slot] = -sweeps; dbg_res[slot] = 0.f; }
+  // eigenvalue of column j = ||g_j|| - 2; rank columns, keep the k largest, ascending
+  const float* mu = nrm;
   for (int j = tid; j < n; j += 256) {
-    const double mj = G[j * LD + j];
+    const float mj = mu[j];
     int rank = 0;
     for (int i = 0; i < n; ++i) {
-      double mi = G[i * LD + i];
+      float mi = mu[i];
       rank += (mi > mj) || (mi == mj && i < j);
     }
     if (rank < k) sel[k - 1 - rank] = j;                // ascending: slot k-1 = largest
   }
   __syncthreads();
   if (eigvals) {
-    // eigenvalues as Rayleigh quotients v^T L v against the ORIGINAL sparse matrix (the rotated
-    // diagonal carries the accumulated rounding of all rotations, ~1e-6..1e-5)
+    // eigenvalues as Rayleigh quotients v^T L v against the ORIGINAL sparse matrix: the column
+    // norms carry the accumulated rounding of ~n rotations per sweep (~1e-5)
     for (int c = warp; c < pos_dim; c += 8) {
       float acc = 0.f;
       if (c < k) {
-        const double* col = V + sel[c] * LD;
+        const float* col = G + (size_t)sel[c] * ld;
         for (int i = lane; i < n; i += 32) {
           const int beg = v_indptr[noff + i], end = v_indptr[noff + i + 1];
           float rowacc = 0.f;
           for (int e = beg; e < end; ++e) {
             int j = v_indices[e] - noff;
-            rowacc = fmaf(dinv[j], (float)col[j], rowacc);
+            rowacc = fmaf(dinv[j], col[j], rowacc);
           }
-          acc = fmaf((float)col[i] * dinv[i], rowacc, acc);
+          acc = fmaf(col[i] * dinv[i], rowacc, acc);
         }
         acc = warp_sum(acc);
+        const float m2 = mu[sel[c]];
+        acc = acc / (m2 * m2);
       }
       if (lane == 0) eigvals[(size_t)slot * pos_dim + c] = acc;
     }
   }
-  const double* Vc = V;
+  const float* Gc = G;
   const int* selc = sel;
-  write_features(n, k, pos_dim, normalize, sgn, out, [&](int c, int r) { return (float)Vc[selc[c] * LD + r]; });
+  write_features(n, k, pos_dim, normalize, sgn, out,
+                 [&](int c, int r) { const int j = selc[c]; return Gc[(size_t)j * ld + r] / mu[j]; });
 }
 
 // ---- solver (2): Chebyshev-filtered subspace iteration, any n > 64 -------------------------------
@@ -381,17 +389,21 @@ __device__ __forceinline__ void spmm_cheb(const SubCsr& S, const float* __restri
     const float dr = S.dinv[r];
     float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
     int e = beg;
-    for (; e + 1 < end; e += 2) {                         // two edges in flight
+    for (; e + 3 < end; e += 4) {                         // four edges (gathers) in flight
       const int j0 = S.indices[e] - S.noff, j1 = S.indices[e + 1] - S.noff;
-      const float w0 = dr * S.dinv[j0], w1 = dr * S.dinv[j1];
-      a0 = fmaf(w0, src[(size_t)j0 * ld + lane], a0);
-      b0 = fmaf(w1, src[(size_t)j1 * ld + lane], b0);
+      const int j2 = S.indices[e + 2] - S.noff, j3 = S.indices[e + 3] - S.noff;
+      const float x0 = src[(size_t)j0 * ld + lane], x1 = src[(size_t)j1 * ld + lane];
+      const float x2 = src[(size_t)j2 * ld + lane], x3 = src[(size_t)j3 * ld + lane];
+      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
       if (hi) {
-        a1 = fmaf(w0, src[(size_t)j0 * ld + 32 + lane], a1);
-        b1 = fmaf(w1, src[(size_t)j1 * ld + 32 + lane], b1);
+        y0 = src[(size_t)j0 * ld + 32 + lane]; y1 = src[(size_t)j1 * ld + 32 + lane];
+        y2 = src[(size_t)j2 * ld + 32 + lane]; y3 = src[(size_t)j3 * ld + 32 + lane];
       }
+      const float w0 = dr * S.dinv[j0], w1 = dr * S.dinv[j1], w2 = dr * S.dinv[j2], w3 = dr * S.dinv[j3];
+      a0 = fmaf(w0, x0, a0); b0 = fmaf(w1, x1, b0); a0 = fmaf(w2, x2, a0); b0 = fmaf(w3, x3, b0);
+      a1 = fmaf(w0, y0, a1); b1 = fmaf(w1, y1, b1); a1 = fmaf(w2, y2, a1); b1 = fmaf(w3, y3, b1);
     }
-    if (e < end) {
+    for (; e < end; ++e) {
       const int j0 = S.indices[e] - S.noff;
       const float w0 = dr * S.dinv[j0];
       a0 = fmaf(w0, src[(size_t)j0 * ld + lane], a0);
@@ -432,16 +444,20 @@ __device__ __forceinline__ void column_sums(int n, float* part /*[32][48]*/, flo
   __syncthreads();
 }
 
-// SMEM_BLOCKS: the two n x 48 blocks live in dynamic shared memory (ld = 49, conflict-free) instead
-// of the L2-resident workspace (ld = 48).  cls selects the work list; blockDim.x = 256 or 1024.
-template <bool SMEM_BLOCKS, int NT>
+// MODE 1: both n x 48 blocks live in dynamic shared memory (ld = 49, conflict-free); MODE 0: both in
+// the L2-resident workspace (ld = 48); MODE 2: X in shared memory, Y in the workspace -- the filter
+// then keeps the block that is GATHERED from in shared memory and swaps rows after every step, so
+// random accesses never leave the SM (ego-nets of 480 < n <= 1000 nodes).
+// cls selects the work list; blockDim.x = 256 or 1024.
+template <int MODE, int NT>
 __global__ void __launch_bounds__(NT)
 posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts, int cls,
                     int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
                     const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
                     const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
                     float* __restrict__ blocks /* [2][2*node_cap*48] */, float* __restrict__ dinv_g /* [2*node_cap] */,
-                    float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags) {
+                    float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags,
+                    int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res) {
   constexpr int CB = GCCB_CF_B, LD = CB + 1;
   GCCB_DYN_SMEM(float, dynsm);
   __shared__ float Gs[CB * LD];                   // Ritz problem
@@ -474,15 +490,18 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
   S.dinv = dinv;
   S.noff = noff; S.n = n;
   const int32_t* v_deg = sub_deg + (size_t)view * node_cap;
-  const int ld = SMEM_BLOCKS ? LD : CB;
+  const int ld = LD;                                    // 49 everywhere (odd: conflict-free in smem)
   float* X;
   float* Y;
-  if (SMEM_BLOCKS) {
+  if (MODE == 1) {
     X = dynsm;
     Y = dynsm + (size_t)n * LD;
+  } else if (MODE == 2) {
+    X = dynsm;
+    Y = blocks + ((size_t)view * node_cap + noff) * LD;
   } else {
-    X = blocks + ((size_t)view * node_cap + noff) * CB;                // n x CB, row-major
-    Y = X + (size_t)2 * node_cap * CB;
+    X = blocks + ((size_t)view * node_cap + noff) * LD;                // n x 48 (ld 49), row-major
+    Y = X + (size_t)2 * node_cap * LD;
   }
   for (int i = tid; i < n; i += NT) {
     int d = v_deg[noff + i];
@@ -497,7 +516,8 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
   float cut = 0.0f;                                     // the filter suppresses [-1, cut]
   float prev_worst = 3.0e38f;
   bool converged = false;
-  for (int iter = 0; iter < GCCB_CF_MAXIT && !converged; ++iter) {
+  int iter = 0;
+  for (; iter < GCCB_CF_MAXIT && !converged; ++iter) {
     // ---- Chebyshev filter on [-1, cut] (scaled three-term recurrence) -----------------------------
     {
       const int deg = iter == 0 ? GCCB_CF_DEG0 : GCCB_CF_DEG;
@@ -506,6 +526,31 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
       const float sigma1 = sigma;
       spmm_cheb(S, X, Y, ld, sigma1 / e, cen, 0.f);                           // Y1
       __syncthreads();
+      if (MODE == 2) {
+        // cur must stay in shared memory: swap rows X <-> Y (now X = Y1 = cur, Y = prev)
+        for (int r = warp; r < n; r += NW) {
+          const size_t o = (size_t)r * ld + lane;
+          float a = X[o], b = Y[o], a1 = 0.f, b1 = 0.f;
+          if (hi) { a1 = X[o + 32]; b1 = Y[o + 32]; }
+          X[o] = b; Y[o] = a;
+          if (hi) { X[o + 32] = b1; Y[o + 32] = a1; }
+        }
+        __syncthreads();
+        for (int i = 2; i <= deg; ++i) {
+          const float sigma2 = 1.0f / (2.0f / sigma1 - sigma);
+          spmm_cheb(S, X, Y, ld, 2.0f * sigma2 / e, cen, sigma * sigma2);     // new overwrites prev (in Y)
+          __syncthreads();
+          for (int r = warp; r < n; r += NW) {                                // swap: X = new, Y = old cur
+            const size_t o = (size_t)r * ld + lane;
+            float a = X[o], b = Y[o], a1 = 0.f, b1 = 0.f;
+            if (hi) { a1 = X[o + 32]; b1 = Y[o + 32]; }
+            X[o] = b; Y[o] = a;
+            if (hi) { X[o + 32] = b1; Y[o + 32] = a1; }
+          }
+          __syncthreads();
+          sigma = sigma2;
+        }
+      } else {
       float* cur = Y; float* prev = X;
       for (int i = 2; i <= deg; ++i) {
         const float sigma2 = 1.0f / (2.0f / sigma1 - sigma);
@@ -515,6 +560,7 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
         sigma = sigma2;
       }
       X = cur; Y = prev;                                 // filtered block in X, Y is scratch
+      }
     }
     // ---- CGS2: orthonormalise the columns of X in place (row-major: all dots of a column at once)
     for (int j = 0; j < CB; ++j) {
@@ -651,12 +697,13 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
     __syncthreads();
     const float w_all = s_bc[0];
     // converged, or stagnating at the fp32 noise floor of the Rayleigh-Ritz residual
-    converged = (w_all < GCCB_CF_TOL) || (w_all < GCCB_CF_STAG && w_all > 0.5f * prev_worst);
+    converged = (w_all < GCCB_CF_TOL) || (iter >= 2 && w_all < GCCB_CF_STAG && w_all > 0.5f * prev_worst);
     prev_worst = w_all;
     cut = fminf(fmaxf(s_bc[1], -0.9f), 0.95f);          // smallest Ritz value of the block
     __syncthreads();
   }
   if (!converged && tid == 0) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
+  if (tid == 0) { dbg_iters[slot] = iter; dbg_res[slot] = prev_worst; }
   // columns 0..k-1 of X hold the k largest Ritz pairs in DESCENDING order; emit ascending
   // (data_util.py: eigsh(which='LA') returns ascending eigenvalues)
   if (eigvals)
@@ -670,12 +717,12 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
 
 using namespace gccb;
 
-// workspace: worklist[4][2B] ints | counts[4] ints | pad | dinv[2*node_cap] | blocks[2][2*node_cap*48] floats
-static size_t posenc_ws_ints(int B) { return (((size_t)4 * 2 * B + 4) + 63) & ~(size_t)63; }
+// workspace: worklist[6][2B] | counts[6] | iters[2B] (ints) | pad | res[2B] | dinv[2*node_cap] | blocks[2][2*node_cap*49] (floats)
+static size_t posenc_ws_ints(int B) { return (((size_t)6 * 2 * B + 6 + 2 * B) + 63) & ~(size_t)63; }
 
 extern "C" size_t gccb_posenc_workspace(int32_t batch, int32_t node_cap) {
   return posenc_ws_ints(batch) * sizeof(int32_t) +
-         ((size_t)2 * node_cap + (size_t)2 * 2 * node_cap * GCCB_CF_B) * sizeof(float);
+         ((size_t)2 * batch + (size_t)2 * node_cap + (size_t)2 * 2 * node_cap * (GCCB_CF_B + 1)) * sizeof(float);
 }
 
 extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t normalize,
@@ -691,25 +738,31 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
     return GCCB_ERR_CAPACITY;
   }
   int32_t* worklist = (int32_t*)workspace;
-  int32_t* counts = worklist + (size_t)4 * 2 * B;
-  float* dinv = (float*)((int32_t*)workspace + posenc_ws_ints(B));
+  int32_t* counts = worklist + (size_t)6 * 2 * B;
+  int32_t* dbg_iters = counts + 6;                       // per slot: ChFSI outer iterations (Jacobi: -sweeps)
+  float* dbg_res = (float*)((int32_t*)workspace + posenc_ws_ints(B));      // per slot: final residual
+  float* dinv = dbg_res + (size_t)2 * B;
   float* blocks = dinv + (size_t)2 * batch->node_cap;
   GCCB_LAUNCH(posenc_classify_kernel, 1, 256, 0, stream, batch->counters, batch->node_off, B, worklist, counts);
-  auto kbig = posenc_chfsi_kernel<false, 1024>;
-  auto kmid = posenc_chfsi_kernel<true, 256>;
+  auto kgiant = posenc_chfsi_kernel<0, 1024>;
+  auto khuge = posenc_chfsi_kernel<2, 1024>;
+  auto kbig = posenc_chfsi_kernel<1, 1024>;
+  auto kmid = posenc_chfsi_kernel<1, 256>;
   auto ksmall = posenc_jacobi_kernel;
   const size_t s_a = (size_t)2 * GCCB_CF_NSM_A * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_b = (size_t)2 * GCCB_CF_NSM * (GCCB_CF_B + 1) * sizeof(float);
-  const size_t ssmall = (size_t)2 * GCCB_EIG_SMALL * (GCCB_EIG_SMALL + 1) * sizeof(double);
+  const size_t s_c = (size_t)2 * GCCB_CF_NSM_C * (GCCB_CF_B + 1) * sizeof(float);
+  const size_t s_d = (size_t)GCCB_CF_NSM_D * (GCCB_CF_B + 1) * sizeof(float);
+  cudaFuncSetAttribute(khuge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_d);
   cudaFuncSetAttribute(kmid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_b);
-  cudaFuncSetAttribute(ksmall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmall);
-  // The four size classes are independent: fork them over side streams (event fork/join, legal
-  // inside CUDA-graph capture) so that the few long-running large ego-nets overlap the many small ones.
+  cudaFuncSetAttribute(kbig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_c);
+  // The size classes are independent: fork them over side streams (event fork/join, legal inside
+  // CUDA-graph capture) so that the few long-running large ego-nets overlap the many small ones.
 #ifndef GCCB_EMU
-  static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
-  static cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  static cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  static cudaEvent_t ev_fork = nullptr, ev_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (!side[0]) {
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 5; ++i) {
       cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
       cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
     }
@@ -717,25 +770,23 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   }
   cudaStream_t main_s = (cudaStream_t)stream;
   cudaEventRecord(ev_fork, main_s);
-  for (int i = 0; i < 3; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
-  gccb_stream_t s_big = side[0], s_mid2 = side[1], s_small = side[2], s_mid1 = stream;
+  for (int i = 0; i < 5; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
+  gccb_stream_t s_giant = side[4], s_huge = side[0], s_big = side[1], s_mid2 = side[2], s_small = side[3], s_mid1 = stream;
 #else
-  gccb_stream_t s_big = stream, s_mid2 = stream, s_small = stream, s_mid1 = stream;
+  gccb_stream_t s_giant = stream, s_huge = stream, s_big = stream, s_mid2 = stream, s_small = stream, s_mid1 = stream;
 #endif
-  GCCB_LAUNCH(kbig, 2 * B, 1024, 0, s_big, worklist, counts, 3, B, batch->node_cap, batch->edge_cap,
-              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
-              pos, eigvals, batch->flags);
-  GCCB_LAUNCH(kmid, 2 * B, 256, s_b, s_mid2, worklist, counts, 2, B, batch->node_cap, batch->edge_cap,
-              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
-              pos, eigvals, batch->flags);
-  GCCB_LAUNCH(kmid, 2 * B, 256, s_a, s_mid1, worklist, counts, 1, B, batch->node_cap, batch->edge_cap,
-              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv,
-              pos, eigvals, batch->flags);
-  GCCB_LAUNCH(ksmall, 2 * B, 256, ssmall, s_small, worklist, counts, B, batch->node_cap, batch->edge_cap,
+#define GCCB_PE_ARGS(cls) worklist, counts, cls, B, batch->node_cap, batch->edge_cap, batch->node_off, batch->indptr, \
+    batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv, pos, eigvals, batch->flags, dbg_iters, dbg_res
+  GCCB_LAUNCH(kgiant, 2 * B, 1024, 0, s_giant, GCCB_PE_ARGS(5));
+  GCCB_LAUNCH(khuge, 2 * B, 1024, s_d, s_huge, GCCB_PE_ARGS(4));
+  GCCB_LAUNCH(kbig, 2 * B, 1024, s_c, s_big, GCCB_PE_ARGS(3));
+  GCCB_LAUNCH(kmid, 2 * B, 256, s_b, s_mid2, GCCB_PE_ARGS(2));
+  GCCB_LAUNCH(kmid, 2 * B, 256, s_a, s_mid1, GCCB_PE_ARGS(1));
+  GCCB_LAUNCH(ksmall, 2 * B, 256, 0, s_small, worklist, counts, B, batch->node_cap, batch->edge_cap,
               batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, pos, eigvals,
-              batch->flags);
+              batch->flags, dbg_iters, dbg_res);
 #ifndef GCCB_EMU
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 5; ++i) {
     cudaEventRecord(ev_join[i], side[i]);
     cudaStreamWaitEvent(main_s, ev_join[i], 0);
   }

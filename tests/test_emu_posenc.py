@@ -111,6 +111,15 @@ def test_posenc_matches_reference_golden():
     assert checked >= 8
 
 
+def test_huge_egonet_one_block_in_shared_memory():
+    g = synthetic.chung_lu(560, 1500, exponent=0.8, seed=3)    # 480 < n <= 1000: X in smem, Y in workspace
+    assert 480 < g.num_nodes <= 1000
+    views = [[_sub(g)], [_sub(synthetic.path_graph(5))]]
+    b, pos, eig = _posenc(views, normalize=0)
+    assert b.flags[0] == 0
+    _check_spectral(views[0][0], pos[0, :g.num_nodes], eig[0])
+
+
 def test_large_egonet_goes_through_chfsi():
     g = synthetic.chung_lu(260, 700, seed=3)              # hub-and-leaves: large degenerate cluster
     assert g.num_nodes > 200

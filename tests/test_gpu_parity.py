@@ -92,7 +92,7 @@ def _spectral_check(sub, u, lam, tol_l=2e-5):
     w, _ = opos.eig_topk_exact(lap, k)
     assert np.allclose(lam[:k], w, atol=tol_l), np.abs(lam[:k] - w).max()
     theta, resid, ortho = opos.spectral_report(lap, u[:, :k].astype(np.float64))
-    assert resid.max() < 2e-4 and ortho < 1e-4, (resid.max(), ortho)   # fp32 Rayleigh-Ritz floor
+    assert resid.max() < 3e-4 and ortho < 1e-4, (resid.max(), ortho)   # fp32 Rayleigh-Ritz floor
     assert np.all(u[:, k:] == 0)
 
 
