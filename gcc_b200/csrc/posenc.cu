@@ -42,7 +42,7 @@ namespace gccb {
 #define GCCB_CF_NSM_A 96            // shared-memory block classes: n <= 96 (3 CTAs/SM) and
 #define GCCB_CF_NSM 160            //   n <= 160 (2 CTAs/SM),
 #define GCCB_CF_NSM_C 480          //   n <= 480 (1 CTA of 1024 threads per SM);
-#define GCCB_CF_NSM_D 1000         //   n <= 1000: one block in shared memory (MODE 2); larger: L2 workspace
+#define GCCB_CF_NSM_D 3840         //   n <= 3840: cluster of 8 CTAs (DSMEM); larger: L2 workspace
 #define GCCB_CF_MAXIT 8
 #define GCCB_CF_TOL 4.0e-5f        // max residual ||L x - theta x|| over the wanted pairs
 #define GCCB_CF_STAG 1.0e-3f       // accepted when the residual stops halving below this: ego-nets whose
@@ -713,6 +713,455 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
                  [&](int c, int r) { return Xf[(size_t)r * ld + (k - 1 - c)]; });
 }
 
+
+// ---- solver (3): ChFSI over a thread-block cluster (distributed shared memory), n > 480 ------------
+// A hub ego-net (up to ~3400 vertices at the C2 walk budget) would otherwise keep ONE SM busy for
+// tens of milliseconds while 147 idle.  Here a cluster of CS CTAs owns it: rows are partitioned,
+// each CTA keeps its slice of both n x 48 blocks in its own shared memory, neighbour rows are
+// gathered from the owning CTA through DSMEM, column reductions / the 48 x 48 projected matrix are
+// all-reduced through a small exchange buffer, and every CTA solves the (identical) Ritz problem
+// redundantly.  With CS = 1 the code degenerates to the single-CTA algorithm (that is what the CPU
+// emulator exercises); the cluster paths are validated on the GPU by the spectral parity tests.
+#ifndef GCCB_EMU
+}  // namespace gccb
+#include <cooperative_groups.h>
+namespace gccb {
+namespace cg = cooperative_groups;
+#endif
+
+template <int CS> __device__ __forceinline__ int cl_rank() {
+#ifndef GCCB_EMU
+  if (CS > 1) return (int)cg::this_cluster().block_rank();
+#endif
+  return 0;
+}
+template <int CS> __device__ __forceinline__ void cl_sync() {
+#ifndef GCCB_EMU
+  if (CS > 1) { cg::this_cluster().sync(); return; }
+#endif
+  __syncthreads();
+}
+template <int CS> __device__ __forceinline__ const float* cl_map(const float* p, int rank) {
+#ifndef GCCB_EMU
+  if (CS > 1) return (const float*)cg::this_cluster().map_shared_rank((void*)p, (unsigned)rank);
+#endif
+  return p;
+}
+
+#define GCCB_CL_HEAVY 192          // rows with more neighbours are processed by the whole CTA
+#define GCCB_CL_MAXHEAVY 16
+
+template <int NT, int CS>
+struct ClCtx {
+  const int32_t* indptr; const int32_t* indices; const float* dinv;
+  int noff, n, R, rank, r_lo, nloc, ld;
+  float* part;          // [32][48] block scratch
+  float* xch;           // [2][48] cluster exchange (own shared memory)
+  int xbuf;
+  const int* heavy; int nheavy;
+};
+
+// row j of a row-partitioned block whose local slice starts at `base`
+template <int NT, int CS>
+__device__ __forceinline__ const float* cl_row(const ClCtx<NT, CS>& c, const float* base, int j) {
+  const int owner = j / c.R, loc = j - owner * c.R;
+  const float* p = base + (size_t)loc * c.ld;
+  return owner == c.rank ? p : cl_map<CS>(p, owner);
+}
+
+// dst_loc[r][c] = alpha * (sum_j w_rj src[j][c] - cen * src[r][c]) - beta * dst_loc[r][c] over OWNED rows
+template <int NT, int CS>
+__device__ __forceinline__ void cl_spmm(const ClCtx<NT, CS>& C, const float* src, float* dst, float alpha,
+                                        float cen, float beta) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = NT / 32;
+  const bool hi = lane < GCCB_CF_B - 32;
+  for (int rl = warp; rl < C.nloc; rl += NW) {
+    const int r = C.r_lo + rl;
+    const int beg = C.indptr[C.noff + r], end = C.indptr[C.noff + r + 1];
+    if (end - beg > GCCB_CL_HEAVY && C.nheavy > 0) {
+      bool listed = false;
+      for (int h = 0; h < C.nheavy; ++h) listed |= C.heavy[h] == rl;
+      if (listed) continue;                              // done cooperatively below
+    }
+    const float dr = C.dinv[r];
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    int e = beg;
+    for (; e + 3 < end; e += 4) {
+      const int j0 = C.indices[e] - C.noff, j1 = C.indices[e + 1] - C.noff;
+      const int j2 = C.indices[e + 2] - C.noff, j3 = C.indices[e + 3] - C.noff;
+      const float* p0 = cl_row(C, src, j0); const float* p1 = cl_row(C, src, j1);
+      const float* p2 = cl_row(C, src, j2); const float* p3 = cl_row(C, src, j3);
+      const float x0 = p0[lane], x1 = p1[lane], x2 = p2[lane], x3 = p3[lane];
+      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+      if (hi) { y0 = p0[32 + lane]; y1 = p1[32 + lane]; y2 = p2[32 + lane]; y3 = p3[32 + lane]; }
+      const float w0 = dr * C.dinv[j0], w1 = dr * C.dinv[j1], w2 = dr * C.dinv[j2], w3 = dr * C.dinv[j3];
+      a0 = fmaf(w0, x0, a0); b0 = fmaf(w1, x1, b0); a0 = fmaf(w2, x2, a0); b0 = fmaf(w3, x3, b0);
+      a1 = fmaf(w0, y0, a1); b1 = fmaf(w1, y1, b1); a1 = fmaf(w2, y2, a1); b1 = fmaf(w3, y3, b1);
+    }
+    for (; e < end; ++e) {
+      const int j0 = C.indices[e] - C.noff;
+      const float* p0 = cl_row(C, src, j0);
+      const float w0 = dr * C.dinv[j0];
+      a0 = fmaf(w0, p0[lane], a0);
+      if (hi) a1 = fmaf(w0, p0[32 + lane], a1);
+    }
+    a0 += b0; a1 += b1;
+    const size_t o = (size_t)rl * C.ld + lane;
+    float v = alpha * (a0 - cen * src[o]);
+    if (beta != 0.f) v -= beta * dst[o];
+    dst[o] = v;
+    if (hi) {
+      float v1 = alpha * (a1 - cen * src[o + 32]);
+      if (beta != 0.f) v1 -= beta * dst[o + 32];
+      dst[o + 32] = v1;
+    }
+  }
+  // hub rows: every warp takes a slice of the neighbour list, partial rows meet in part[][]
+  for (int h = 0; h < C.nheavy; ++h) {
+    const int rl = C.heavy[h], r = C.r_lo + rl;
+    const int beg = C.indptr[C.noff + r], end = C.indptr[C.noff + r + 1];
+    const int per = (end - beg + NW - 1) / NW;
+    const int e0 = beg + warp * per, e1 = min(end, e0 + per);
+    const float dr = C.dinv[r];
+    float a0 = 0.f, a1 = 0.f;
+    for (int e = e0; e < e1; ++e) {
+      const int j0 = C.indices[e] - C.noff;
+      const float* p0 = cl_row(C, src, j0);
+      const float w0 = dr * C.dinv[j0];
+      a0 = fmaf(w0, p0[lane], a0);
+      if (hi) a1 = fmaf(w0, p0[32 + lane], a1);
+    }
+    __syncthreads();                                     // part[] free
+    C.part[warp * GCCB_CF_B + lane] = a0;
+    if (hi) C.part[warp * GCCB_CF_B + 32 + lane] = a1;
+    __syncthreads();
+    for (int c = threadIdx.x; c < GCCB_CF_B; c += NT) {
+      float sacc = 0.f;
+      for (int w = 0; w < NW; ++w) sacc += C.part[w * GCCB_CF_B + c];
+      const size_t o = (size_t)rl * C.ld + c;
+      float v = alpha * (sacc - cen * src[o]);
+      if (beta != 0.f) v -= beta * dst[o];
+      dst[o] = v;
+    }
+  }
+}
+
+// cluster-wide per-column sums of f(local row, column) -> out[48] (identical on every CTA)
+template <int NT, int CS, class RowFn>
+__device__ __forceinline__ void cl_column_sums(ClCtx<NT, CS>& C, float* out, RowFn f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = NT / 32;
+  const bool hi = lane < GCCB_CF_B - 32;
+  float a0 = 0.f, a1 = 0.f;
+  for (int rl = warp; rl < C.nloc; rl += NW) {
+    a0 += f(rl, lane);
+    if (hi) a1 += f(rl, 32 + lane);
+  }
+  C.part[warp * GCCB_CF_B + lane] = a0;
+  if (hi) C.part[warp * GCCB_CF_B + 32 + lane] = a1;
+  __syncthreads();
+  float* mine = C.xch + C.xbuf * GCCB_CF_B;
+  for (int c = threadIdx.x; c < GCCB_CF_B; c += NT) {
+    float sacc = 0.f;
+    for (int w = 0; w < NW; ++w) sacc += C.part[w * GCCB_CF_B + c];
+    if (CS > 1) mine[c] = sacc; else out[c] = sacc;
+  }
+  if (CS > 1) {
+    cl_sync<CS>();
+    for (int c = threadIdx.x; c < GCCB_CF_B; c += NT) {
+      float sacc = 0.f;
+      for (int q = 0; q < CS; ++q) sacc += cl_map<CS>(mine, q)[c];     // fixed rank order: deterministic
+      out[c] = sacc;
+    }
+    C.xbuf ^= 1;
+  }
+  __syncthreads();
+}
+
+template <int NT, int CS>
+__global__ void __launch_bounds__(NT)
+posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts, int cls,
+                            int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
+                            const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
+                            const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
+                            float* __restrict__ dinv_g, float* __restrict__ pos, float* __restrict__ eigvals,
+                            int32_t* __restrict__ flags, int32_t* __restrict__ dbg_iters,
+                            float* __restrict__ dbg_res) {
+  constexpr int CB = GCCB_CF_B, LD = CB + 1, NW = NT / 32;
+  GCCB_DYN_SMEM(float, dynsm);
+  __shared__ float Gs[CB * LD];                   // Ritz problem
+  __shared__ float Hp[CB * LD];                   // this CTA's partial of H (read by the others)
+  __shared__ float WT[32 * (CB + 1) * 2];         // union: Ritz vectors Ws[CB*LD] | tiles [2][32][CB+1]
+  __shared__ float part[32 * CB];
+  __shared__ float xch[2 * CB + 8];
+  __shared__ float rdot[CB];
+  __shared__ float theta[CB];
+  __shared__ float resid[CB];
+  __shared__ float cs[64];
+  __shared__ int pq[32];
+  __shared__ int perm[CB];
+  __shared__ int heavy[GCCB_CL_MAXHEAVY];
+  __shared__ int s_nheavy;
+  __shared__ float s_bc[2];
+  __shared__ float sgn[32];
+  float* Ws = WT;
+  float (*tile)[32][CB + 1] = reinterpret_cast<float (*)[32][CB + 1]>(WT);
+  for (int item = blockIdx.x / CS; item < counts[cls]; item += gridDim.x / CS) {   // uniform over the cluster
+  const int slot = worklist[(size_t)cls * 2 * B + item];
+  const int view = slot / B, g = slot - view * B;
+  const int noff = node_off[view * (B + 1) + g];
+  const int n = node_off[view * (B + 1) + g + 1] - noff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool hi = lane < CB - 32;
+  const int k = min(n - 2, pos_dim);
+  ClCtx<NT, CS> C;
+  C.indptr = b_indptr + (size_t)view * (node_cap + 1);
+  C.indices = b_indices + (size_t)view * edge_cap;
+  float* dinv = dinv_g + (size_t)view * node_cap + noff;
+  C.dinv = dinv;
+  C.noff = noff; C.n = n;
+  C.R = (n + CS - 1) / CS;
+  C.rank = cl_rank<CS>();
+  C.r_lo = C.rank * C.R;
+  C.nloc = max(0, min(n, C.r_lo + C.R) - C.r_lo);
+  C.ld = LD;
+  C.part = part; C.xch = xch; C.xbuf = 0; C.heavy = heavy;
+  const int nloc = C.nloc, r_lo = C.r_lo, ld = LD;
+  float* X = dynsm;                                     // local slices: R x 49 each
+  float* Y = dynsm + (size_t)C.R * LD;
+  const int32_t* v_deg = sub_deg + (size_t)view * node_cap;
+  if (tid == 0) s_nheavy = 0;
+  __syncthreads();
+  for (int rl = tid; rl < nloc; rl += NT) {
+    int d = v_deg[noff + r_lo + rl];
+    if (d > GCCB_CL_HEAVY) {
+      int h = atomicAdd(&s_nheavy, 1);
+      if (h < GCCB_CL_MAXHEAVY) heavy[h] = rl;
+    }
+  }
+  // every CTA needs all of dinv (neighbour weights): each writes its own rows, visible after the sync
+  for (int rl = tid; rl < nloc; rl += NT) {
+    int d = v_deg[noff + r_lo + rl];
+    dinv[r_lo + rl] = 1.0f / sqrtf((float)(d < 1 ? 1 : d));
+  }
+  for (int i = tid; i < nloc * CB; i += NT) {
+    const int rl = i / CB, c = i - rl * CB;
+    const uint32_t gi = (uint32_t)((r_lo + rl) * CB + c);           // same stream as the single-CTA kernel
+    u32x4 w = philox4x32_10(gi, (uint32_t)n, 0x51ED270Bu, 3u, 0xC0FFEEu, 0x5EEDu);
+    X[(size_t)rl * ld + c] = (float)(int32_t)w.x * (1.0f / 2147483648.0f);
+  }
+  __threadfence();                                       // dinv[] (global) before the other CTAs read it
+  cl_sync<CS>();
+  C.nheavy = min(s_nheavy, GCCB_CL_MAXHEAVY);
+  float cut = 0.0f, prev_worst = 3.0e38f;
+  bool converged = false;
+  int iter = 0;
+  for (; iter < GCCB_CF_MAXIT && !converged; ++iter) {
+    {   // ---- Chebyshev filter ---------------------------------------------------------------------
+      const int deg = iter == 0 ? GCCB_CF_DEG0 : GCCB_CF_DEG;
+      const float e = (cut + 1.0f) * 0.5f, cen = (cut - 1.0f) * 0.5f;
+      float sigma = e / (1.0f - cen);
+      const float sigma1 = sigma;
+      cl_spmm(C, X, Y, sigma1 / e, cen, 0.f);
+      cl_sync<CS>();
+      float* cur = Y; float* prev = X;
+      for (int i = 2; i <= deg; ++i) {
+        const float sigma2 = 1.0f / (2.0f / sigma1 - sigma);
+        cl_spmm(C, cur, prev, 2.0f * sigma2 / e, cen, sigma * sigma2);
+        cl_sync<CS>();
+        float* t = cur; cur = prev; prev = t;
+        sigma = sigma2;
+      }
+      X = cur; Y = prev;
+    }
+    // ---- CGS2 over the cluster --------------------------------------------------------------------
+    for (int j = 0; j < CB; ++j) {
+      for (int pass = 0; pass < 2; ++pass) {
+        const float* Xc = X;
+        cl_column_sums(C, rdot, [&](int rl, int c) { return Xc[(size_t)rl * ld + c] * Xc[(size_t)rl * ld + j]; });
+        for (int rl = tid; rl < nloc; rl += NT) {
+          float* row = X + (size_t)rl * ld;
+          float v0 = row[j], v1 = 0.f;
+          int i = 0;
+          for (; i + 1 < j; i += 2) {
+            v0 = fmaf(-rdot[i], row[i], v0);
+            v1 = fmaf(-rdot[i + 1], row[i + 1], v1);
+          }
+          if (i < j) v0 = fmaf(-rdot[i], row[i], v0);
+          row[j] = v0 + v1;
+        }
+        __syncthreads();
+      }
+      {
+        const float* Xc = X;
+        cl_column_sums(C, theta, [&](int rl, int c) { return c == j ? Xc[(size_t)rl * ld + j] * Xc[(size_t)rl * ld + j] : 0.f; });
+      }
+      const float t = theta[j];
+      const float inv = t > 1e-30f ? 1.0f / sqrtf(t) : 0.f;
+      for (int rl = tid; rl < nloc; rl += NT) X[(size_t)rl * ld + j] *= inv;
+      __syncthreads();
+    }
+    // ---- Z = L Q, H = Q^T Z (partial per CTA, summed over the cluster) -------------------------------
+    cl_sync<CS>();                                       // every slice of Q final before remote gathers
+    cl_spmm(C, X, Y, 1.0f, 0.f, 0.f);
+    __syncthreads();
+    {
+      const int ti = (tid & 255) >> 4, tj = tid & 15;
+      float acc[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 3; ++b2) acc[a][b2] = 0.f;
+      for (int r0 = 0; r0 < nloc; r0 += 32) {
+        for (int idx = tid; idx < 32 * CB; idx += NT) {
+          const int rr = idx / CB, c = idx - rr * CB;
+          const int rl = r0 + rr;
+          tile[0][rr][c] = rl < nloc ? X[(size_t)rl * ld + c] : 0.f;
+          tile[1][rr][c] = rl < nloc ? Y[(size_t)rl * ld + c] : 0.f;
+        }
+        __syncthreads();
+        if (tid < 256) {
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            float qa[3], zb[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { qa[a] = tile[0][rr][ti * 3 + a]; zb[a] = tile[1][rr][tj * 3 + a]; }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+              for (int b2 = 0; b2 < 3; ++b2) acc[a][b2] = fmaf(qa[a], zb[b2], acc[a][b2]);
+          }
+        }
+        __syncthreads();
+      }
+      if (tid < 256) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b2 = 0; b2 < 3; ++b2) Hp[(tj * 3 + b2) * LD + ti * 3 + a] = acc[a][b2];
+      }
+      cl_sync<CS>();
+      for (int idx = tid; idx < CB * CB; idx += NT) {   // all-reduce of the partials, fixed rank order
+        const int j = idx / CB, i = idx - j * CB;
+        float sacc = 0.f;
+        for (int q = 0; q < CS; ++q) sacc += cl_map<CS>(Hp, q)[j * LD + i];
+        Gs[j * LD + i] = sacc;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < CB * CB; idx += NT) {   // G = sym(H) + 2 I
+        const int i = idx / CB, j = idx - i * CB;
+        if (i < j) {
+          float v = 0.5f * (Gs[j * LD + i] + Gs[i * LD + j]);
+          Gs[j * LD + i] = v;
+          Gs[i * LD + j] = v;
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < CB; i += NT) Gs[i * LD + i] += 2.0f;
+      __syncthreads();
+    }
+    jacobi_twosided<NT, float>(Gs, Ws, cs, pq, CB, LD);   // redundant on every CTA, bit-identical
+    for (int j = tid; j < CB; j += NT) {
+      const float mj = Gs[j * LD + j];
+      int rank = 0;
+      for (int i = 0; i < CB; ++i) {
+        float mi = Gs[i * LD + i];
+        rank += (mi > mj) || (mi == mj && i < j);
+      }
+      perm[rank] = j;
+    }
+    __syncthreads();
+    for (int rl = warp; rl < nloc; rl += NW) {            // X <- Q W[:, perm] on the owned rows
+      const float* w0 = Ws + perm[lane] * LD;
+      const float* w1 = Ws + perm[hi ? 32 + lane : 0] * LD;
+      const float* row = X + (size_t)rl * ld;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < CB; ++i) {
+        const float q = row[i];
+        a0 = fmaf(q, w0[i], a0);
+        a1 = fmaf(q, w1[i], a1);
+      }
+      __syncwarp();
+      X[(size_t)rl * ld + lane] = a0;
+      if (hi) X[(size_t)rl * ld + 32 + lane] = a1;
+    }
+    cl_sync<CS>();                                       // also orders the Hp reads before its next write
+    cl_spmm(C, X, Y, 1.0f, 0.f, 0.f);                    // Y = L X
+    __syncthreads();
+    {
+      const float* Xc = X; const float* Yc = Y;
+      cl_column_sums(C, theta, [&](int rl, int c) { return Xc[(size_t)rl * ld + c] * Yc[(size_t)rl * ld + c]; });
+      cl_column_sums(C, resid, [&](int rl, int c) {
+        float d = Yc[(size_t)rl * ld + c] - theta[c] * Xc[(size_t)rl * ld + c];
+        return d * d;
+      });
+    }
+    if (tid == 0) {
+      float w = 0.f, lo = theta[0];
+      for (int c = 0; c < k; ++c) w = fmaxf(w, resid[c]);
+      for (int i = 1; i < CB; ++i) lo = fminf(lo, theta[i]);
+      s_bc[0] = sqrtf(w);
+      s_bc[1] = lo;
+    }
+    __syncthreads();
+    const float w_all = s_bc[0];
+    converged = (w_all < GCCB_CF_TOL) || (iter >= 2 && w_all < GCCB_CF_STAG && w_all > 0.5f * prev_worst);
+    prev_worst = w_all;
+    cut = fminf(fmaxf(s_bc[1], -0.9f), 0.95f);
+    __syncthreads();
+  }
+  if (C.rank == 0 && tid == 0) {
+    if (!converged) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
+    dbg_iters[slot] = iter; dbg_res[slot] = prev_worst;
+  }
+  if (eigvals && C.rank == 0)
+    for (int c = tid; c < pos_dim; c += NT) eigvals[(size_t)slot * pos_dim + c] = c < k ? theta[k - 1 - c] : 0.f;
+  // deterministic sign: largest-|.| component over ALL rows (lowest row on ties) positive
+  {
+    float* best = part;                 // [48] value of max |x|, [48..96) row, [96..144) signed value
+    for (int c = warp; c < k; c += NW) {
+      float bb = -1.f, bval = 0.f; int brow = 0x7fffffff;
+      for (int rl = lane; rl < nloc; rl += 32) {
+        float x = X[(size_t)rl * ld + (k - 1 - c)], a = fabsf(x);
+        if (a > bb) { bb = a; brow = r_lo + rl; bval = x; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, bb, o);
+        int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+        float ov = __shfl_xor_sync(0xffffffffu, bval, o);
+        if (ob > bb || (ob == bb && orow < brow)) { bb = ob; brow = orow; bval = ov; }
+      }
+      if (lane == 0) { best[c] = bb; best[48 + c] = __int_as_float(brow); best[96 + c] = bval; }
+    }
+    cl_sync<CS>();
+    for (int c = tid; c < k; c += NT) {
+      float bb = -1.f, bval = 0.f; int brow = 0x7fffffff;
+      for (int q = 0; q < CS; ++q) {
+        const float* rb = cl_map<CS>(best, q);
+        float ob = rb[c]; int orow = __float_as_int(rb[48 + c]); float ov = rb[96 + c];
+        if (ob > bb || (ob == bb && orow < brow)) { bb = ob; brow = orow; bval = ov; }
+      }
+      sgn[c] = bval < 0.f ? -1.0f : 1.0f;
+    }
+    __syncthreads();
+  }
+  float* out = pos + ((size_t)view * node_cap + noff) * pos_dim;
+  for (int rl = warp; rl < nloc; rl += NW) {
+    float u = 0.f;
+    if (lane < k) u = sgn[lane] * X[(size_t)rl * ld + (k - 1 - lane)];
+    if (normalize) {
+      float ss = warp_sum(u * u);
+      if (ss > 0.f) u = u / sqrtf(ss);
+    }
+    if (lane < pos_dim) out[(size_t)(r_lo + rl) * pos_dim + lane] = u;
+  }
+  cl_sync<CS>();                                         // nobody leaves while its shared memory is still read
+  }
+}
+
 }  // namespace gccb
 
 using namespace gccb;
@@ -745,17 +1194,22 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   float* blocks = dinv + (size_t)2 * batch->node_cap;
   GCCB_LAUNCH(posenc_classify_kernel, 1, 256, 0, stream, batch->counters, batch->node_off, B, worklist, counts);
   auto kgiant = posenc_chfsi_kernel<0, 1024>;
-  auto khuge = posenc_chfsi_kernel<2, 1024>;
+#ifndef GCCB_EMU
+  constexpr int CLUSTER = 8;
+#else
+  constexpr int CLUSTER = 1;                             // the emulator runs the same kernel with one CTA
+#endif
+  auto khuge = posenc_chfsi_cluster_kernel<1024, CLUSTER>;
   auto kbig = posenc_chfsi_kernel<1, 1024>;
   auto kmid = posenc_chfsi_kernel<1, 256>;
   auto ksmall = posenc_jacobi_kernel;
   const size_t s_a = (size_t)2 * GCCB_CF_NSM_A * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_b = (size_t)2 * GCCB_CF_NSM * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_c = (size_t)2 * GCCB_CF_NSM_C * (GCCB_CF_B + 1) * sizeof(float);
-  const size_t s_d = (size_t)GCCB_CF_NSM_D * (GCCB_CF_B + 1) * sizeof(float);
-  cudaFuncSetAttribute(khuge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_d);
+  const size_t s_d = (size_t)2 * ((GCCB_CF_NSM_D + CLUSTER - 1) / CLUSTER) * (GCCB_CF_B + 1) * sizeof(float);
   cudaFuncSetAttribute(kmid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_b);
   cudaFuncSetAttribute(kbig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_c);
+  cudaFuncSetAttribute(khuge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_d);
   // The size classes are independent: fork them over side streams (event fork/join, legal inside
   // CUDA-graph capture) so that the few long-running large ego-nets overlap the many small ones.
 #ifndef GCCB_EMU
@@ -778,7 +1232,27 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
 #define GCCB_PE_ARGS(cls) worklist, counts, cls, B, batch->node_cap, batch->edge_cap, batch->node_off, batch->indptr, \
     batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv, pos, eigvals, batch->flags, dbg_iters, dbg_res
   GCCB_LAUNCH(kgiant, 2 * B, 1024, 0, s_giant, GCCB_PE_ARGS(5));
-  GCCB_LAUNCH(khuge, 2 * B, 1024, s_d, s_huge, GCCB_PE_ARGS(4));
+  {
+    const int items = 2 * B < 32 ? 2 * B : 32;           // persistent over the work list
+#ifndef GCCB_EMU
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CLUSTER * items); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = s_d;
+    cfg.stream = (cudaStream_t)s_huge;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ++gccb::g_launch_count;
+    cudaLaunchKernelEx(&cfg, khuge, (const int32_t*)worklist, (const int32_t*)counts, 4, B, batch->node_cap,
+                       batch->edge_cap, (const int32_t*)batch->node_off, (const int32_t*)batch->indptr,
+                       (const int32_t*)batch->indices, (const int32_t*)batch->sub_deg, pos_dim, normalize, dinv, pos,
+                       eigvals, batch->flags, dbg_iters, dbg_res);
+#else
+    GCCB_LAUNCH(khuge, items, 1024, s_d, s_huge, worklist, counts, 4, B, batch->node_cap, batch->edge_cap,
+                batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, dinv, pos,
+                eigvals, batch->flags, dbg_iters, dbg_res);
+#endif
+  }
   GCCB_LAUNCH(kbig, 2 * B, 1024, s_c, s_big, GCCB_PE_ARGS(3));
   GCCB_LAUNCH(kmid, 2 * B, 256, s_b, s_mid2, GCCB_PE_ARGS(2));
   GCCB_LAUNCH(kmid, 2 * B, 256, s_a, s_mid1, GCCB_PE_ARGS(1));

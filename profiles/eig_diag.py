@@ -30,15 +30,31 @@ for rep in range(3):
     print("posenc ms", ev[0].elapsed_time(ev[1]))
 ws = buf.ws_posenc
 ints = ws.view(torch.int32)
-ni = (((5 * 2 * B + 5 + 2 * B) + 63) // 64) * 64
-iters = ints[5 * 2 * B + 5: 5 * 2 * B + 5 + 2 * B].cpu().numpy()
+NC = 6
+ni = (((NC * 2 * B + NC + 2 * B) + 63) // 64) * 64
+iters = ints[NC * 2 * B + NC: NC * 2 * B + NC + 2 * B].cpu().numpy()
 res = ws[ni * 4: ni * 4 + 2 * B * 4].view(torch.float32).cpu().numpy()
 n = buf.counters[:, 0].cpu().numpy()
 print("flags", int(buf.flags.item()))
-for lo, hi in ((0, 64), (64, 96), (96, 160), (160, 480), (480, 100000)):
+for lo, hi in ((0, 64), (64, 96), (96, 160), (160, 480), (480, 1000), (1000, 100000)):
     m = (n > lo) & (n <= hi)
     if m.sum():
         print("n in (%d,%d]: count %d  iters mean %.2f max %d  res mean %.2e max %.2e" % (
             lo, hi, m.sum(), iters[m].mean(), iters[m].max(), res[m].mean(), res[m].max()))
 big = np.argsort(-n)[:8]
 print("largest:", [(int(n[i]), int(iters[i]), float(res[i])) for i in big])
+
+# several batches: size extremes and eigensolver time
+for st in range(1, 9):
+    buf = ds.sample_batch(posenc=False)
+    ev[0].record()
+    _lib.check(lib.gccb_posenc(C.byref(buf.c), 32, 1, _lib.dptr(buf.pos), _lib.dptr(buf.eigvals),
+                               _lib.dptr(buf.ws_posenc), buf.ws_posenc.numel(), _lib.stream_ptr()))
+    ev[1].record()
+    torch.cuda.synchronize()
+    n = buf.counters[:, 0].cpu().numpy()
+    it = ints[NC * 2 * B + NC: NC * 2 * B + NC + 2 * B].cpu().numpy()
+    rs = ws[ni * 4: ni * 4 + 2 * B * 4].view(torch.float32).cpu().numpy()
+    top = np.argsort(-n)[:3]
+    print("batch %d: posenc %.2f ms; largest (n, iters, res): %s; max iters %d" % (
+        st, ev[0].elapsed_time(ev[1]), [(int(n[i]), int(it[i]), float("%.1e" % rs[i])) for i in top], it.max()))
