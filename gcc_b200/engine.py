@@ -20,6 +20,7 @@ import torch
 
 from . import _lib
 from .datasets.data_util import BatchedSubgraphs
+from .parallel import StepExchange, first_sample_id
 
 
 class PretrainEngine:
@@ -65,9 +66,8 @@ class PretrainEngine:
         self.index_dev.fill_(contrast.index)
         self.global_step = 0
         if world_size > 1:
-            self.payload = B * H + n_live + 4
-            self.send = torch.zeros(self.payload, **f32)
-            self.gathered = torch.zeros(world_size, self.payload, **f32)
+            self.xch = StepExchange(B, H, n_live, world_size, dev, process_group)
+            self.payload = self.xch.payload
             if moco and K % (world_size * B) != 0:
                 raise ValueError("queue size must be a multiple of world_size*batch (identical queues)")
         self.launches_per_step = None
@@ -88,7 +88,7 @@ class PretrainEngine:
         ds, model, ema = self.ds, self.model, self.model_ema
         B, H, L = self.B, self.H, self.L
         lr = self.lr0 if lr is None else lr
-        first = (self.global_step * self.world + self.rank) * B
+        first = first_sample_id(self.global_step, self.world, self.rank, B)
         buf = ds.buffers if _presampled else ds.sample_batch(first_sample=first, seeds=seeds)
         gq, gk = BatchedSubgraphs(buf, 0), BatchedSubgraphs(buf, 1)
         step = self.global_step
@@ -116,12 +116,11 @@ class PretrainEngine:
         if self.world > 1:
             # the ONE collective of the step: keys + gradients + stats, then a fixed-rank-order sum
             n_live = model.n_live
-            self.send[:B * H].copy_(self.feat_k.reshape(-1))
-            self.send[B * H:B * H + n_live].copy_(self.grads)
-            self.send[B * H + n_live:].copy_(self.stats)
-            torch.distributed.all_gather_into_tensor(self.gathered.reshape(-1), self.send, group=self.pg)
-            _lib.check(lib.gccb_sum_ranks(C.c_void_p(self.gathered.data_ptr() + 4 * B * H), self.world,
-                                          self.payload, n_live, _lib.dptr(self.grads), st), "gccb_sum_ranks")
+            self.xch.pack(self.feat_k, self.grads, self.stats)
+            gathered = self.xch.all_gather()
+            _lib.check(lib.gccb_sum_ranks(C.c_void_p(gathered.data_ptr() + self.xch.grad_offset_bytes()),
+                                          self.world, self.payload, n_live, _lib.dptr(self.grads), st),
+                       "gccb_sum_ranks")
             scale = 1.0 / self.world
         self._hyper(lr)
         _lib.check(lib.gccb_clip_adam_ema(_lib.dptr(model.flat_params), _lib.dptr(grads),
@@ -136,7 +135,7 @@ class PretrainEngine:
             if self.world > 1:
                 for r in range(self.world):     # rank order -> identical queues on every rank
                     _lib.check(lib.gccb_moco_enqueue(_lib.dptr(self.contrast.memory),
-                                                     C.c_void_p(self.gathered.data_ptr() + 4 * r * self.payload),
+                                                     C.c_void_p(self.xch.gathered.data_ptr() + 4 * r * self.payload),
                                                      B, H, self.K, _lib.dptr(self.index_dev), st),
                                "gccb_moco_enqueue")
             else:

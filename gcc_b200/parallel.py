@@ -1,0 +1,54 @@
+"""Data-parallel plumbing of the pretraining step.
+
+The reference is single-process (no collectives at all).  Here every rank holds the full CSR and
+its own seeds; the ONE collective per step is an all-gather of
+    [ keys k_local (B*d) | flat gradient (n_live) | stats (4) ]
+after which each rank adds the gradients in fixed rank order (bit-identical replicas) and enqueues
+all world*B keys in rank order (identical queues).  This module holds the host-side protocol so it
+can be exercised on CPU with the gloo backend; the arithmetic on the gathered buffer runs in
+libgccb200 (gccb_sum_ranks, gccb_moco_enqueue) inside PretrainEngine.
+"""
+import torch
+import torch.distributed as dist
+
+
+def first_sample_id(global_step, world_size, rank, batch):
+    """Global Philox sample id of this rank's first pair at `global_step`: results are a pure
+    function of (seed, sample id), hence independent of the world size."""
+    return (global_step * world_size + rank) * batch
+
+
+class StepExchange:
+    def __init__(self, batch, dim, n_live, world_size, device, group=None):
+        self.B, self.d, self.n_live, self.world, self.group = batch, dim, n_live, world_size, group
+        self.payload = batch * dim + n_live + 4
+        self.send = torch.zeros(self.payload, dtype=torch.float32, device=device)
+        self.gathered = torch.zeros(world_size, self.payload, dtype=torch.float32, device=device)
+
+    def pack(self, keys, grads, stats):
+        kd = self.B * self.d
+        self.send[:kd].copy_(keys.reshape(-1))
+        self.send[kd:kd + self.n_live].copy_(grads)
+        self.send[kd + self.n_live:].copy_(stats)
+
+    def all_gather(self):
+        if self.send.is_cuda:
+            dist.all_gather_into_tensor(self.gathered.view(-1), self.send, group=self.group)
+        else:   # gloo has no all_gather_into_tensor for every torch build: use the list form
+            parts = list(self.gathered.unbind(0))
+            dist.all_gather(parts, self.send, group=self.group)
+        return self.gathered
+
+    # views into the gathered buffer
+    def keys_of(self, rank):
+        return self.gathered[rank, :self.B * self.d].view(self.B, self.d)
+
+    def grads_of(self, rank):
+        kd = self.B * self.d
+        return self.gathered[rank, kd:kd + self.n_live]
+
+    def stats_of(self, rank):
+        return self.gathered[rank, self.B * self.d + self.n_live:]
+
+    def grad_offset_bytes(self):
+        return 4 * self.B * self.d

@@ -1,0 +1,226 @@
+#!/usr/bin/env python
+"""Pretraining driver with the reference's command line (THUDM/GCC train.py:40-130, pretraining
+flags only) on the B200-native hot path.
+
+    python train.py --moco --nce-k 16384 --dataset synthetic-chunglu --graph-nodes 1000000 \
+        --graph-edges 20000000 --batch-size 256 --epochs 1 --num-samples 2000 --num-workers 12
+    torchrun --nproc-per-node 8 train.py --moco --nce-k 16384 ...          (one process per GPU)
+
+What it keeps from the reference: flag names and defaults, run naming (train.py:133-166), the
+triangular LR schedule with 10% warm-up (train.py:411-416, gcc/utils/misc.py:5-10), BatchNorm of the
+momentum encoder in train mode (train.py:357-365), the checkpoint dict
+{"opt","model","contrast","optimizer","epoch","model_ema"} with the reference's state_dict keys
+(train.py:748-786), print/TensorBoard scalars (train.py:438-472).  What changes: the data loader and
+the whole step run on the GPU through gcc_b200.engine.PretrainEngine (no DataLoader workers, no
+.item() per step: scalars are read every --print-freq steps).  Fine-tuning (--finetune) is out of
+scope.
+"""
+import argparse
+import os
+import time
+
+import numpy as np
+import torch
+
+from gcc_b200.contrastive.memory_moco import MemoryMoCo
+from gcc_b200.datasets import synthetic
+from gcc_b200.datasets.graph_dataset import LoadBalanceGraphDataset
+from gcc_b200.engine import PretrainEngine
+from gcc_b200.models import GraphEncoder
+from gcc_b200.utils.misc import AverageMeter, warmup_linear
+
+
+def parse_option(argv=None):
+    # fmt: off
+    parser = argparse.ArgumentParser("argument for training")
+    parser.add_argument("--print-freq", type=int, default=10, help="print frequency")
+    parser.add_argument("--tb-freq", type=int, default=250, help="tb frequency")
+    parser.add_argument("--save-freq", type=int, default=1, help="save frequency")
+    parser.add_argument("--batch-size", type=int, default=32, help="batch_size")
+    parser.add_argument("--num-workers", type=int, default=12, help="num of workers to use (sizes an epoch: total = num_samples * num_workers)")
+    parser.add_argument("--num-copies", type=int, default=6, help="num of dataset copies that fit in memory")
+    parser.add_argument("--num-samples", type=int, default=2000, help="num of samples per batch per worker")
+    parser.add_argument("--epochs", type=int, default=100, help="number of training epochs")
+    # optimization
+    parser.add_argument("--optimizer", type=str, default="adam", choices=["adam"], help="optimizer (flat Adam kernel)")
+    parser.add_argument("--learning_rate", type=float, default=0.005, help="learning rate")
+    parser.add_argument("--beta1", type=float, default=0.9, help="beta1 for adam")
+    parser.add_argument("--beta2", type=float, default=0.999, help="beta2 for Adam")
+    parser.add_argument("--weight-decay", type=float, default=1e-5, help="weight decay")
+    parser.add_argument("--clip-norm", type=float, default=1.0, help="clip norm")
+    parser.add_argument("--resume", default="", type=str, metavar="PATH", help="path to latest checkpoint")
+    parser.add_argument("--exp", type=str, default="")
+    # dataset definition
+    parser.add_argument("--dataset", type=str, default="synthetic-chunglu",
+                        help="synthetic-chunglu | synthetic-er | path to .npz(indptr, indices[, graph_sizes])")
+    parser.add_argument("--graph-nodes", type=int, default=1000000)
+    parser.add_argument("--graph-edges", type=int, default=20000000)
+    # model definition
+    parser.add_argument("--model", type=str, default="gin", choices=["gin"])
+    parser.add_argument("--num-layer", type=int, default=5, help="gnn layers")
+    parser.add_argument("--readout", type=str, default="avg", choices=["avg", "set2set"])
+    parser.add_argument("--set2set-lstm-layer", type=int, default=3, help="lstm layers for s2s")
+    parser.add_argument("--set2set-iter", type=int, default=6, help="s2s iteration")
+    parser.add_argument("--norm", action="store_true", default=True, help="apply 2-norm on output feats")
+    # loss function
+    parser.add_argument("--nce-k", type=int, default=32)
+    parser.add_argument("--nce-t", type=float, default=0.07)
+    # random walk
+    parser.add_argument("--rw-hops", type=int, default=256)
+    parser.add_argument("--subgraph-size", type=int, default=128)
+    parser.add_argument("--restart-prob", type=float, default=0.8)
+    parser.add_argument("--hidden-size", type=int, default=64)
+    parser.add_argument("--positional-embedding-size", type=int, default=32)
+    parser.add_argument("--max-node-freq", type=int, default=16)
+    parser.add_argument("--max-edge-freq", type=int, default=16)
+    parser.add_argument("--max-degree", type=int, default=512)
+    parser.add_argument("--freq-embedding-size", type=int, default=16)
+    parser.add_argument("--degree-embedding-size", type=int, default=16)
+    # specify folder
+    parser.add_argument("--model-path", type=str, default="saved", help="path to save model")
+    parser.add_argument("--tb-path", type=str, default="tensorboard", help="path to tensorboard")
+    # memory setting
+    parser.add_argument("--moco", action="store_true", help="using MoCo (otherwise Instance Discrimination)")
+    parser.add_argument("--alpha", type=float, default=0.999, help="exponential moving average weight")
+    parser.add_argument("--gpu", default=None, type=int, nargs="+", help="GPU id to use.")
+    parser.add_argument("--seed", type=int, default=0, help="random seed.")
+    parser.add_argument("--max-steps", type=int, default=0, help="stop after this many steps (0 = full run)")
+    # fmt: on
+    return parser.parse_args(argv)
+
+
+def option_update(opt):
+    """Run naming of the reference (train.py:133-166)."""
+    prefix = "Pretrain_{}".format(opt.exp) if opt.exp else "Pretrain"
+    opt.model_name = "{}_{}_{}_{}_layer_{}_lr_{}_decay_{}_bsz_{}_hid_{}_samples_{}_nce_t_{}_nce_k_{}_rw_hops_{}_restart_prob_{}_aug_1st_ft_False_deg_{}_pos_{}_momentum_{}".format(
+        prefix, "moco" if opt.moco else "e2e", os.path.basename(str(opt.dataset)), opt.model, opt.num_layer,
+        opt.learning_rate, opt.weight_decay, opt.batch_size, opt.hidden_size, opt.num_samples, opt.nce_t,
+        opt.nce_k, opt.rw_hops, opt.restart_prob, opt.degree_embedding_size, opt.positional_embedding_size,
+        opt.alpha)
+    opt.model_folder = os.path.join(opt.model_path, opt.model_name)
+    os.makedirs(opt.model_folder, exist_ok=True)
+    opt.tb_folder = os.path.join(opt.tb_path, opt.model_name)
+    os.makedirs(opt.tb_folder, exist_ok=True)
+    return opt
+
+
+def build_graph(args, device):
+    if args.dataset == "synthetic-chunglu":
+        return synthetic.chung_lu_device(args.graph_nodes, args.graph_edges, 0.5, seed=0, device=device)
+    if args.dataset == "synthetic-er":
+        return synthetic.erdos_renyi(args.graph_nodes, args.graph_edges, seed=0)
+    return args.dataset          # path to .npz
+
+
+def train_moco(epoch, engine, sw, opt, is_main):
+    """One epoch (train.py:350-478): n_batch = dataset.total // batch_size steps."""
+    n_batch = engine.ds.total // (opt.batch_size * engine.world)
+    loss_meter, prob_meter, gs_meter, gnorm_meter = (AverageMeter() for _ in range(4))
+    epoch_loss, batch_time = AverageMeter(), AverageMeter()
+    end = time.time()
+    max_nodes = max_edges = 0
+    for idx in range(n_batch):
+        global_step = epoch * n_batch + idx
+        lr = opt.learning_rate * warmup_linear(global_step / (opt.epochs * n_batch), 0.1)   # train.py:411-416
+        engine.step(lr=lr)
+        if (idx + 1) % opt.print_freq == 0 or idx + 1 == n_batch:
+            s = engine.read_stats()                      # the only host sync of the window
+            bsz = opt.batch_size
+            loss_meter.update(s["loss"], bsz)
+            epoch_loss.update(s["loss"], bsz)
+            prob_meter.update(s["prob"], bsz)
+            gs_meter.update((s["nodes_q"] + s["nodes_k"]) / 2.0 / bsz, 2 * bsz)
+            gnorm_meter.update(s["grad_norm"], 1)
+            max_nodes, max_edges = max(max_nodes, s["nodes_q"]), max(max_edges, s["edges_q"])
+            batch_time.update((time.time() - end) / opt.print_freq)
+            end = time.time()
+            if is_main:
+                print("Train: [{0}][{1}/{2}]\tBT {bt.val:.4f} ({bt.avg:.4f})\tloss {loss.val:.3f} ({loss.avg:.3f})\t"
+                      "prob {prob.val:.3f} ({prob.avg:.3f})\tGS {gs.val:.3f} ({gs.avg:.3f})\tlr {lr:.6f}".format(
+                          epoch, idx + 1, n_batch, bt=batch_time, loss=loss_meter, prob=prob_meter, gs=gs_meter, lr=lr))
+        if sw is not None and (idx + 1) % opt.tb_freq == 0:
+            sw.add_scalar("moco_loss", loss_meter.avg, global_step)
+            sw.add_scalar("moco_prob", prob_meter.avg, global_step)
+            sw.add_scalar("graph_size", gs_meter.avg, global_step)
+            sw.add_scalar("graph_size/max", max_nodes, global_step)
+            sw.add_scalar("graph_size/max_edges", max_edges, global_step)
+            sw.add_scalar("gnorm", gnorm_meter.avg, global_step)
+            sw.add_scalar("learning_rate", lr, global_step)
+            for m in (loss_meter, prob_meter, gs_meter, gnorm_meter):
+                m.reset()
+            max_nodes = max_edges = 0
+        if opt.max_steps and global_step + 1 >= opt.max_steps:
+            break
+    return epoch_loss.avg
+
+
+def main(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(args.gpu[0] if args.gpu else 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    np.random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    torch.cuda.manual_seed(args.seed)
+    args = option_update(args)
+    train_dataset = LoadBalanceGraphDataset(
+        rw_hops=args.rw_hops, restart_prob=args.restart_prob,
+        positional_embedding_size=args.positional_embedding_size, num_workers=args.num_workers,
+        num_samples=args.num_samples, dgl_graphs_file=build_graph(args, dev), num_copies=args.num_copies,
+        batch_size=args.batch_size, seed=args.seed, device=dev)
+    model, model_ema = [
+        GraphEncoder(positional_embedding_size=args.positional_embedding_size, max_node_freq=args.max_node_freq,
+                     max_edge_freq=args.max_edge_freq, max_degree=args.max_degree,
+                     freq_embedding_size=args.freq_embedding_size,
+                     degree_embedding_size=args.degree_embedding_size, output_dim=args.hidden_size,
+                     node_hidden_dim=args.hidden_size, edge_hidden_dim=args.hidden_size,
+                     num_layers=args.num_layer, num_step_set2set=args.set2set_iter,
+                     num_layer_set2set=args.set2set_lstm_layer, norm=args.norm, gnn_model=args.model,
+                     degree_input=True) for _ in range(2)]
+    if args.moco:
+        model_ema.load_state_dict(model.state_dict())          # moment_update(model, model_ema, 0), train.py:623-624
+    contrast = MemoryMoCo(args.hidden_size, None, args.nce_k, args.nce_t, use_softmax=True)
+    start_epoch = 1
+    if args.resume:
+        ckpt = torch.load(args.resume, map_location="cpu", weights_only=False)
+        model.load_state_dict(ckpt["model"])
+        contrast.load_state_dict(ckpt["contrast"])
+        if args.moco and "model_ema" in ckpt:
+            model_ema.load_state_dict(ckpt["model_ema"])
+        # like the reference (train.py:689-691) the optimiser state and start epoch are NOT restored
+    model, model_ema, contrast = model.to(dev), model_ema.to(dev), contrast.to(dev)
+    engine = PretrainEngine(train_dataset, model, model_ema, contrast, moco=args.moco,
+                            learning_rate=args.learning_rate, betas=(args.beta1, args.beta2),
+                            weight_decay=args.weight_decay, clip_norm=args.clip_norm, alpha=args.alpha,
+                            nce_t=args.nce_t, rank=rank, world_size=world)
+    sw = None
+    if rank == 0:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            sw = SummaryWriter(args.tb_folder)
+        except Exception:
+            sw = None
+    for epoch in range(start_epoch, args.epochs + 1):
+        t0 = time.time()
+        loss = train_moco(epoch - 1, engine, sw, args, rank == 0)
+        if rank == 0:
+            print("epoch {}, loss {:.4f}, total time {:.2f}".format(epoch, loss, time.time() - t0))
+            if epoch % args.save_freq == 0:
+                state = {"opt": args, "model": model.state_dict(), "contrast": contrast.state_dict(),
+                         "optimizer": {"adam_m": engine.adam_m, "adam_v": engine.adam_v, "adam_t": engine.adam_t},
+                         "epoch": epoch}
+                if args.moco:
+                    state["model_ema"] = model_ema.state_dict()
+                torch.save(state, os.path.join(args.model_folder, "ckpt_epoch_{epoch}.pth".format(epoch=epoch)))
+                torch.save(state, os.path.join(args.model_folder, "current.pth"))
+        if args.max_steps and engine.global_step >= args.max_steps:
+            break
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(parse_option())
