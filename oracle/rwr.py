@@ -134,9 +134,9 @@ def rwr_batch(indptr, indices, key, sample_ids, seeds, btable, restart_thresh,
     seeds = np.ascontiguousarray(seeds, dtype=np.int64)
     btable = np.ascontiguousarray(btable, dtype=np.int32)
     B = len(seeds)
-    subv = np.zeros((2 * B, cap_n), dtype=np.int32)
-    sp = np.zeros((2 * B, cap_n + 1), dtype=np.int32)
-    si = np.zeros((2 * B, cap_m), dtype=np.int32)
+    subv = np.empty((2 * B, cap_n), dtype=np.int32)      # empty, not zeros: only [:n] / [:m] is read back
+    sp = np.empty((2 * B, cap_n + 1), dtype=np.int32)
+    si = np.empty((2 * B, cap_m), dtype=np.int32)
     cnt = np.zeros((2 * B, 5), dtype=np.int64)
     rc = lib().gccb_o_rwr_batch(_p(indptr), _p(indices), len(indptr) - 1, key,
                                 _p(sample_ids), _p(seeds), _p(btable), len(btable),
