@@ -181,7 +181,7 @@ def cpu_arm(cfg, graph_np, steps, seconds_budget, cores=None):
     ctx = mp.get_context("fork")
     # Phase 1 -- loader rate: every loader process assembles ONE whole batch, all in parallel
     # (steady-state DataLoader behaviour); rate = workers * 2B / wall time.
-    n_load = workers if not steps or steps >= workers else max(1, steps)
+    n_load = workers                                           # one whole batch per loader process
     with ctx.Pool(workers) as pool:
         pool.map(abs, range(workers))                          # processes are up before the clock starts
         t0 = time.perf_counter()

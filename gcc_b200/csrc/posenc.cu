@@ -45,7 +45,7 @@ namespace gccb {
 #define GCCB_CF_NSM_D 3840         //   n <= 3840: cluster of 8 CTAs (DSMEM); larger: L2 workspace
 #define GCCB_CF_MAXIT 8
 #define GCCB_CF_TOL 4.0e-5f        // max residual ||L x - theta x|| over the wanted pairs
-#define GCCB_CF_STAG 1.0e-3f       // accepted when the residual stops halving below this: ego-nets whose
+#define GCCB_CF_STAG 2.0e-3f       // accepted when the residual stops halving below this: ego-nets whose
                                    // near-degenerate cluster is wider than the block stall at its spread
 
 // class 0: n <= 64 (dense Jacobi); 1, 2, 3: ChFSI with shared-memory blocks; 4: ChFSI with L2 blocks
@@ -180,6 +180,7 @@ __device__ __forceinline__ int jacobi_twosided(T* A, T* V, T* cs /*[64]*/, int* 
   for (; sweep < GCCB_EIG_MAXSWEEP; ++sweep) {
     int rotated = 0;
     for (int r = 0; r < mm - 1; ++r) {
+      int rot_round = 0;
       if (tid < half) {
         int p, q;
         if (tid == 0) { p = mm - 1; q = r; }
@@ -188,20 +189,21 @@ __device__ __forceinline__ int jacobi_twosided(T* A, T* V, T* cs /*[64]*/, int* 
         T c = (T)1, s = (T)0;
         if (q < m) {
           const T app = A[p * LD + p], aqq = A[q * LD + q], apq = A[q * LD + p];
-          const T tol = sizeof(T) == 8 ? (T)1e-14 : (T)2.0e-7;
+          const T tol = sizeof(T) == 8 ? (T)1e-14 : (T)1.0e-6;
           if (fabs(apq) > tol * sqrt(fabs(app * aqq))) {
             const T zeta = (aqq - app) / ((T)2 * apq);
             const T t = (zeta >= (T)0 ? (T)1 : (T)-1) / (fabs(zeta) + sqrt((T)1 + zeta * zeta));
             c = (T)1 / sqrt((T)1 + t * t);
             s = c * t;
             rotated = 1;
+            rot_round = 1;
           }
         } else {
           p = q = -1;                                  // bye
         }
         cs[2 * tid] = c; cs[2 * tid + 1] = s; pq[tid] = (p & 0xffff) | (q << 16);
       }
-      __syncthreads();
+      if (!__syncthreads_or(rot_round)) continue;         // nothing to rotate in this round
       // columns: A <- A J, V <- V J      (item = pair, row)
       for (int item = tid; item < half * m; item += THREADS) {
         const int pr = item / m, i = item - pr * m;
@@ -564,9 +566,16 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
     }
     // ---- CGS2: orthonormalise the columns of X in place (row-major: all dots of a column at once)
     for (int j = 0; j < CB; ++j) {
+      // classical Gram-Schmidt with selective re-orthogonalisation (Daniel-Gragg-Kaufman test): the
+      // dots of column j with all columns (itself included) come from one pass over the rows;
+      // ||y - Q Q^T y||^2 = y.y - sum r_i^2, so neither the test nor the norm needs another reduction
+      float nrm2 = 0.f;
       for (int pass = 0; pass < 2; ++pass) {
         const float* Xc = X;
         column_sums(n, part, rdot, [&](int r, int c) { return Xc[(size_t)r * ld + c] * Xc[(size_t)r * ld + j]; });
+        const float yy = rdot[j];
+        float rr = 0.f;
+        for (int i = 0; i < j; ++i) rr = fmaf(rdot[i], rdot[i], rr);
         for (int r = tid; r < n; r += NT) {
           float* row = X + (size_t)r * ld;
           float v0 = row[j], v1 = 0.f;
@@ -578,21 +587,16 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
           if (i < j) v0 = fmaf(-rdot[i], row[i], v0);
           row[j] = v0 + v1;
         }
+        nrm2 = yy - rr;
         __syncthreads();
+        if (nrm2 > 0.5f * yy) break;                     // little was removed: no second pass needed
       }
-      // normalise column j: the pass-2 dot of column j with itself is stale, recompute
-      float s = 0.f;
-      for (int r = tid; r < n; r += NT) { float v = X[(size_t)r * ld + j]; s = fmaf(v, v, s); }
-      s = warp_sum(s);
-      if (lane == 0) part[warp] = s;
-      __syncthreads();
-      if (tid == 0) {
-        float t = 0.f;
-        for (int w = 0; w < NW; ++w) t += part[w];
-        s_bc[0] = t > 1e-30f ? 1.0f / sqrtf(t) : 0.f;
+      if (!(nrm2 > 1e-30f)) {                            // cancellation: measure the norm directly
+        const float* Xc = X;
+        column_sums(n, part, rdot, [&](int r, int c) { return c == j ? Xc[(size_t)r * ld + j] * Xc[(size_t)r * ld + j] : 0.f; });
+        nrm2 = rdot[j];
       }
-      __syncthreads();
-      const float inv = s_bc[0];
+      const float inv = nrm2 > 1e-30f ? 1.0f / sqrtf(nrm2) : 0.f;
       for (int r = tid; r < n; r += NT) X[(size_t)r * ld + j] *= inv;
       __syncthreads();
     }
@@ -977,9 +981,13 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
     }
     // ---- CGS2 over the cluster --------------------------------------------------------------------
     for (int j = 0; j < CB; ++j) {
+      float nrm2 = 0.f;
       for (int pass = 0; pass < 2; ++pass) {
         const float* Xc = X;
         cl_column_sums(C, rdot, [&](int rl, int c) { return Xc[(size_t)rl * ld + c] * Xc[(size_t)rl * ld + j]; });
+        const float yy = rdot[j];
+        float rr = 0.f;
+        for (int i = 0; i < j; ++i) rr = fmaf(rdot[i], rdot[i], rr);
         for (int rl = tid; rl < nloc; rl += NT) {
           float* row = X + (size_t)rl * ld;
           float v0 = row[j], v1 = 0.f;
@@ -991,14 +999,16 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
           if (i < j) v0 = fmaf(-rdot[i], row[i], v0);
           row[j] = v0 + v1;
         }
+        nrm2 = yy - rr;
         __syncthreads();
+        if (nrm2 > 0.5f * yy) break;                     // identical decision on every CTA (same rdot bits)
       }
-      {
+      if (!(nrm2 > 1e-30f)) {
         const float* Xc = X;
-        cl_column_sums(C, theta, [&](int rl, int c) { return c == j ? Xc[(size_t)rl * ld + j] * Xc[(size_t)rl * ld + j] : 0.f; });
+        cl_column_sums(C, rdot, [&](int rl, int c) { return c == j ? Xc[(size_t)rl * ld + j] * Xc[(size_t)rl * ld + j] : 0.f; });
+        nrm2 = rdot[j];
       }
-      const float t = theta[j];
-      const float inv = t > 1e-30f ? 1.0f / sqrtf(t) : 0.f;
+      const float inv = nrm2 > 1e-30f ? 1.0f / sqrtf(nrm2) : 0.f;
       for (int rl = tid; rl < nloc; rl += NT) X[(size_t)rl * ld + j] *= inv;
       __syncthreads();
     }
