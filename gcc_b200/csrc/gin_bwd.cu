@@ -13,7 +13,7 @@
 
 namespace gccb {
 
-#define GCCB_WG_CHUNKS 256    // row chunks of the weight-gradient split-K (>= one wave of CTAs)
+#define GCCB_WG_CHUNKS 64     // row chunks of the weight-gradient split-K
 
 struct BwdLayout {            // byte offsets in the backward workspace
   size_t dh, g1, dz2, da, red, dS, dpool, part, total;
@@ -145,7 +145,20 @@ gin_bwd_dh_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_t* 
         int c = lane + 32 * j;
         if (c < W) acc[j] += da[(size_t)r * W + c];
       }
-      for (int e = beg; e < end; ++e) {
+      int e = beg;
+      for (; e + 3 < end; e += 4) {                       // four neighbour rows in flight
+        const int u0 = indices[e], u1 = indices[e + 1], u2 = indices[e + 2], u3 = indices[e + 3];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          int c = lane + 32 * j;
+          if (c < W) {
+            float x0 = da[(size_t)u0 * W + c], x1 = da[(size_t)u1 * W + c];
+            float x2 = da[(size_t)u2 * W + c], x3 = da[(size_t)u3 * W + c];
+            acc[j] += (x0 + x1) + (x2 + x3);
+          }
+        }
+      }
+      for (; e < end; ++e) {
         const int u = indices[e];
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
@@ -414,7 +427,7 @@ gin_wgrad_kernel(const int32_t* __restrict__ node_off_v, int B, int H, int KQ,
         double n = N > 0 ? (double)N : 1.0;
         double mean = q_sums[k] / n, var = q_sums[KQ + k] / n - mean * mean;
         if (var < 0.0) var = 0.0;
-        float invstd = (float)(1.0 / sqrt(var + (double)bn_eps));
+        float invstd = 1.0f / sqrtf((float)var + bn_eps);
         sc = q_gamma[k] * invstd;
         sh = q_beta[k] - (float)mean * sc;
       }
@@ -485,9 +498,12 @@ gin_wgrad_reduce_kernel(int H, int KQ, int in_features, const float* __restrict_
   if (idx < H * KQ) {
     const int o = idx / KQ, k = idx - o * KQ;
     if (k < in_features) {
-      float s = 0.f;
-      for (int ch = 0; ch < GCCB_WG_CHUNKS; ++ch) s += part[ch * stride + idx];
-      gw[(size_t)o * in_features + k] += s;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // fixed order, 4 loads in flight
+      for (int ch = 0; ch < GCCB_WG_CHUNKS; ch += 4) {
+        s0 += part[(ch + 0) * stride + idx]; s1 += part[(ch + 1) * stride + idx];
+        s2 += part[(ch + 2) * stride + idx]; s3 += part[(ch + 3) * stride + idx];
+      }
+      gw[(size_t)o * in_features + k] += (s0 + s1) + (s2 + s3);
     }
   } else if (idx < H * KQ + H) {
     float s = 0.f;

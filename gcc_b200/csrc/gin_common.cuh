@@ -120,7 +120,9 @@ __device__ __forceinline__ void bn_prepare(const double* __restrict__ sums, int 
         running[H + c] = (float)((1.0 - momentum) * running[H + c] + momentum * unb);
       }
     }
-    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    // only the cancellation-prone E[x^2]-E[x]^2 is done in float64 (fp64 runs at a small
+    // fraction of the fp32 rate on this part); the square root is float like torch's batch_norm
+    float invstd = 1.0f / sqrtf((float)var + eps);
     float g = gamma[c];
     mean_s[c] = (float)mean;
     invstd_s[c] = invstd;

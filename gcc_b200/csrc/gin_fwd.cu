@@ -77,7 +77,20 @@ gin_agg_gemm1_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_
           int c = lane + 32 * j;
           if (c < KIN) acc[j] = (1.0f + eps_gin) * h[(size_t)r * KIN + c];
         }
-        for (int e = beg; e < end; ++e) {
+        int e = beg;
+        for (; e + 3 < end; e += 4) {                     // four neighbour rows in flight
+          const int u0 = indices[e], u1 = indices[e + 1], u2 = indices[e + 2], u3 = indices[e + 3];
+#pragma unroll
+          for (int j = 0; j < PER; ++j) {
+            int c = lane + 32 * j;
+            if (c < KIN) {
+              float x0 = h[(size_t)u0 * KIN + c], x1 = h[(size_t)u1 * KIN + c];
+              float x2 = h[(size_t)u2 * KIN + c], x3 = h[(size_t)u3 * KIN + c];
+              acc[j] += (x0 + x1) + (x2 + x3);
+            }
+          }
+        }
+        for (; e < end; ++e) {
           const int u = indices[e];
 #pragma unroll
           for (int j = 0; j < PER; ++j) {
@@ -233,6 +246,7 @@ gin_pool_predict_kernel(GinDims d, const int32_t* __restrict__ node_off_v, int B
                         float* __restrict__ pooled, float* __restrict__ score_out,
                         float* __restrict__ feat_out, float* __restrict__ pooled_user) {
   constexpr int MAXW = H > GCCB_DINP ? H : GCCB_DINP;
+  GCCB_DYN_SMEM(float, wt);                // [MAXW][H + 1] transposed head weight
   __shared__ float part[4][MAXW];
   __shared__ float pl[MAXW];
   __shared__ float score[H];
@@ -246,13 +260,25 @@ gin_pool_predict_kernel(GinDims d, const int32_t* __restrict__ node_off_v, int B
     const int W = l == 0 ? GCCB_DINP : H;                 // stored width
     const int inf = l == 0 ? d.din : H;                   // in_features of the head
     const float* src = l == 0 ? x0 : h_layers[l - 1];
-    // segment sum: thread (c, rg) with c < W, rg in 0..RG-1
+    // segment sum: thread (c, rg) with c < W, rg in 0..RG-1, four rows in flight per thread
     const int RG = 256 / W >= 4 ? 4 : (256 / W > 0 ? 256 / W : 1);
     const int c = tid % W, rg = tid / W;
     if (rg < RG) {
-      float s = 0.f;
-      for (int r = r0 + rg; r < r1; r += RG) s += src[(size_t)r * W + c];
-      part[rg][c] = s;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int r = r0 + rg;
+      for (; r + 3 * RG < r1; r += 4 * RG) {
+        s0 += src[(size_t)r * W + c]; s1 += src[(size_t)(r + RG) * W + c];
+        s2 += src[(size_t)(r + 2 * RG) * W + c]; s3 += src[(size_t)(r + 3 * RG) * W + c];
+      }
+      for (; r < r1; r += RG) s0 += src[(size_t)r * W + c];
+      part[rg][c] = (s0 + s1) + (s2 + s3);
+    }
+    // stage the head's weight transposed: wt[k][o] = Wp[o][k]  (coalesced global reads)
+    const float* Wp = params + wp_off[l];
+    const float* bp = params + bp_off[l];
+    for (int idx = tid; idx < H * inf; idx += 256) {
+      const int o = idx / inf, k2 = idx - o * inf;
+      wt[k2 * (H + 1) + o] = Wp[idx];
     }
     __syncthreads();
     for (int cc = tid; cc < W; cc += 256) {
@@ -263,11 +289,9 @@ gin_pool_predict_kernel(GinDims d, const int32_t* __restrict__ node_off_v, int B
       if (pooled_user && l > 0) pooled_user[((size_t)(l - 1) * B + g) * H + cc] = s;   // all_outputs[1:]
     }
     __syncthreads();
-    const float* Wp = params + wp_off[l];
-    const float* bp = params + bp_off[l];
     for (int o = tid; o < H; o += 256) {
       float s = bp[o];
-      for (int k = 0; k < inf; ++k) s = fmaf(pl[k], Wp[(size_t)o * inf + k], s);
+      for (int k = 0; k < inf; ++k) s = fmaf(pl[k], wt[k * (H + 1) + o], s);
       if (drop_layer_base >= 0) {                          // Dropout(p) in train mode, Philox mask
         const uint32_t e = (uint32_t)(g * H + o);
         u32x4 w = philox_at(drop_key, drop_step, e >> 2, 0, (uint32_t)(drop_layer_base + l),
@@ -383,7 +407,9 @@ static int run_forward(const FwdArgs& a) {
   }
   const uint32_t keep = (uint32_t)fmin((1.0 - (double)d.drop_p) * 4294967296.0, 4294967295.0);
   auto kp = gin_pool_predict_kernel<H>;
-  GCCB_LAUNCH(kp, B, 256, 0, a.stream, d, node_off_v, B, x0, a.d_hptrs, a.params, a.d_offs, a.d_offs + 8,
+  const size_t sm_pool = (size_t)(H > GCCB_DINP ? H : GCCB_DINP) * (H + 1) * sizeof(float);
+  cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pool);
+  GCCB_LAUNCH(kp, B, 256, sm_pool, a.stream, d, node_off_v, B, x0, a.d_hptrs, a.params, a.d_offs, a.d_offs + 8,
               a.al.PW, a.drop_key, a.drop_step, a.drop_base, keep, (float*)(a.acts + a.al.pooled),
               (float*)(a.acts + a.al.score), a.feat, a.pooled_user);
   return check_launch("gccb_gin_forward");

@@ -59,10 +59,13 @@ __device__ __forceinline__ bool adj_find(const int32_t* __restrict__ indices, in
 // A hub row (parent degree >> ego-net size) is not streamed: each ego-net vertex is looked up in the
 // hub's sorted neighbour list instead (n log deg probes instead of deg reads).
 #define GCCB_REVERSE_FACTOR 16
+#define GCCB_ST 1024           // threads per CTA of the walk / fill kernels: hub ego-nets (thousands of
+                               // vertices, ~1e5..1e6 neighbour probes) are the tail of these kernels
+#define GCCB_SW (GCCB_ST / 32)
 
-// Pass 1: walk + sort/unique + induced-degree count.  grid = 2B, block = 256.
+// Pass 1: walk + sort/unique + induced-degree count.  grid = 2B, block = GCCB_ST.
 // dyn smem: keys[P] ints, P = pow2 >= max_budget + HOPCAP.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(GCCB_ST)
 rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                        const int32_t* __restrict__ budget_table, int budget_table_len,
                        uint32_t restart_thresh, uint64_t key, const int64_t* __restrict__ seeds,
@@ -89,7 +92,7 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
   int base = 0;          // recorded nodes before this chunk
   int total = 0;
   for (int chunk = 0;; ++chunk) {
-    const uint32_t t = (uint32_t)(chunk * 256 + tid);
+    const uint32_t t = (uint32_t)(chunk * GCCB_ST + tid);
     int len = 1;         // hop 0 is always taken
     for (uint32_t hop = 1; hop < GCCB_HOPCAP; ++hop) {
       u32x4 w = philox_at(key, sample, t, hop, (uint32_t)view, GCCB_TAG_WALK);
@@ -131,11 +134,11 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
   // ---- phase C: bitonic sort of keys[0..total), padded to a power of two --------------
   int P = 1;
   while (P < total) P <<= 1;
-  for (int i = total + tid; i < P; i += 256) keys[i] = 0x7fffffff;
+  for (int i = total + tid; i < P; i += GCCB_ST) keys[i] = 0x7fffffff;
   __syncthreads();
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < P; i += 256) {
+      for (int i = tid; i < P; i += GCCB_ST) {
         int ixj = i ^ j;
         if (ixj > i) {
           int a = keys[i], b = keys[ixj];
@@ -149,7 +152,7 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
   // ---- unique, drop the seed; subv = [seed] + sorted rest (data_util.py:221-226) -------
   int32_t* subv = subv_scratch + (size_t)slot * cap_n;
   int n_rest = 0;
-  for (int b0 = 0; b0 < total; b0 += 256) {
+  for (int b0 = 0; b0 < total; b0 += GCCB_ST) {
     int i = b0 + tid;
     int head = 0, v = 0;
     if (i < total) {
@@ -164,14 +167,14 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
   const int n = n_rest + 1;
   if (tid == 0) subv[0] = seed;
   __syncthreads();                       // global writes of this block visible to the block
-  for (int i = tid; i < n; i += 256) keys[i] = subv[i];
+  for (int i = tid; i < n; i += GCCB_ST) keys[i] = subv[i];
   __syncthreads();
 
   // ---- phase D: induced degree of every ego-net vertex (warp per vertex) ---------------
   int32_t* subdeg = subdeg_scratch + (size_t)slot * cap_n;
   int m_local = 0;
   unsigned long long sumdeg_local = 0ull;
-  for (int i = warp; i < n; i += 8) {
+  for (int i = warp; i < n; i += GCCB_SW) {
     const int64_t v = keys[i];
     const int64_t beg = indptr[v], end = indptr[v + 1];
     int cnt = 0;
@@ -240,8 +243,8 @@ batch_offsets_kernel(const int64_t* __restrict__ counters, int B, int node_cap, 
   }
 }
 
-// Pass 3: fill the batched CSR.  grid = 2B, block = 256, dyn smem keys[P].
-__global__ void __launch_bounds__(256)
+// Pass 3: fill the batched CSR.  grid = 2B, block = GCCB_ST, dyn smem keys[P].
+__global__ void __launch_bounds__(GCCB_ST)
 induce_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                    const int64_t* __restrict__ counters, int B, int cap_n, int node_cap,
                    int edge_cap, const int32_t* __restrict__ subv_scratch,
@@ -265,11 +268,11 @@ induce_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
   int32_t* v_indptr = out_indptr + (size_t)view * (node_cap + 1);
   int32_t* v_indices = out_indices + (size_t)view * edge_cap;
   const size_t nb = (size_t)view * node_cap;
-  for (int i = tid; i < n; i += 256) keys[i] = subv[i];
+  for (int i = tid; i < n; i += GCCB_ST) keys[i] = subv[i];
   const int seed = subv[0];
   // row starts (view-local edge positions) = eoff + exclusive scan of induced degrees
   int run = 0;
-  for (int b0 = 0; b0 < n; b0 += 256) {
+  for (int b0 = 0; b0 < n; b0 += GCCB_ST) {
     int i = b0 + tid;
     int d = i < n ? subdeg[i] : 0;
     int tot;
@@ -284,7 +287,7 @@ induce_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
   }
   if (g == B - 1 && tid == 0) v_indptr[noff + n] = eoff + run;   // closing entry = E_v
   __syncthreads();                                               // keys[] + v_indptr visible
-  for (int i = warp; i < n; i += 8) {
+  for (int i = warp; i < n; i += GCCB_SW) {
     const int64_t v = keys[i];
     const int64_t beg = indptr[v], end = indptr[v + 1];
     int wpos = v_indptr[noff + i];
@@ -373,12 +376,12 @@ extern "C" int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds
     cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  GCCB_LAUNCH(k1, 2 * B, 256, smem, stream, graph->indptr, graph->indices, graph->budget_table,
+  GCCB_LAUNCH(k1, 2 * B, GCCB_ST, smem, stream, graph->indptr, graph->indices, graph->budget_table,
               graph->budget_table_len, graph->restart_thresh, graph->key, seeds, sample_ids, B,
               cap_n, subv, subdeg, batch->counters, batch->flags);
   GCCB_LAUNCH(batch_offsets_kernel, 2, 256, 0, stream, batch->counters, B, batch->node_cap,
               batch->edge_cap, batch->node_off, batch->edge_off, batch->flags);
-  GCCB_LAUNCH(k3, 2 * B, 256, smem, stream, graph->indptr, graph->indices, batch->counters, B,
+  GCCB_LAUNCH(k3, 2 * B, GCCB_ST, smem, stream, graph->indptr, graph->indices, batch->counters, B,
               cap_n, batch->node_cap, batch->edge_cap, subv, subdeg, batch->node_off,
               batch->edge_off, batch->indptr, batch->indices, batch->sub_deg, batch->graph_id,
               batch->orig_id);
