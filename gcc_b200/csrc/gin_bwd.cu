@@ -305,7 +305,8 @@ gin_bwd_gemm2_kernel(const int32_t* __restrict__ node_off_v, int B, const float*
   for (int tile = blockIdx.x; tile * GCCB_TILE_ROWS < N; tile += gridDim.x) {
     const int row0 = tile * GCCB_TILE_ROWS;
     __syncthreads();
-    for (int idx = tid; idx < GCCB_TILE_ROWS * H; idx += 256) {
+#pragma unroll 8
+    for (int idx = tid; idx < GCCB_TILE_ROWS * H; idx += 256) {   // 8 independent L2 loads in flight
       int rr = idx / H, c = idx - rr * H;
       int r = row0 + rr;
       float dz = 0.f;
@@ -376,7 +377,8 @@ gin_bwd_gemm1_kernel(const int32_t* __restrict__ node_off_v, int B, const float*
   for (int tile = blockIdx.x; tile * GCCB_TILE_ROWS < N; tile += gridDim.x) {
     const int row0 = tile * GCCB_TILE_ROWS;
     __syncthreads();
-    for (int idx = tid; idx < GCCB_TILE_ROWS * H; idx += 256) {
+#pragma unroll 8
+    for (int idx = tid; idx < GCCB_TILE_ROWS * H; idx += 256) {   // 8 independent L2 loads in flight
       int rr = idx / H, c = idx - rr * H;
       int r = row0 + rr;
       float dz = 0.f;
@@ -447,6 +449,7 @@ gin_wgrad_kernel(const int32_t* __restrict__ node_off_v, int B, int H, int KQ,
   for (int tile = t_beg; tile < t_end; ++tile) {
     const int row0 = tile * GCCB_TILE_ROWS;
     __syncthreads();
+#pragma unroll 8
     for (int idx = tid; idx < GCCB_TILE_ROWS * 64; idx += 256) {
       int rr = idx >> 6, c = idx & 63;
       int r = row0 + rr;

@@ -144,6 +144,7 @@ template <int NOUT> struct TileCols {
 template <int NOUT, class GetW>
 __device__ __forceinline__ void stage_weights(float* Ws, int k0, int kc, GetW getw) {
   constexpr int LDW = NOUT + 4;
+#pragma unroll 8
   for (int idx = threadIdx.x; idx < kc * NOUT; idx += blockDim.x) {
     int kk = idx % kc, c = idx / kc;                 // consecutive threads -> consecutive k (coalesced in W rows)
     Ws[kk * LDW + c] = getw(k0 + kk, c);

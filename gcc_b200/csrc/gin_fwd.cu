@@ -154,7 +154,8 @@ gin_bn_gemm2_kernel(const int32_t* __restrict__ node_off_v, int B, const float* 
   for (int tile = blockIdx.x; tile * GCCB_TILE_ROWS < N; tile += gridDim.x) {
     const int row0 = tile * GCCB_TILE_ROWS;
     __syncthreads();
-    for (int idx = tid; idx < GCCB_TILE_ROWS * H; idx += 256) {
+#pragma unroll 8
+    for (int idx = tid; idx < GCCB_TILE_ROWS * H; idx += 256) {   // 8 independent L2 loads in flight
       int rr = idx / H, c = idx - rr * H;
       int r = row0 + rr;
       float x = 0.f;

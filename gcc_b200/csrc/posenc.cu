@@ -425,23 +425,34 @@ __device__ __forceinline__ void spmm_cheb(const SubCsr& S, const float* __restri
 }
 
 // Per-column reduction helper: every warp accumulates (lane -> columns lane, 32+lane) over its rows,
-// partial sums go through part[32][48] and end up in out[48].  Ends with a barrier.
+// partial sums go through part[32][48] and end up in out[48]; rr2[0] + rr2[1] = sum_{c < jlim} out[c]^2
+// (the Gram-Schmidt norm update) comes out of the same pass.  Ends with a barrier.
 template <class RowFn>
-__device__ __forceinline__ void column_sums(int n, float* part /*[32][48]*/, float* out /*[48]*/, RowFn f) {
+__device__ __forceinline__ void column_sums(int n, float* part /*[32][48]*/, float* out /*[48]*/, float* rr2 /*[2]*/,
+                                            int jlim, RowFn f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const bool hi = lane < GCCB_CF_B - 32;
-  float a0 = 0.f, a1 = 0.f;
-  for (int r = warp; r < n; r += nw) {
-    a0 += f(r, lane);
-    if (hi) a1 += f(r, 32 + lane);
+  const int nwu = nw < 8 ? nw : 8;                      // 8 accumulating warps keep the partial reduce short
+  if (warp < nwu) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = warp; r < n; r += nwu) {
+      a0 += f(r, lane);
+      if (hi) a1 += f(r, 32 + lane);
+    }
+    part[warp * GCCB_CF_B + lane] = a0;
+    if (hi) part[warp * GCCB_CF_B + 32 + lane] = a1;
   }
-  part[warp * GCCB_CF_B + lane] = a0;
-  if (hi) part[warp * GCCB_CF_B + 32 + lane] = a1;
   __syncthreads();
-  for (int c = threadIdx.x; c < GCCB_CF_B; c += blockDim.x) {
-    float s = 0.f;
-    for (int w = 0; w < nw; ++w) s += part[w * GCCB_CF_B + c];
-    out[c] = s;
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    float sacc = 0.f;
+    if (c < GCCB_CF_B) {
+      for (int w = 0; w < nwu; ++w) sacc += part[w * GCCB_CF_B + c];
+      out[c] = sacc;
+    }
+    float sq = c < jlim ? sacc * sacc : 0.f;
+    sq = warp_sum(sq);
+    if (lane == 0) rr2[warp] = sq;
   }
   __syncthreads();
 }
@@ -466,6 +477,7 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
   __shared__ float WT[32 * (CB + 1) * 2];         // union: Ritz vectors Ws[CB*LD] | tiles [2][32][CB+1]
   __shared__ float part[32 * CB];
   __shared__ float rdot[CB];
+  __shared__ float rr2[2];
   __shared__ float theta[CB];
   __shared__ float resid[CB];
   __shared__ float cs[64];
@@ -572,10 +584,9 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
       float nrm2 = 0.f;
       for (int pass = 0; pass < 2; ++pass) {
         const float* Xc = X;
-        column_sums(n, part, rdot, [&](int r, int c) { return Xc[(size_t)r * ld + c] * Xc[(size_t)r * ld + j]; });
+        column_sums(n, part, rdot, rr2, j, [&](int r, int c) { return Xc[(size_t)r * ld + c] * Xc[(size_t)r * ld + j]; });
         const float yy = rdot[j];
-        float rr = 0.f;
-        for (int i = 0; i < j; ++i) rr = fmaf(rdot[i], rdot[i], rr);
+        const float rr = rr2[0] + rr2[1];
         for (int r = tid; r < n; r += NT) {
           float* row = X + (size_t)r * ld;
           float v0 = row[j], v1 = 0.f;
@@ -593,7 +604,7 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
       }
       if (!(nrm2 > 1e-30f)) {                            // cancellation: measure the norm directly
         const float* Xc = X;
-        column_sums(n, part, rdot, [&](int r, int c) { return c == j ? Xc[(size_t)r * ld + j] * Xc[(size_t)r * ld + j] : 0.f; });
+        column_sums(n, part, rdot, rr2, 0, [&](int r, int c) { return c == j ? Xc[(size_t)r * ld + j] * Xc[(size_t)r * ld + j] : 0.f; });
         nrm2 = rdot[j];
       }
       const float inv = nrm2 > 1e-30f ? 1.0f / sqrtf(nrm2) : 0.f;
@@ -685,8 +696,8 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
     __syncthreads();
     {
       const float* Xc = X; const float* Yc = Y;
-      column_sums(n, part, theta, [&](int r, int c) { return Xc[(size_t)r * ld + c] * Yc[(size_t)r * ld + c]; });
-      column_sums(n, part, resid, [&](int r, int c) {
+      column_sums(n, part, theta, rr2, 0, [&](int r, int c) { return Xc[(size_t)r * ld + c] * Yc[(size_t)r * ld + c]; });
+      column_sums(n, part, resid, rr2, 0, [&](int r, int c) {
         float d = Yc[(size_t)r * ld + c] - theta[c] * Xc[(size_t)r * ld + c];
         return d * d;
       });
@@ -851,34 +862,45 @@ __device__ __forceinline__ void cl_spmm(const ClCtx<NT, CS>& C, const float* src
   }
 }
 
-// cluster-wide per-column sums of f(local row, column) -> out[48] (identical on every CTA)
+// cluster-wide per-column sums of f(local row, column) -> out[48] (identical on every CTA);
+// rr2[0] + rr2[1] = sum_{c < jlim} out[c]^2
 template <int NT, int CS, class RowFn>
-__device__ __forceinline__ void cl_column_sums(ClCtx<NT, CS>& C, float* out, RowFn f) {
+__device__ __forceinline__ void cl_column_sums(ClCtx<NT, CS>& C, float* out, float* rr2, int jlim, RowFn f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = NT / 32;
+  constexpr int NW = NT / 32, NWU = NW < 8 ? NW : 8;
   const bool hi = lane < GCCB_CF_B - 32;
-  float a0 = 0.f, a1 = 0.f;
-  for (int rl = warp; rl < C.nloc; rl += NW) {
-    a0 += f(rl, lane);
-    if (hi) a1 += f(rl, 32 + lane);
+  if (warp < NWU) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int rl = warp; rl < C.nloc; rl += NWU) {
+      a0 += f(rl, lane);
+      if (hi) a1 += f(rl, 32 + lane);
+    }
+    C.part[warp * GCCB_CF_B + lane] = a0;
+    if (hi) C.part[warp * GCCB_CF_B + 32 + lane] = a1;
   }
-  C.part[warp * GCCB_CF_B + lane] = a0;
-  if (hi) C.part[warp * GCCB_CF_B + 32 + lane] = a1;
   __syncthreads();
   float* mine = C.xch + C.xbuf * GCCB_CF_B;
-  for (int c = threadIdx.x; c < GCCB_CF_B; c += NT) {
-    float sacc = 0.f;
-    for (int w = 0; w < NW; ++w) sacc += C.part[w * GCCB_CF_B + c];
-    if (CS > 1) mine[c] = sacc; else out[c] = sacc;
+  float sacc = 0.f;
+  const int c = threadIdx.x;
+  if (c < GCCB_CF_B) {
+#pragma unroll
+    for (int w = 0; w < NWU; ++w) sacc += C.part[w * GCCB_CF_B + c];
+    if (CS > 1) mine[c] = sacc;
   }
   if (CS > 1) {
     cl_sync<CS>();
-    for (int c = threadIdx.x; c < GCCB_CF_B; c += NT) {
-      float sacc = 0.f;
+    if (c < GCCB_CF_B) {
+      sacc = 0.f;
+#pragma unroll
       for (int q = 0; q < CS; ++q) sacc += cl_map<CS>(mine, q)[c];     // fixed rank order: deterministic
-      out[c] = sacc;
     }
     C.xbuf ^= 1;
+  }
+  if (c < 64) {
+    if (c < GCCB_CF_B) out[c] = sacc;
+    float sq = c < jlim ? sacc * sacc : 0.f;
+    sq = warp_sum(sq);
+    if (lane == 0) rr2[warp] = sq;
   }
   __syncthreads();
 }
@@ -900,6 +922,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
   __shared__ float part[32 * CB];
   __shared__ float xch[2 * CB + 8];
   __shared__ float rdot[CB];
+  __shared__ float rr2[2];
   __shared__ float theta[CB];
   __shared__ float resid[CB];
   __shared__ float cs[64];
@@ -984,10 +1007,9 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       float nrm2 = 0.f;
       for (int pass = 0; pass < 2; ++pass) {
         const float* Xc = X;
-        cl_column_sums(C, rdot, [&](int rl, int c) { return Xc[(size_t)rl * ld + c] * Xc[(size_t)rl * ld + j]; });
+        cl_column_sums(C, rdot, rr2, j, [&](int rl, int c) { return Xc[(size_t)rl * ld + c] * Xc[(size_t)rl * ld + j]; });
         const float yy = rdot[j];
-        float rr = 0.f;
-        for (int i = 0; i < j; ++i) rr = fmaf(rdot[i], rdot[i], rr);
+        const float rr = rr2[0] + rr2[1];
         for (int rl = tid; rl < nloc; rl += NT) {
           float* row = X + (size_t)rl * ld;
           float v0 = row[j], v1 = 0.f;
@@ -1005,7 +1027,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       }
       if (!(nrm2 > 1e-30f)) {
         const float* Xc = X;
-        cl_column_sums(C, rdot, [&](int rl, int c) { return c == j ? Xc[(size_t)rl * ld + j] * Xc[(size_t)rl * ld + j] : 0.f; });
+        cl_column_sums(C, rdot, rr2, 0, [&](int rl, int c) { return c == j ? Xc[(size_t)rl * ld + j] * Xc[(size_t)rl * ld + j] : 0.f; });
         nrm2 = rdot[j];
       }
       const float inv = nrm2 > 1e-30f ? 1.0f / sqrtf(nrm2) : 0.f;
@@ -1102,8 +1124,8 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
     __syncthreads();
     {
       const float* Xc = X; const float* Yc = Y;
-      cl_column_sums(C, theta, [&](int rl, int c) { return Xc[(size_t)rl * ld + c] * Yc[(size_t)rl * ld + c]; });
-      cl_column_sums(C, resid, [&](int rl, int c) {
+      cl_column_sums(C, theta, rr2, 0, [&](int rl, int c) { return Xc[(size_t)rl * ld + c] * Yc[(size_t)rl * ld + c]; });
+      cl_column_sums(C, resid, rr2, 0, [&](int rl, int c) {
         float d = Yc[(size_t)rl * ld + c] - theta[c] * Xc[(size_t)rl * ld + c];
         return d * d;
       });
