@@ -48,6 +48,15 @@ namespace gccb {
 #define GCCB_CF_STAG 2.0e-3f       // accepted when the residual stops halving below this: ego-nets whose
                                    // near-degenerate cluster is wider than the block stall at its spread
 
+// phase cycle counters (diagnostics; thread 0 only, negligible cost): 0 filter, 1 gram-schmidt, 2 projected
+// matrix, 3 Ritz solve, 4 X = QW, 5 residual
+#ifdef GCCB_EMU
+#define GCCB_CLK() 0ll
+#else
+#define GCCB_CLK() clock64()
+#endif
+#define GCCB_TICK(k) do { if (threadIdx.x == 0) { long long t_ = GCCB_CLK(); ph[k] += t_ - t_last; t_last = t_; } } while (0)
+
 // class 0: n <= 64 (dense Jacobi); 1, 2, 3: ChFSI with shared-memory blocks; 4: ChFSI with L2 blocks
 __device__ __forceinline__ int eig_class(int n) {
   return n <= GCCB_EIG_SMALL ? 0 : n <= GCCB_CF_NSM_A ? 1 : n <= GCCB_CF_NSM ? 2 : n <= GCCB_CF_NSM_C ? 3 :
@@ -233,6 +242,87 @@ __device__ __forceinline__ int jacobi_twosided(T* A, T* V, T* cs /*[64]*/, int* 
         const T x = A[j * LD + p], y = A[j * LD + q];
         A[j * LD + p] = c * x - s * y;
         A[j * LD + q] = s * x + c * y;
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) break;
+  }
+  return sweep;
+}
+
+// Two-sided Jacobi specialised for the even-order Ritz problem (m = 48): per round ONE thread per pair
+// derives (c, s); then every thread applies BOTH sides of the similarity transform to whole 2 x 2
+// blocks (rows of pair a, columns of pair b) -- no barrier between the row and the column update --
+// and rotates V.  Two barriers per round instead of three, independent items unrolled for ILP.
+// `tol`: relative skip threshold (adaptive: the Ritz vectors need no more accuracy than the
+// current outer residual).
+template <int NT>
+__device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64]*/, int* pq /*[32]*/, int LD,
+                                              float tol) {
+  constexpr int M = GCCB_CF_B, HALF = M / 2;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < M * M; idx += NT) {
+    const int j = idx / M, i = idx - j * M;
+    V[j * LD + i] = i == j ? 1.0f : 0.f;
+  }
+  __syncthreads();
+  int sweep = 0;
+  for (; sweep < GCCB_EIG_MAXSWEEP; ++sweep) {
+    int rotated = 0;
+    for (int r = 0; r < M - 1; ++r) {
+      int rot_round = 0;
+      if (tid < HALF) {
+        int p, q;
+        if (tid == 0) { p = M - 1; q = r; }
+        else { p = (r + tid) % (M - 1); q = (r + M - 1 - tid) % (M - 1); }
+        if (p > q) { int t = p; p = q; q = t; }
+        float c = 1.0f, s = 0.f;
+        const float app = A[p * LD + p], aqq = A[q * LD + q], apq = A[q * LD + p];
+        if (fabsf(apq) > tol * sqrtf(fabsf(app * aqq))) {
+          const float zeta = (aqq - app) / (2.0f * apq);
+          const float t = (zeta >= 0.f ? 1.0f : -1.0f) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+          c = 1.0f / sqrtf(1.0f + t * t);
+          s = c * t;
+          rotated = 1;
+          rot_round = 1;
+        }
+        cs[2 * tid] = c; cs[2 * tid + 1] = s; pq[tid] = p | (q << 16);
+      }
+      if (!__syncthreads_or(rot_round)) continue;
+      // A <- J^T A J on 2x2 blocks: rows (p1,q1) of pair a, columns (p2,q2) of pair b
+      constexpr int NB = HALF * HALF, ITB = (NB + NT - 1) / NT;
+#pragma unroll
+      for (int t = 0; t < ITB; ++t) {
+        const int item = tid + t * NT;
+        if (item < NB) {
+          const int pa = item / HALF, pb = item - pa * HALF;
+          const int ca = pq[pa], cb = pq[pb];
+          const int p1 = ca & 0xffff, q1 = ca >> 16, p2 = cb & 0xffff, q2 = cb >> 16;
+          const float c1 = cs[2 * pa], s1 = cs[2 * pa + 1], c2 = cs[2 * pb], s2 = cs[2 * pb + 1];
+          float a = A[p2 * LD + p1], b = A[q2 * LD + p1], c_ = A[p2 * LD + q1], d = A[q2 * LD + q1];
+          // columns: [x y] -> [c2 x - s2 y, s2 x + c2 y]
+          float a2 = c2 * a - s2 * b, b2 = s2 * a + c2 * b, c3 = c2 * c_ - s2 * d, d2 = s2 * c_ + c2 * d;
+          // rows: [x; y] -> [c1 x - s1 y; s1 x + c1 y]
+          A[p2 * LD + p1] = c1 * a2 - s1 * c3;
+          A[q2 * LD + p1] = c1 * b2 - s1 * d2;
+          A[p2 * LD + q1] = s1 * a2 + c1 * c3;
+          A[q2 * LD + q1] = s1 * b2 + c1 * d2;
+        }
+      }
+      // V <- V J
+      constexpr int NV = HALF * M, ITV = (NV + NT - 1) / NT;
+#pragma unroll
+      for (int t = 0; t < ITV; ++t) {
+        const int item = tid + t * NT;
+        if (item < NV) {
+          const int pr = item / M, i = item - pr * M;
+          const int code = pq[pr];
+          const int p = code & 0xffff, q = code >> 16;
+          const float c = cs[2 * pr], s = cs[2 * pr + 1];
+          const float x = V[p * LD + i], y = V[q * LD + i];
+          V[p * LD + i] = c * x - s * y;
+          V[q * LD + i] = s * x + c * y;
+        }
       }
       __syncthreads();
     }
@@ -470,9 +560,10 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
                     const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
                     float* __restrict__ blocks /* [2][2*node_cap*48] */, float* __restrict__ dinv_g /* [2*node_cap] */,
                     float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags,
-                    int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res) {
+                    int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res, long long* __restrict__ dbg_phase) {
   constexpr int CB = GCCB_CF_B, LD = CB + 1;
   GCCB_DYN_SMEM(float, dynsm);
+  long long ph[6] = {0, 0, 0, 0, 0, 0}, t_last = GCCB_CLK();
   __shared__ float Gs[CB * LD];                   // Ritz problem
   __shared__ float WT[32 * (CB + 1) * 2];         // union: Ritz vectors Ws[CB*LD] | tiles [2][32][CB+1]
   __shared__ float part[32 * CB];
@@ -576,6 +667,7 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
       X = cur; Y = prev;                                 // filtered block in X, Y is scratch
       }
     }
+    GCCB_TICK(0);
     // ---- CGS2: orthonormalise the columns of X in place (row-major: all dots of a column at once)
     for (int j = 0; j < CB; ++j) {
       // classical Gram-Schmidt with selective re-orthogonalisation (Daniel-Gragg-Kaufman test): the
@@ -611,6 +703,7 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
       for (int r = tid; r < n; r += NT) X[(size_t)r * ld + j] *= inv;
       __syncthreads();
     }
+    GCCB_TICK(1);
     // ---- Z = L Q (into Y), H = Q^T Z ----------------------------------------------------------------
     spmm_cheb(S, X, Y, ld, 1.0f, 0.f, 0.f);
     __syncthreads();
@@ -662,8 +755,10 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
       for (int i = tid; i < CB; i += NT) Gs[i * LD + i] += 2.0f;
       __syncthreads();
     }
+    GCCB_TICK(2);
     // ---- 48 x 48 Ritz problem: two-sided Jacobi, eigenvectors in Ws (tiles are dead now) ----------
-    jacobi_twosided<NT, float>(Gs, Ws, cs, pq, CB, LD);
+    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, fminf(1e-3f, fmaxf(1e-6f, 1e-2f * prev_worst)));
+    GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
       int rank = 0;
@@ -691,6 +786,7 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
       if (hi) X[(size_t)r * ld + 32 + lane] = a1;
     }
     __syncthreads();
+    GCCB_TICK(4);
     // ---- residuals of the wanted pairs: theta_c = x_c . L x_c ; ||L x_c - theta_c x_c|| -----------
     spmm_cheb(S, X, Y, ld, 1.0f, 0.f, 0.f);              // Y = L X
     __syncthreads();
@@ -716,9 +812,13 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
     prev_worst = w_all;
     cut = fminf(fmaxf(s_bc[1], -0.9f), 0.95f);          // smallest Ritz value of the block
     __syncthreads();
+    GCCB_TICK(5);
   }
   if (!converged && tid == 0) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
-  if (tid == 0) { dbg_iters[slot] = iter; dbg_res[slot] = prev_worst; }
+  if (tid == 0) {
+    dbg_iters[slot] = iter; dbg_res[slot] = prev_worst;
+    for (int i = 0; i < 6; ++i) dbg_phase[(size_t)slot * 8 + i] = ph[i];
+  }
   // columns 0..k-1 of X hold the k largest Ritz pairs in DESCENDING order; emit ascending
   // (data_util.py: eigsh(which='LA') returns ascending eigenvalues)
   if (eigvals)
@@ -913,9 +1013,10 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
                             const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
                             float* __restrict__ dinv_g, float* __restrict__ pos, float* __restrict__ eigvals,
                             int32_t* __restrict__ flags, int32_t* __restrict__ dbg_iters,
-                            float* __restrict__ dbg_res) {
+                            float* __restrict__ dbg_res, long long* __restrict__ dbg_phase) {
   constexpr int CB = GCCB_CF_B, LD = CB + 1, NW = NT / 32;
   GCCB_DYN_SMEM(float, dynsm);
+  long long ph[6] = {0, 0, 0, 0, 0, 0}, t_last = GCCB_CLK();
   __shared__ float Gs[CB * LD];                   // Ritz problem
   __shared__ float Hp[CB * LD];                   // this CTA's partial of H (read by the others)
   __shared__ float WT[32 * (CB + 1) * 2];         // union: Ritz vectors Ws[CB*LD] | tiles [2][32][CB+1]
@@ -1002,6 +1103,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       }
       X = cur; Y = prev;
     }
+    GCCB_TICK(0);
     // ---- CGS2 over the cluster --------------------------------------------------------------------
     for (int j = 0; j < CB; ++j) {
       float nrm2 = 0.f;
@@ -1034,6 +1136,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       for (int rl = tid; rl < nloc; rl += NT) X[(size_t)rl * ld + j] *= inv;
       __syncthreads();
     }
+    GCCB_TICK(1);
     // ---- Z = L Q, H = Q^T Z (partial per CTA, summed over the cluster) -------------------------------
     cl_sync<CS>();                                       // every slice of Q final before remote gathers
     cl_spmm(C, X, Y, 1.0f, 0.f, 0.f);
@@ -1093,7 +1196,9 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       for (int i = tid; i < CB; i += NT) Gs[i * LD + i] += 2.0f;
       __syncthreads();
     }
-    jacobi_twosided<NT, float>(Gs, Ws, cs, pq, CB, LD);   // redundant on every CTA, bit-identical
+    GCCB_TICK(2);
+    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, fminf(1e-3f, fmaxf(1e-6f, 1e-2f * prev_worst)));   // redundant per CTA, bit-identical
+    GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
       int rank = 0;
@@ -1120,6 +1225,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       if (hi) X[(size_t)rl * ld + 32 + lane] = a1;
     }
     cl_sync<CS>();                                       // also orders the Hp reads before its next write
+    GCCB_TICK(4);
     cl_spmm(C, X, Y, 1.0f, 0.f, 0.f);                    // Y = L X
     __syncthreads();
     {
@@ -1143,10 +1249,12 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
     prev_worst = w_all;
     cut = fminf(fmaxf(s_bc[1], -0.9f), 0.95f);
     __syncthreads();
+    GCCB_TICK(5);
   }
   if (C.rank == 0 && tid == 0) {
     if (!converged) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
     dbg_iters[slot] = iter; dbg_res[slot] = prev_worst;
+    for (int i = 0; i < 6; ++i) dbg_phase[(size_t)slot * 8 + i] = ph[i];
   }
   if (eigvals && C.rank == 0)
     for (int c = tid; c < pos_dim; c += NT) eigvals[(size_t)slot * pos_dim + c] = c < k ? theta[k - 1 - c] : 0.f;
@@ -1203,7 +1311,8 @@ static size_t posenc_ws_ints(int B) { return (((size_t)6 * 2 * B + 6 + 2 * B) + 
 
 extern "C" size_t gccb_posenc_workspace(int32_t batch, int32_t node_cap) {
   return posenc_ws_ints(batch) * sizeof(int32_t) +
-         ((size_t)2 * batch + (size_t)2 * node_cap + (size_t)2 * 2 * node_cap * (GCCB_CF_B + 1)) * sizeof(float);
+         ((size_t)2 * batch + (size_t)2 * node_cap + (size_t)2 * 2 * node_cap * (GCCB_CF_B + 1)) * sizeof(float) +
+         (size_t)2 * batch * 8 * sizeof(long long) + 64;
 }
 
 extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t normalize,
@@ -1224,6 +1333,8 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   float* dbg_res = (float*)((int32_t*)workspace + posenc_ws_ints(B));      // per slot: final residual
   float* dinv = dbg_res + (size_t)2 * B;
   float* blocks = dinv + (size_t)2 * batch->node_cap;
+  // diagnostics tail: per-slot phase cycle counters (8-byte aligned)
+  long long* dbg_phase = (long long*)(((uintptr_t)(blocks + (size_t)2 * 2 * batch->node_cap * (GCCB_CF_B + 1)) + 15) & ~(uintptr_t)15);
   GCCB_LAUNCH(posenc_classify_kernel, 1, 256, 0, stream, batch->counters, batch->node_off, B, worklist, counts);
   auto kgiant = posenc_chfsi_kernel<0, 1024>;
 #ifndef GCCB_EMU
@@ -1262,7 +1373,7 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   gccb_stream_t s_giant = stream, s_huge = stream, s_big = stream, s_mid2 = stream, s_small = stream, s_mid1 = stream;
 #endif
 #define GCCB_PE_ARGS(cls) worklist, counts, cls, B, batch->node_cap, batch->edge_cap, batch->node_off, batch->indptr, \
-    batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv, pos, eigvals, batch->flags, dbg_iters, dbg_res
+    batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv, pos, eigvals, batch->flags, dbg_iters, dbg_res, dbg_phase
   GCCB_LAUNCH(kgiant, 2 * B, 1024, 0, s_giant, GCCB_PE_ARGS(5));
   {
     const int items = 2 * B < 32 ? 2 * B : 32;           // persistent over the work list
@@ -1278,11 +1389,11 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
     cudaLaunchKernelEx(&cfg, khuge, (const int32_t*)worklist, (const int32_t*)counts, 4, B, batch->node_cap,
                        batch->edge_cap, (const int32_t*)batch->node_off, (const int32_t*)batch->indptr,
                        (const int32_t*)batch->indices, (const int32_t*)batch->sub_deg, pos_dim, normalize, dinv, pos,
-                       eigvals, batch->flags, dbg_iters, dbg_res);
+                       eigvals, batch->flags, dbg_iters, dbg_res, dbg_phase);
 #else
     GCCB_LAUNCH(khuge, items, 1024, s_d, s_huge, worklist, counts, 4, B, batch->node_cap, batch->edge_cap,
                 batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, dinv, pos,
-                eigvals, batch->flags, dbg_iters, dbg_res);
+                eigvals, batch->flags, dbg_iters, dbg_res, dbg_phase);
 #endif
   }
   GCCB_LAUNCH(kbig, 2 * B, 1024, s_c, s_big, GCCB_PE_ARGS(3));

@@ -58,3 +58,20 @@ for st in range(1, 9):
     top = np.argsort(-n)[:3]
     print("batch %d: posenc %.2f ms; largest (n, iters, res): %s; max iters %d" % (
         st, ev[0].elapsed_time(ev[1]), [(int(n[i]), int(it[i]), float("%.1e" % rs[i])) for i in top], it.max()))
+
+# phase cycle counters of the last batch (thread 0 of each CTA / rank 0 of each cluster)
+cap = buf.node_cap
+off_f = ni * 4 + (2 * B + 2 * cap + 2 * 2 * cap * 49) * 4
+off_f = (off_f + 15) // 16 * 16
+# the tail is aligned relative to the buffer base address
+base = ws.data_ptr()
+addr = (base + ni * 4 + (2 * B + 2 * cap + 2 * 2 * cap * 49) * 4 + 15) // 16 * 16
+phase = ws[addr - base: addr - base + 2 * B * 8 * 8].view(torch.int64).view(2 * B, 8).cpu().numpy()
+names = ["filter", "gram-schmidt", "H=QtLQ", "ritz", "X=QW", "residual"]
+n = buf.counters[:, 0].cpu().numpy()
+for lo, hi in ((64, 96), (96, 160), (160, 480), (480, 100000)):
+    m = (n > lo) & (n <= hi)
+    if m.sum():
+        tot = phase[m][:, :6].sum(0).astype(float)
+        print("n in (%d,%d]: cycles/ego-net %.0f k; split %s" % (lo, hi, tot.sum() / m.sum() / 1e3,
+              ", ".join("%s %.0f%%" % (nm, 100 * t / tot.sum()) for nm, t in zip(names, tot))))
