@@ -12,6 +12,7 @@ One step = sample -> induce -> positional features -> GIN q/k -> InfoNCE -> back
 step with host-side seeds (pinned -> H2D) and a loss read-back (D2H) inside the timed region.
 """
 import argparse
+import contextlib
 import json
 import math
 import os
@@ -282,7 +283,8 @@ def run_ours(args, cfg):
     model, ema = mk(), mk()
     ema.load_state_dict(model.state_dict())                 # moment_update(model, model_ema, 0), train.py:623-624
     model, ema = model.to(dev), ema.to(dev)
-    contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
+    with contextlib.redirect_stdout(sys.stderr):           # the reference prints the queue shape; keep stdout = one JSON line
+        contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
     eng = PretrainEngine(ds, model, ema, contrast, moco=True, rank=rank, world_size=world)
     lib = _lib.get()
     total_steps = 75000                                     # train.py defaults: 100 epochs x 750
@@ -299,41 +301,38 @@ def run_ours(args, cfg):
     for i in range(args.warmup):
         eng.step(lr=lr_at(eng.global_step))
     barrier()
-    ds.buffers.check_flags()
+    for b_ in eng.bufs:
+        b_.check_flags()
     # ---- timed region: K steps, inputs resident in HBM, no host sync inside -------------------
+    # eng.step() trains on batch t (main stream) while sampler + eigensolver of batch t+1 run on
+    # the engine's data stream (loader run-ahead, as the reference's DataLoader workers do).
     clocks = ClockSampler(local)
     clocks.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    samp_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-                torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    cnt_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+    eng.count_acc = torch.zeros(4, dtype=torch.float64, device=dev)   # algorithmic-byte counters (device side)
+    eng.timing = []
     launches0 = lib.gccb_launch_count()
     barrier()
     ev[0].record()
     for i in range(args.steps):
-        # same step as eng.step(), with events around the sampler and the eigensolver
-        samp_ev[i][0].record()
-        first = (eng.global_step * world + rank) * B
-        ds.sample_batch(first_sample=first, posenc=False)
-        samp_ev[i][1].record()
-        cnt_acc += ds.buffers.counters.double().sum(0)      # algorithmic-byte counters (device side)
-        _posenc(ds)
-        samp_ev[i][2].record()
-        _rest_of_step(eng, lr_at(eng.global_step))
+        eng.step(lr=lr_at(eng.global_step))
     ev[1].record()
     barrier()
     ms = ev[0].elapsed_time(ev[1])
     launches = lib.gccb_launch_count() - launches0
     clk = clocks.stop()
+    samp_ev, eng.timing = eng.timing, None
+    cnt_acc, eng.count_acc = eng.count_acc, None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = 2.0 * B * world * args.steps / (ms_max / 1e3)
-    ds.buffers.check_flags()
+    for b_ in eng.bufs:
+        b_.check_flags()
     stats = eng.read_stats()
-    samp_ms = sum(a.elapsed_time(b) for a, b, _ in samp_ev) / args.steps
-    eig_ms = sum(b.elapsed_time(c) for _, b, c in samp_ev) / args.steps
+    samp_ms = sum(a.elapsed_time(b) for a, b, _ in samp_ev) / len(samp_ev)
+    eig_ms = sum(b.elapsed_time(c) for _, b, c in samp_ev) / len(samp_ev)
     n_sum, m_sum, t_sum, deg_sum = [float(x) / args.steps for x in cnt_acc.tolist()]
     # per view bytes = T*(8+4) + sum_{v in subv}(8 + 4 deg v) + 4*(2n + 1 + m)
     alg_bytes = t_sum * 12 + (8 * n_sum + 4 * deg_sum) + 4 * (2 * n_sum + 2 * B + m_sum)
@@ -350,8 +349,9 @@ def run_ours(args, cfg):
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_step": alg_bytes, "ms_per_launch_group": samp_ms,
                 "note": "latency-bound at 512 ego-nets/step (12 MB of traffic); see DESIGN.md"}
-    phases = {"sampler_ms": samp_ms, "eigensolver_ms": eig_ms,
-              "encoder_head_optim_ms": ms / args.steps - samp_ms - eig_ms}
+    phases = {"sampler_ms": samp_ms, "eigensolver_ms": eig_ms, "step_ms": ms / args.steps,
+              "note": "sampler + eigensolver of batch t+1 run on the data stream concurrently with the "
+                      "encoder/head/optimizer of batch t on the main stream; step_ms is the pipeline period"}
 
     # ---- e2e: host seeds (pinned) -> H2D each step, loss D2H each step ---------------------------
     cdf_host = ds.graph.cdf.cpu().numpy()
@@ -359,17 +359,17 @@ def run_ours(args, cfg):
     n_e2e = max(args.steps // 2, 5)
     host_seeds = torch.from_numpy(np.searchsorted(cdf_host, rs.random_sample((n_e2e + 2, B)), side="right")
                                   .clip(max=len(cdf_host) - 1).astype(np.int64)).pin_memory()
-    seeds_dev = torch.zeros(B, dtype=torch.int64, device=dev)
     loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+    seeds_ring = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
     for i in range(2):
-        seeds_dev.copy_(host_seeds[i], non_blocking=True)
-        eng.step(lr=lr_at(eng.global_step), seeds=seeds_dev)
+        seeds_ring[i & 1].copy_(host_seeds[i], non_blocking=True)
+        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i & 1])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n_e2e):
-        seeds_dev.copy_(host_seeds[2 + i], non_blocking=True)
-        eng.step(lr=lr_at(eng.global_step), seeds=seeds_dev)
+        seeds_ring[i & 1].copy_(host_seeds[2 + i], non_blocking=True)   # seeds of the batch prepared this step
+        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i & 1])
         loss_host.copy_(eng.stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()           # the reference's .item() per step (train.py:420-422)
     e1.record()
@@ -394,7 +394,7 @@ def run_ours(args, cfg):
             "pairs_per_sec": value / 2.0,
             "e2e": {"value": e2e_value, "unit": "subgraphs/sec", "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": 16, "steps": n_e2e,
-                    "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step -> stats D2H + sync"},
+                    "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step (trains batch t, prepares batch t+1 from these seeds) -> stats D2H + sync"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "clocks": clk, "roofline": roofline, "phases_ms": phases,
             "loss": stats["loss"], "grad_norm": stats["grad_norm"]}
@@ -407,20 +407,6 @@ def run_ours(args, cfg):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def _posenc(ds):
-    import ctypes as C
-    from gcc_b200 import _lib
-    buf = ds.buffers
-    _lib.check(_lib.get().gccb_posenc(C.byref(buf.c), buf.pos_dim, 1, _lib.dptr(buf.pos), _lib.dptr(buf.eigvals),
-                                      _lib.dptr(buf.ws_posenc), buf.ws_posenc.numel(), _lib.stream_ptr()),
-               "gccb_posenc")
-
-
-def _rest_of_step(eng, lr):
-    """PretrainEngine.step() minus sampling/posenc (already issued with events around them)."""
-    eng.step(lr=lr, _presampled=True)
 
 
 def main():

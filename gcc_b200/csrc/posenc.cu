@@ -757,7 +757,7 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
     }
     GCCB_TICK(2);
     // ---- 48 x 48 Ritz problem: two-sided Jacobi, eigenvectors in Ws (tiles are dead now) ----------
-    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, fminf(1e-3f, fmaxf(1e-6f, 1e-2f * prev_worst)));
+    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-4f : 1e-6f);   // the first block is random: no need for more
     GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
@@ -1197,7 +1197,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       __syncthreads();
     }
     GCCB_TICK(2);
-    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, fminf(1e-3f, fmaxf(1e-6f, 1e-2f * prev_worst)));   // redundant per CTA, bit-identical
+    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-4f : 1e-6f);   // redundant per CTA, bit-identical
     GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];

@@ -213,10 +213,15 @@ class LoadBalanceGraphDataset(torch.utils.data.IterableDataset):
                                          _lib.dptr(buf.ws_sample), buf.ws_sample.numel(), st),
                    "gccb_sample_batch")
         if posenc:
-            _lib.check(lib.gccb_posenc(C.byref(buf.c), buf.pos_dim, 1, _lib.dptr(buf.pos),
-                                       _lib.dptr(buf.eigvals), _lib.dptr(buf.ws_posenc),
-                                       buf.ws_posenc.numel(), st), "gccb_posenc")
+            self.posenc(buf)
         return buf
+
+    def posenc(self, buffers=None):
+        """Positional features of both views of a sampled batch (data_util.py:242-281)."""
+        buf = buffers or self.buffers
+        _lib.check(_lib.get().gccb_posenc(C.byref(buf.c), buf.pos_dim, 1, _lib.dptr(buf.pos),
+                                          _lib.dptr(buf.eigvals), _lib.dptr(buf.ws_posenc),
+                                          buf.ws_posenc.numel(), _lib.stream_ptr()), "gccb_posenc")
 
     def __iter__(self):
         """Yields batched (graph_q, graph_k) -- what DataLoader(collate_fn=batcher()) yields in the

@@ -26,7 +26,7 @@ from .parallel import StepExchange, first_sample_id
 class PretrainEngine:
     def __init__(self, dataset, model, model_ema, contrast, moco=True, learning_rate=0.005,
                  betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, clip_norm=1.0, alpha=0.999,
-                 nce_t=0.07, rank=0, world_size=1, process_group=None):
+                 nce_t=0.07, rank=0, world_size=1, process_group=None, prefetch=True):
         _lib.require_device()
         self.lib = _lib.get()
         self.ds, self.model, self.model_ema, self.contrast = dataset, model, model_ema, contrast
@@ -71,6 +71,22 @@ class PretrainEngine:
             if moco and K % (world_size * B) != 0:
                 raise ValueError("queue size must be a multiple of world_size*batch (identical queues)")
         self.launches_per_step = None
+        # Loader run-ahead (the reference's DataLoader workers prepare batch t+1 while the model
+        # trains on batch t, train.py:577-586): sampler + eigensolver of the NEXT batch run on a
+        # second stream into the other half of a double buffer and overlap this step's encoder.
+        self.prefetch = bool(prefetch)
+        self.count_acc = None                          # optional float64[4]: sums of buf.counters
+        self.timing = None                             # optional list collecting per-step events
+        if self.prefetch:
+            from .datasets.graph_dataset import BatchBuffers
+            ds = dataset
+            self.bufs = [ds.buffers, BatchBuffers(B, ds.node_cap, ds.edge_cap, ds.buffers.pos_dim,
+                                                  ds.graph.max_budget, dev)]
+            self.data_stream = torch.cuda.Stream(device=dev, priority=0)
+            self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            self.prepared = 0                          # batches issued to the data stream so far
+        self.cur_buf = dataset.buffers
 
     # -------------------------------------------------------------------------------------------
     def _hyper(self, lr):
@@ -81,15 +97,57 @@ class PretrainEngine:
         self.hyper_host[2] = math.sqrt(1.0 - b2 ** self.adam_t)
         self.hyper.copy_(self.hyper_host, non_blocking=True)
 
+    def _prepare(self, seeds):
+        """Issue sampler + eigensolver of batch number `self.prepared` on the data stream."""
+        j = self.prepared
+        buf = self.bufs[j & 1]
+        main = torch.cuda.current_stream(self.dev)
+        ds_ = self.data_stream
+        if j >= 2:
+            ds_.wait_event(self.consumed[j & 1])       # the step that read this half has finished with it
+        else:
+            ds_.wait_stream(main)
+        if seeds is not None:
+            ds_.wait_stream(main)                      # the caller's H2D copy of the seeds is ordered on `main`
+            seeds.record_stream(ds_)
+        with torch.cuda.stream(ds_):
+            t = None
+            if self.timing is not None:
+                t = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                t[0].record()
+            first = first_sample_id(j, self.world, self.rank, self.B)
+            self.ds.sample_batch(first_sample=first, seeds=seeds, buffers=buf, posenc=False)
+            if t:
+                t[1].record()
+            self.ds.posenc(buf)
+            if t:
+                t[2].record()
+                self.timing.append(t)
+            self.ready[j & 1].record()
+        self.prepared = j + 1
+
     def step(self, lr=None, seeds=None, _presampled=False):
         """One optimisation step.  `seeds`: optional int64 CUDA tensor [B] (else drawn on device
-        from the Philox stream).  Returns nothing; read_stats() syncs."""
+        from the Philox stream); with prefetch on they seed the batch being PREPARED by this call
+        (consumed by the next one), like a DataLoader running one batch ahead -- the first call
+        prepares two.  Returns nothing; read_stats() syncs."""
         lib, st = self.lib, _lib.stream_ptr()
         ds, model, ema = self.ds, self.model, self.model_ema
         B, H, L = self.B, self.H, self.L
         lr = self.lr0 if lr is None else lr
-        first = first_sample_id(self.global_step, self.world, self.rank, B)
-        buf = ds.buffers if _presampled else ds.sample_batch(first_sample=first, seeds=seeds)
+        if _presampled:
+            buf = ds.buffers
+        elif self.prefetch:
+            while self.prepared < self.global_step + 2:
+                self._prepare(seeds)
+            buf = self.bufs[self.global_step & 1]
+            torch.cuda.current_stream(self.dev).wait_event(self.ready[self.global_step & 1])
+        else:
+            first = first_sample_id(self.global_step, self.world, self.rank, B)
+            buf = ds.sample_batch(first_sample=first, seeds=seeds)
+        self.cur_buf = buf
+        if self.count_acc is not None:
+            self.count_acc += buf.counters.double().sum(0)
         gq, gk = BatchedSubgraphs(buf, 0), BatchedSubgraphs(buf, 1)
         step = self.global_step
         _, _, saved_q = model._run_forward(gq, True, drop_step=step, drop_base=0, acts=self.acts_q,
@@ -112,6 +170,8 @@ class PretrainEngine:
                                         _lib.dptr(self.nce_ws), self.nce_ws.numel(), st), "gccb_e2e_nce")
             model._run_backward(gq, saved_q, self.dq, grads_flat=self.grads, ws=self.bwd_ws)
             model._run_backward(gk, saved_k, self.dk, grads_flat=self.grads, ws=self.bwd_ws)
+        if self.prefetch and not _presampled:
+            self.consumed[self.global_step & 1].record()
         grads, scale = self.grads, 1.0
         if self.world > 1:
             # the ONE collective of the step: keys + gradients + stats, then a fixed-rank-order sum
@@ -147,7 +207,8 @@ class PretrainEngine:
 
     def read_stats(self):
         """Host sync: loss, prob (mean positive logit), pre-clip grad norm, batch sizes, flags."""
-        buf = self.ds.buffers
+        buf = self.cur_buf
+        torch.cuda.synchronize(self.dev)
         buf.check_flags()
         s = self.stats.tolist()
         sizes = buf.node_off[:, self.B].tolist() + buf.edge_off[:, self.B].tolist()
