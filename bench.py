@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--prefetch", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="batches the sampler/eigensolver streams run ahead of the training stream")
     return ap.parse_args()
 
 
@@ -285,7 +287,8 @@ def run_ours(args, cfg):
     model, ema = model.to(dev), ema.to(dev)
     with contextlib.redirect_stdout(sys.stderr):           # the reference prints the queue shape; keep stdout = one JSON line
         contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
-    eng = PretrainEngine(ds, model, ema, contrast, moco=True, rank=rank, world_size=world)
+    eng = PretrainEngine(ds, model, ema, contrast, moco=True, rank=rank, world_size=world,
+                         prefetch=args.prefetch)
     lib = _lib.get()
     total_steps = 75000                                     # train.py defaults: 100 epochs x 750
 
@@ -360,16 +363,16 @@ def run_ours(args, cfg):
     host_seeds = torch.from_numpy(np.searchsorted(cdf_host, rs.random_sample((n_e2e + 2, B)), side="right")
                                   .clip(max=len(cdf_host) - 1).astype(np.int64)).pin_memory()
     loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
-    seeds_ring = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
+    seeds_ring = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(4)]
     for i in range(2):
-        seeds_ring[i & 1].copy_(host_seeds[i], non_blocking=True)
-        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i & 1])
+        seeds_ring[i & 3].copy_(host_seeds[i], non_blocking=True)
+        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i & 3])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n_e2e):
-        seeds_ring[i & 1].copy_(host_seeds[2 + i], non_blocking=True)   # seeds of the batch prepared this step
-        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i & 1])
+        seeds_ring[i & 3].copy_(host_seeds[2 + i], non_blocking=True)   # seeds of the batch prepared this step
+        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i & 3])
         loss_host.copy_(eng.stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()           # the reference's .item() per step (train.py:420-422)
     e1.record()

@@ -1356,15 +1356,29 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   // The size classes are independent: fork them over side streams (event fork/join, legal inside
   // CUDA-graph capture) so that the few long-running large ego-nets overlap the many small ones.
 #ifndef GCCB_EMU
-  static cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  static cudaEvent_t ev_fork = nullptr, ev_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  if (!side[0]) {
-    for (int i = 0; i < 5; ++i) {
-      cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
-      cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
+  // one set of side streams per caller stream (several batches may be in flight on different
+  // caller streams; sharing one set would serialise their size classes)
+  struct SideSet { cudaStream_t key; bool used; cudaStream_t side[5]; cudaEvent_t ev_fork, ev_join[5]; };
+  static SideSet sets[8];
+  static int nsets = 0;
+  SideSet* ss = nullptr;
+  for (int i = 0; i < nsets; ++i)
+    if (sets[i].key == (cudaStream_t)stream) ss = &sets[i];
+  if (!ss) {
+    ss = &sets[nsets < 8 ? nsets++ : 7];                   // beyond 8 caller streams: share the last set
+    if (!ss->used) {
+      for (int i = 0; i < 5; ++i) {
+        cudaStreamCreateWithFlags(&ss->side[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ss->ev_join[i], cudaEventDisableTiming);
+      }
+      cudaEventCreateWithFlags(&ss->ev_fork, cudaEventDisableTiming);
+      ss->used = true;
     }
-    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    ss->key = (cudaStream_t)stream;
   }
+  cudaStream_t* side = ss->side;
+  cudaEvent_t ev_fork = ss->ev_fork;
+  cudaEvent_t* ev_join = ss->ev_join;
   cudaStream_t main_s = (cudaStream_t)stream;
   cudaEventRecord(ev_fork, main_s);
   for (int i = 0; i < 5; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);

@@ -26,7 +26,7 @@ from .parallel import StepExchange, first_sample_id
 class PretrainEngine:
     def __init__(self, dataset, model, model_ema, contrast, moco=True, learning_rate=0.005,
                  betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, clip_norm=1.0, alpha=0.999,
-                 nce_t=0.07, rank=0, world_size=1, process_group=None, prefetch=True):
+                 nce_t=0.07, rank=0, world_size=1, process_group=None, prefetch=2):
         _lib.require_device()
         self.lib = _lib.get()
         self.ds, self.model, self.model_ema, self.contrast = dataset, model, model_ema, contrast
@@ -71,21 +71,26 @@ class PretrainEngine:
             if moco and K % (world_size * B) != 0:
                 raise ValueError("queue size must be a multiple of world_size*batch (identical queues)")
         self.launches_per_step = None
-        # Loader run-ahead (the reference's DataLoader workers prepare batch t+1 while the model
-        # trains on batch t, train.py:577-586): sampler + eigensolver of the NEXT batch run on a
-        # second stream into the other half of a double buffer and overlap this step's encoder.
-        self.prefetch = bool(prefetch)
+        # Loader run-ahead (the reference's DataLoader workers prepare later batches while the
+        # model trains on batch t, train.py:577-586): sampler + eigensolver of batches t+1..t+S run
+        # on S data streams into a ring of S+1 batch buffers and overlap this step's encoder.  The
+        # eigensolver's critical path is a few very large ego-nets, so S=2 batches in flight fill
+        # the SMs that one batch leaves idle.  prefetch=0 runs everything on the caller's stream.
+        self.prefetch = 2 if prefetch is True else int(prefetch)
         self.count_acc = None                          # optional float64[4]: sums of buf.counters
-        self.timing = None                             # optional list collecting per-step events
+        self.timing = None                             # optional list collecting per-batch events
+        self.timing_main = None                        # same for the training stream
         if self.prefetch:
             from .datasets.graph_dataset import BatchBuffers
             ds = dataset
-            self.bufs = [ds.buffers, BatchBuffers(B, ds.node_cap, ds.edge_cap, ds.buffers.pos_dim,
-                                                  ds.graph.max_budget, dev)]
-            self.data_stream = torch.cuda.Stream(device=dev, priority=0)
-            self.ready = [torch.cuda.Event(), torch.cuda.Event()]
-            self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
-            self.prepared = 0                          # batches issued to the data stream so far
+            S = self.prefetch
+            self.depth = S + 1
+            self.bufs = [ds.buffers] + [BatchBuffers(B, ds.node_cap, ds.edge_cap, ds.buffers.pos_dim,
+                                                     ds.graph.max_budget, dev) for _ in range(S)]
+            self.data_streams = [torch.cuda.Stream(device=dev, priority=0) for _ in range(S)]
+            self.ready = [torch.cuda.Event() for _ in range(self.depth)]
+            self.consumed = [torch.cuda.Event() for _ in range(self.depth)]
+            self.prepared = 0                          # batches issued to the data streams so far
         self.cur_buf = dataset.buffers
 
     # -------------------------------------------------------------------------------------------
@@ -100,11 +105,12 @@ class PretrainEngine:
     def _prepare(self, seeds):
         """Issue sampler + eigensolver of batch number `self.prepared` on the data stream."""
         j = self.prepared
-        buf = self.bufs[j & 1]
+        slot = j % self.depth
+        buf = self.bufs[slot]
         main = torch.cuda.current_stream(self.dev)
-        ds_ = self.data_stream
-        if j >= 2:
-            ds_.wait_event(self.consumed[j & 1])       # the step that read this half has finished with it
+        ds_ = self.data_streams[j % self.prefetch]
+        if j >= self.depth:
+            ds_.wait_event(self.consumed[slot])        # the step that read this slot has finished with it
         else:
             ds_.wait_stream(main)
         if seeds is not None:
@@ -123,14 +129,14 @@ class PretrainEngine:
             if t:
                 t[2].record()
                 self.timing.append(t)
-            self.ready[j & 1].record()
+            self.ready[slot].record()
         self.prepared = j + 1
 
     def step(self, lr=None, seeds=None, _presampled=False):
         """One optimisation step.  `seeds`: optional int64 CUDA tensor [B] (else drawn on device
         from the Philox stream); with prefetch on they seed the batch being PREPARED by this call
-        (consumed by the next one), like a DataLoader running one batch ahead -- the first call
-        prepares two.  Returns nothing; read_stats() syncs."""
+        (consumed `prefetch` steps later), like a DataLoader running ahead -- the first call
+        prepares prefetch+1 batches.  Returns nothing; read_stats() syncs."""
         lib, st = self.lib, _lib.stream_ptr()
         ds, model, ema = self.ds, self.model, self.model_ema
         B, H, L = self.B, self.H, self.L
@@ -138,14 +144,18 @@ class PretrainEngine:
         if _presampled:
             buf = ds.buffers
         elif self.prefetch:
-            while self.prepared < self.global_step + 2:
+            while self.prepared < self.global_step + self.depth:
                 self._prepare(seeds)
-            buf = self.bufs[self.global_step & 1]
-            torch.cuda.current_stream(self.dev).wait_event(self.ready[self.global_step & 1])
+            slot = self.global_step % self.depth
+            buf = self.bufs[slot]
+            torch.cuda.current_stream(self.dev).wait_event(self.ready[slot])
         else:
             first = first_sample_id(self.global_step, self.world, self.rank, B)
             buf = ds.sample_batch(first_sample=first, seeds=seeds)
         self.cur_buf = buf
+        if self.timing_main is not None:
+            tm = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            tm[0].record()
         if self.count_acc is not None:
             self.count_acc += buf.counters.double().sum(0)
         gq, gk = BatchedSubgraphs(buf, 0), BatchedSubgraphs(buf, 1)
@@ -171,7 +181,7 @@ class PretrainEngine:
             model._run_backward(gq, saved_q, self.dq, grads_flat=self.grads, ws=self.bwd_ws)
             model._run_backward(gk, saved_k, self.dk, grads_flat=self.grads, ws=self.bwd_ws)
         if self.prefetch and not _presampled:
-            self.consumed[self.global_step & 1].record()
+            self.consumed[self.global_step % self.depth].record()
         grads, scale = self.grads, 1.0
         if self.world > 1:
             # the ONE collective of the step: keys + gradients + stats, then a fixed-rank-order sum
@@ -203,6 +213,9 @@ class PretrainEngine:
                                                  B, H, self.K, _lib.dptr(self.index_dev), st),
                            "gccb_moco_enqueue")
             self.contrast.index = (self.contrast.index + B * self.world) % self.K
+        if self.timing_main is not None:
+            tm[1].record()
+            self.timing_main.append(tm)
         self.global_step += 1
 
     def read_stats(self):
