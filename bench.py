@@ -241,7 +241,7 @@ def run_reference(args, cfg):
     cpu_arm(cfg, graph_np, max(args.warmup, 1), 0)                      # warm-up steps
     r = cpu_arm(cfg, graph_np, args.steps, 240.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "subgraphs/sec",
-            "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "model_steps_timed": r["steps"],
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(cfg, 1), "config": args.config},
@@ -249,7 +249,7 @@ def run_reference(args, cfg):
                                                "sample", "split_seconds", "split_note")},
             "e2e": {"value": r["value"], "unit": "subgraphs/sec", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args, cfg):
@@ -352,6 +352,13 @@ def run_ours(args, cfg):
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_step": alg_bytes, "ms_per_launch_group": samp_ms,
                 "note": "latency-bound at 512 ego-nets/step (12 MB of traffic); see DESIGN.md"}
+    try:
+        roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[
+            "sampler_group_dram_bytes_per_step"]
+        roofline["traffic_source"] = "profiles/r01_sampler_ncu_full.csv (one ncu --set full capture)"
+    except Exception:
+        pass
+    eig = eigensolver_report(eng.cur_buf, eig_ms)
     phases = {"sampler_ms": samp_ms, "eigensolver_ms": eig_ms, "step_ms": ms / args.steps,
               "note": "sampler + eigensolver of batch t+1 run on the data stream concurrently with the "
                       "encoder/head/optimizer of batch t on the main stream; step_ms is the pipeline period"}
@@ -399,7 +406,7 @@ def run_ours(args, cfg):
                     "d2h_bytes_per_step": 16, "steps": n_e2e,
                     "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step (trains batch t, prepares batch t+1 from these seeds) -> stats D2H + sync"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
-            "clocks": clk, "roofline": roofline, "phases_ms": phases,
+            "clocks": clk, "roofline": roofline, "eigensolver": eig, "phases_ms": phases,
             "loss": stats["loss"], "grad_norm": stats["grad_norm"]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         graph_np = (g.indptr.cpu().numpy(), g.indices.cpu().numpy())
@@ -407,14 +414,58 @@ def run_ours(args, cfg):
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "workers", "model_threads", "kind",
                                                    "sample", "split_seconds", "split_note")}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def eigensolver_report(buf, eig_ms):
+    """the eigensolver has no closed-form byte count -- report n, k, iterations and
+    an fp32 FLOP estimate against the CUDA-core peak.  Per ChFSI iteration on an n-node, m-edge
+    ego-net with a 48-column block: filter deg*(2(m+n)+3n)*48, Gram-Schmidt 2n*48^2 (one pass),
+    H = Q^T L Q 2(m+n)*48 + 2n*48^2, 48x48 Jacobi ~6 sweeps * 47 rounds * 14e3, X = QW 2n*48^2,
+    residual 2(m+n)*48 + 6n*48; direct Jacobi (n <= 64): sweeps * 4 n^3."""
+    import numpy as np
+    it, res = buf.eig_debug()
+    it, res = it.cpu().numpy().astype(np.int64), res.cpu().numpy()
+    cnt = buf.counters.cpu().numpy().astype(np.float64)
+    n, m = cnt[:, 0], cnt[:, 1]
+    ch = it > 0
+    deg_sum = np.where(it >= 1, 4, 0) + 8 * np.maximum(it - 1, 0)
+    per_iter = 2 * n * 48 ** 2 * 3 + (2 * (m + n) * 48) * 2 + 6 * n * 48 + 6 * 47 * 14e3
+    flops = np.where(ch, deg_sum * (2 * (m + n) + 3 * n) * 48 + it * per_iter, -it * 4.0 * n ** 3)
+    total = float(flops.sum())
+    peak = 148 * 128 * 2 * 1.965e9 / 1e12                   # fp32 FMA on the CUDA cores at 1965 MHz
+    ach = total / (eig_ms / 1e3) / 1e12
+    return {"bound": "fp32 CUDA-core FMA + shared-memory/barrier latency (neither HBM nor tensor; SURVEY 8d)",
+            "k": 32, "block": 48, "egonets": int(len(n)), "mean_n": float(n.mean()), "max_n": int(n.max()),
+            "mean_iterations_chfsi": float(it[ch].mean()) if ch.any() else 0.0,
+            "max_iterations": int(it.max()), "max_residual": float(res.max()),
+            "est_flop_per_batch": total, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak, "ms_per_batch": eig_ms, "egonets_per_sec": len(n) / (eig_ms / 1e3)}
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's
+    version banner, the reference-style queue-shape print) was diverted to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
     cfg = CONFIGS[args.config]
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                          # fd-level: also catches C libraries
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

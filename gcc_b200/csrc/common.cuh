@@ -16,6 +16,28 @@ namespace gccb { extern unsigned long long g_launch_count; }
   (++gccb::g_launch_count, kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__))
 #endif
 
+namespace gccb {
+// Opt a kernel into `bytes` of dynamic shared memory.  The driver call costs microseconds, so the
+// largest value already granted is remembered per kernel and the call is skipped afterwards
+// (benign race: concurrent first calls set the same attribute twice).
+template <class K>
+inline void ensure_dyn_smem(K kern, size_t bytes) {
+  struct Slot { const void* fn; size_t bytes; };
+  static Slot slots[128];
+  static int nslots = 0;
+  const void* key = (const void*)kern;
+  for (int i = 0; i < nslots; ++i)
+    if (slots[i].fn == key) {
+      if (slots[i].bytes >= bytes) return;
+      slots[i].bytes = bytes;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      return;
+    }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (nslots < 128) { slots[nslots].fn = key; slots[nslots].bytes = bytes; ++nslots; }
+}
+}  // namespace gccb
+
 #include "../../include/gccb200.h"
 
 #define GCCB_HOPCAP 64u

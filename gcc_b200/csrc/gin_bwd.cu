@@ -623,7 +623,7 @@ static int run_backward(const BwdArgs& a) {
     {
       auto k = gin_bwd_gemm2_kernel<H>;
       size_t sm = ((size_t)GCCB_TILE_ROWS * (H + 1) + (size_t)GCCB_KC * (H + 4) + 2 * 16 * H + 16 * H) * 4;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      gccb::ensure_dyn_smem(k, sm);
       GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, z1, z2, (const float*)dh, s1, P + a.lay.bn1_w[l],
                   P + a.lay.bn1_b[l], sa, P + a.lay.bna_w[l], P + a.lay.bna_b[l], sb, P + a.lay.bnb_w[l],
                   P + a.lay.bnb_b[l], d.bn_eps, (const double*)rB, (const double*)rA, P + a.lay.w2[l], dz2,
@@ -633,13 +633,13 @@ static int run_backward(const BwdArgs& a) {
     if (l == 0) {
       auto k = gin_bwd_gemm1_kernel<GCCB_DINP, H>;
       size_t sm = ((size_t)GCCB_TILE_ROWS * (H + 1) + (size_t)GCCB_KC * (GCCB_DINP + 4) + 6 * H) * 4;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      gccb::ensure_dyn_smem(k, sm);
       GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, z1, g1, s1, P + a.lay.bn1_w[l], P + a.lay.bn1_b[l],
                   d.bn_eps, (const double*)r1, P + a.lay.w1[l], inf, da);
     } else {
       auto k = gin_bwd_gemm1_kernel<H, H>;
       size_t sm = ((size_t)GCCB_TILE_ROWS * (H + 1) + (size_t)GCCB_KC * (H + 4) + 6 * H) * 4;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      gccb::ensure_dyn_smem(k, sm);
       GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, z1, g1, s1, P + a.lay.bn1_w[l], P + a.lay.bn1_b[l],
                   d.bn_eps, (const double*)r1, P + a.lay.w1[l], inf, da);
     }
@@ -670,7 +670,7 @@ static int run_backward(const BwdArgs& a) {
   {
     size_t sm = (size_t)(d.maxdeg + 1) * d.D * sizeof(float);
     auto k = gin_bwd_emb_kernel;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    gccb::ensure_dyn_smem(k, sm);
     GCCB_LAUNCH(k, 64, 256, sm, a.stream, d, node_off_v, B, sub_deg, (const float*)dh, G + a.lay.emb);
   }
   return check_launch("gccb_gin_backward");

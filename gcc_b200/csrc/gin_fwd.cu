@@ -380,20 +380,20 @@ static int run_forward(const FwdArgs& a) {
     if (l == 0) {
       auto k = gin_agg_gemm1_kernel<GCCB_DINP, H>;
       size_t sm = smem_gemm<GCCB_DINP, H>();
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      gccb::ensure_dyn_smem(k, sm);
       GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, indptr, indices, hin, P + a.lay.w1[l], d.din,
                   P + a.lay.b1[l], 0.0f, a_l, z1, s1);
     } else {
       auto k = gin_agg_gemm1_kernel<H, H>;
       size_t sm = smem_gemm<H, H>();
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      gccb::ensure_dyn_smem(k, sm);
       GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, indptr, indices, hin, P + a.lay.w1[l], H,
                   P + a.lay.b1[l], 0.0f, a_l, z1, s1);
     }
     {
       auto k = gin_bn_gemm2_kernel<H>;
       size_t sm = smem_gemm<H, H>();
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      gccb::ensure_dyn_smem(k, sm);
       GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, z1, s1, P + a.lay.bn1_w[l], P + a.lay.bn1_b[l],
                   d.bn_eps, run1, use_running, upd, d.bn_mom, P + a.lay.w2[l], P + a.lay.b2[l], z2, sa);
     }
@@ -409,7 +409,7 @@ static int run_forward(const FwdArgs& a) {
   const uint32_t keep = (uint32_t)fmin((1.0 - (double)d.drop_p) * 4294967296.0, 4294967295.0);
   auto kp = gin_pool_predict_kernel<H>;
   const size_t sm_pool = (size_t)(H > GCCB_DINP ? H : GCCB_DINP) * (H + 1) * sizeof(float);
-  cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pool);
+  gccb::ensure_dyn_smem(kp, sm_pool);
   GCCB_LAUNCH(kp, B, 256, sm_pool, a.stream, d, node_off_v, B, x0, a.d_hptrs, a.params, a.d_offs, a.d_offs + 8,
               a.al.PW, a.drop_key, a.drop_step, a.drop_base, keep, (float*)(a.acts + a.al.pooled),
               (float*)(a.acts + a.al.score), a.feat, a.pooled_user);

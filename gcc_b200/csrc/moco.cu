@@ -349,7 +349,7 @@ extern "C" int gccb_infonce_fused(const float* q, const float* k, const float* m
   const int nch = (K + ck - 1) / ck;
   const size_t smem = ((size_t)GCCB_NCE_RB * d + (size_t)ck * (d + 1) + (size_t)GCCB_NCE_RB * ck) * 4;
   auto kp = infonce_partial_kernel;
-  cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gccb::ensure_dyn_smem(kp, smem);
   cudaMemsetAsync(stats, 0, 2 * sizeof(float), (cudaStream_t)stream);
   dim3 grid(nch, (B + GCCB_NCE_RB - 1) / GCCB_NCE_RB);
   GCCB_LAUNCH(kp, grid, 256, smem, stream, q, memory, B, d, K, ck, 1.0f / T, (float*)workspace);
@@ -381,7 +381,7 @@ extern "C" int gccb_e2e_nce(const float* q, const float* k, int32_t B, int32_t d
   cudaMemsetAsync(stats, 0, 2 * sizeof(float), (cudaStream_t)stream);
   const size_t smem = ((size_t)d + B) * 4;
   auto k1 = e2e_rows_kernel;
-  cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gccb::ensure_dyn_smem(k1, smem);
   GCCB_LAUNCH(k1, B, 256, smem, stream, q, k, B, d, 1.0f / T, stats, (float*)workspace);
   dim3 grid(B, 2);
   GCCB_LAUNCH(e2e_grads_kernel, grid, 128, 0, stream, q, k, (const float*)workspace, B, d, 1.0f / T, dq, dk);

@@ -1350,9 +1350,9 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   const size_t s_b = (size_t)2 * GCCB_CF_NSM * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_c = (size_t)2 * GCCB_CF_NSM_C * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_d = (size_t)2 * ((GCCB_CF_NSM_D + CLUSTER - 1) / CLUSTER) * (GCCB_CF_B + 1) * sizeof(float);
-  cudaFuncSetAttribute(kmid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_b);
-  cudaFuncSetAttribute(kbig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_c);
-  cudaFuncSetAttribute(khuge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_d);
+  gccb::ensure_dyn_smem(kmid, s_b);
+  gccb::ensure_dyn_smem(kbig, s_c);
+  gccb::ensure_dyn_smem(khuge, s_d);
   // The size classes are independent: fork them over side streams (event fork/join, legal inside
   // CUDA-graph capture) so that the few long-running large ego-nets overlap the many small ones.
 #ifndef GCCB_EMU

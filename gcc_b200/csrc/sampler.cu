@@ -373,8 +373,8 @@ extern "C" int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds
   auto k1 = rwr_walk_unique_kernel;
   auto k3 = induce_fill_kernel;
   if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gccb::ensure_dyn_smem(k1, smem);
+    gccb::ensure_dyn_smem(k3, smem);
   }
   GCCB_LAUNCH(k1, 2 * B, GCCB_ST, smem, stream, graph->indptr, graph->indices, graph->budget_table,
               graph->budget_table_len, graph->restart_thresh, graph->key, seeds, sample_ids, B,

@@ -118,6 +118,16 @@ class BatchBuffers:
                              self.graph_id.data_ptr(), self.orig_id.data_ptr(),
                              self.counters.data_ptr(), self.flags.data_ptr())
 
+    def eig_debug(self):
+        """(iterations, worst residual) per ego-net of the last gccb_posenc on these buffers, read
+        from the debug area of its workspace (posenc.cu: worklist[6][2B] | counts[6] | iters[2B] |
+        pad to 64 ints | res[2B]).  Direct-Jacobi ego-nets report minus their sweep count."""
+        B, NC = self.B, 6
+        ints = self.ws_posenc.view(torch.int32)
+        o = NC * 2 * B + NC
+        ni = ((o + 2 * B + 63) // 64) * 64
+        return ints[o:o + 2 * B].clone(), self.ws_posenc[ni * 4: ni * 4 + 2 * B * 4].view(torch.float32).clone()
+
     def check_flags(self):
         """Host sync: raise on any device-side failure flag.  Eigensolver non-convergence is not
         fatal (the reference itself falls back to zeros after 10 ARPACK retries,

@@ -91,6 +91,9 @@ class PretrainEngine:
             self.ready = [torch.cuda.Event() for _ in range(self.depth)]
             self.consumed = [torch.cuda.Event() for _ in range(self.depth)]
             self.prepared = 0                          # batches issued to the data streams so far
+            # the training kernels are short and dependent: a high-priority stream lets their CTAs
+            # go ahead of the queued sampler / eigensolver CTAs whenever an SM slot frees up
+            self.train_stream = torch.cuda.Stream(device=dev, priority=-1)
         self.cur_buf = dataset.buffers
 
     # -------------------------------------------------------------------------------------------
@@ -133,6 +136,19 @@ class PretrainEngine:
         self.prepared = j + 1
 
     def step(self, lr=None, seeds=None, _presampled=False):
+        """One optimisation step (see _step); with prefetch on, the training part runs on the
+        engine's high-priority stream, ordered after and before the caller's current stream."""
+        if not self.prefetch or _presampled:
+            return self._step(lr, seeds, _presampled)
+        caller = torch.cuda.current_stream(self.dev)
+        self.train_stream.wait_stream(caller)
+        if seeds is not None:
+            seeds.record_stream(self.train_stream)
+        with torch.cuda.stream(self.train_stream):
+            self._step(lr, seeds, False)
+        caller.wait_stream(self.train_stream)
+
+    def _step(self, lr=None, seeds=None, _presampled=False):
         """One optimisation step.  `seeds`: optional int64 CUDA tensor [B] (else drawn on device
         from the Philox stream); with prefetch on they seed the batch being PREPARED by this call
         (consumed `prefetch` steps later), like a DataLoader running ahead -- the first call
