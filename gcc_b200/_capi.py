@@ -72,6 +72,9 @@ _PROTOS = {
                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_float, p, p, p]),
     "gccb_sum_ranks": (C.c_int, [p, C.c_int32, C.c_int64, C.c_int64, p, p]),
+    "gccb_partition_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "gccb_partition_sm_count": (C.c_int32, [p, C.c_int32]),
+    "gccb_partition_stream": (C.c_int, [p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
 }
 
 SYMBOLS = tuple(_PROTOS)

@@ -3,6 +3,7 @@
 #include <stdio.h>
 
 #include "common.cuh"
+#include <mutex>
 
 namespace gccb {
 #ifndef GCCB_EMU
@@ -25,6 +26,30 @@ int check_launch(const char* what) {
   }
   return GCCB_OK;
 }
+
+#ifndef GCCB_EMU
+cudaStream_t create_stream_like(cudaStream_t like);        // partition.cu
+
+StreamKit* stream_kit(cudaStream_t caller, int family) {
+  static StreamKit kits[16];
+  static int nkits = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < nkits; ++i)
+    if (kits[i].key == caller && kits[i].family == family) return &kits[i];
+  StreamKit* k;
+  if (nkits < 16) {
+    k = &kits[nkits++];
+    for (int i = 0; i < 5; ++i) k->side[i] = create_stream_like(caller);   // same green context as the caller
+    for (int i = 0; i < 24; ++i) cudaEventCreateWithFlags(&k->ev[i], cudaEventDisableTiming);
+  } else {
+    k = &kits[15];                                        // more caller streams than kits: share the last one
+  }
+  k->key = caller;
+  k->family = family;
+  return k;
+}
+#endif
 }  // namespace gccb
 
 extern "C" int gccb_version(void) { return GCCB_VERSION; }

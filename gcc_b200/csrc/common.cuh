@@ -16,6 +16,22 @@ namespace gccb { extern unsigned long long g_launch_count; }
   (++gccb::g_launch_count, kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__))
 #endif
 
+#ifndef GCCB_EMU
+namespace gccb {
+// Side streams + events owned by the library, one kit per (caller stream, family): several
+// calls may be in flight on different caller streams and must not serialise on shared side streams.
+// Fork/join is by events only (legal inside CUDA-graph capture).  Family 0: gccb_posenc size
+// classes; family 1: gccb_gin_backward weight-gradient stream.
+struct StreamKit {
+  cudaStream_t key;
+  int family;
+  cudaStream_t side[5];
+  cudaEvent_t ev[24];
+};
+StreamKit* stream_kit(cudaStream_t caller, int family);
+}  // namespace gccb
+#endif
+
 namespace gccb {
 // Opt a kernel into `bytes` of dynamic shared memory.  The driver call costs microseconds, so the
 // largest value already granted is remembered per kernel and the call is skipped afterwards

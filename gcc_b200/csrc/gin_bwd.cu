@@ -13,10 +13,10 @@
 
 namespace gccb {
 
-#define GCCB_WG_CHUNKS 64     // row chunks of the weight-gradient split-K
+#define GCCB_WG_CHUNKS 148    // row chunks of the weight-gradient split-K
 
 struct BwdLayout {            // byte offsets in the backward workspace
-  size_t dh, g1, dz2, da, red, dS, dpool, part, total;
+  size_t dh, g1[2], dz2[2], da, red, dS, dpool, part, total;   // g1/dz2 alternate between layers
   int DW;                     // width of dh / da rows = max(H, 64)
 };
 
@@ -26,8 +26,10 @@ inline BwdLayout make_bwd_layout(const GinDims& d, int B, int node_cap) {
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   b.DW = d.H > GCCB_DINP ? d.H : GCCB_DINP;
   b.dh = take((size_t)node_cap * b.DW * 4);
-  b.g1 = take((size_t)node_cap * d.H * 4);
-  b.dz2 = take((size_t)node_cap * d.H * 4);
+  for (int i = 0; i < 2; ++i) {
+    b.g1[i] = take((size_t)node_cap * d.H * 4);
+    b.dz2[i] = take((size_t)node_cap * d.H * 4);
+  }
   b.da = take((size_t)node_cap * b.DW * 4);
   b.red = take((size_t)(d.L - 1) * 3 * 2 * d.H * 8);
   b.dS = take((size_t)d.L * B * d.H * 4);
@@ -127,51 +129,50 @@ gin_bwd_dh_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_t* 
                   const int32_t* __restrict__ indices, const int32_t* __restrict__ graph_id,
                   const float* __restrict__ dpool_j, int DW, const float* __restrict__ da, int has_da,
                   float* __restrict__ dh) {
+  __shared__ float scratch[8 * W];
+  __shared__ int hub_rows[8];
+  __shared__ int n_hub;
   const int N = node_off_v[B];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int PER = (W + 31) / 32;
-  for (int r = blockIdx.x * 8 + warp; r < N; r += gridDim.x * 8) {
-    const int g = graph_id[r];
-    float acc[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      int c = lane + 32 * j;
-      acc[j] = c < W ? dpool_j[(size_t)g * DW + c] : 0.f;
-    }
-    if (has_da) {
+  for (int base = blockIdx.x * 8; base < N; base += gridDim.x * 8) {      // uniform over the CTA
+    if (tid == 0) n_hub = 0;
+    __syncthreads();
+    const int r = base + warp;
+    if (r < N) {
       const int beg = indptr[r], end = indptr[r + 1];
-#pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        int c = lane + 32 * j;
-        if (c < W) acc[j] += da[(size_t)r * W + c];
-      }
-      int e = beg;
-      for (; e + 3 < end; e += 4) {                       // four neighbour rows in flight
-        const int u0 = indices[e], u1 = indices[e + 1], u2 = indices[e + 2], u3 = indices[e + 3];
+      if (has_da && end - beg > GCCB_HUB_DEG) {
+        if (lane == 0) hub_rows[atomicAdd(&n_hub, 1)] = r;   // deferred: split across the CTA below
+      } else {
+        const int g = graph_id[r];
+        float acc[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
           int c = lane + 32 * j;
-          if (c < W) {
-            float x0 = da[(size_t)u0 * W + c], x1 = da[(size_t)u1 * W + c];
-            float x2 = da[(size_t)u2 * W + c], x3 = da[(size_t)u3 * W + c];
-            acc[j] += (x0 + x1) + (x2 + x3);
+          acc[j] = c < W ? dpool_j[(size_t)g * DW + c] : 0.f;
+        }
+        if (has_da) {
+#pragma unroll
+          for (int j = 0; j < PER; ++j) {
+            int c = lane + 32 * j;
+            if (c < W) acc[j] += da[(size_t)r * W + c];
           }
+          gather_range<W>(da, indices, beg, end, lane, acc);
         }
-      }
-      for (; e < end; ++e) {
-        const int u = indices[e];
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
           int c = lane + 32 * j;
-          if (c < W) acc[j] += da[(size_t)u * W + c];
+          if (c < W) dh[(size_t)r * W + c] = acc[j];
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      int c = lane + 32 * j;
-      if (c < W) dh[(size_t)r * W + c] = acc[j];
+    __syncthreads();
+    for (int hi = 0; hi < n_hub; ++hi) {
+      const int rh = hub_rows[hi];
+      const float s = gather_hub<W>(da, indices, indptr[rh], indptr[rh + 1], scratch);
+      if (tid < W) dh[(size_t)rh * W + tid] = dpool_j[(size_t)graph_id[rh] * DW + tid] + da[(size_t)rh * W + tid] + s;
     }
+    __syncthreads();
   }
 }
 
@@ -575,8 +576,6 @@ static int run_backward(const BwdArgs& a) {
   const int32_t* graph_id = a.batch->graph_id + (size_t)a.view * cap;
   const double* stats = (const double*)(a.acts + a.al.stats);
   float* dh = (float*)(a.ws + a.bl.dh);
-  float* g1 = (float*)(a.ws + a.bl.g1);
-  float* dz2 = (float*)(a.ws + a.bl.dz2);
   float* da = (float*)(a.ws + a.bl.da);
   double* red = (double*)(a.ws + a.bl.red);
   float* dS = (float*)(a.ws + a.bl.dS);
@@ -588,17 +587,38 @@ static int run_backward(const BwdArgs& a) {
   const int tiles = (cap + GCCB_TILE_ROWS - 1) / GCCB_TILE_ROWS;
   const int grid = tiles < 592 ? tiles : 592;
   const uint32_t keep = (uint32_t)fmin((1.0 - (double)d.drop_p) * 4294967296.0, 4294967295.0);
+  // The input-gradient chain (dh -> BN reductions -> GEMM2 -> GEMM1 -> next layer) is the critical
+  // path; weight / BatchNorm / head gradients only consume its by-products, so they run on a side
+  // stream (event fork per layer, one join at the end).  g1/dz2 alternate between two buffers so
+  // that layer l-1 may overwrite nothing the side stream still reads from layer l; layer l-2
+  // waits for the side work of layer l before reusing its buffers.
+#ifndef GCCB_EMU
+  StreamKit* kit = stream_kit((cudaStream_t)a.stream, 1);
+  cudaStream_t main_s = (cudaStream_t)a.stream;
+  gccb_stream_t side = kit->side[0];
+  cudaEvent_t* ev_main = kit->ev;                          // [0..7]  main -> side, per layer
+  cudaEvent_t* ev_side = kit->ev + 8;                      // [8..15] side -> main, per layer
+  cudaEvent_t ev_head = kit->ev[16], ev_join = kit->ev[17];
+#else
+  gccb_stream_t side = a.stream;
+#endif
   cudaMemsetAsync(red, 0, (size_t)(d.L - 1) * 3 * 2 * H * sizeof(double), (cudaStream_t)a.stream);
   auto kpb = gin_pool_predict_bwd_kernel<H>;
   GCCB_LAUNCH(kpb, B, 256, 0, a.stream, d, node_off_v, B, P, a.lay, (const float*)(a.acts + a.al.score),
               a.dfeat, a.drop_key, a.drop_step, a.drop_base, keep, DW, dS, dpool);
+#ifndef GCCB_EMU
+  cudaEventRecord(ev_head, main_s);
+  cudaStreamWaitEvent((cudaStream_t)side, ev_head, 0);
+#endif
   {
     int maxout = H * (d.din > H ? d.din : H) + H;
     dim3 gr((maxout + 255) / 256, d.L);
-    GCCB_LAUNCH(gin_pred_wgrad_kernel, gr, 256, 0, a.stream, d, B, a.lay, (const float*)dS,
+    GCCB_LAUNCH(gin_pred_wgrad_kernel, gr, 256, 0, side, d, B, a.lay, (const float*)dS,
                 (const float*)(a.acts + a.al.pooled), a.al.PW, G);
   }
   for (int l = d.L - 2; l >= 0; --l) {
+    float* g1 = (float*)(a.ws + a.bl.g1[l & 1]);
+    float* dz2 = (float*)(a.ws + a.bl.dz2[l & 1]);
     const int j = l + 1;                                  // hidden_rep index of this layer's output
     const float* z1 = (const float*)(a.acts + a.al.z1[l]);
     const float* z2 = (const float*)(a.acts + a.al.z2[l]);
@@ -620,6 +640,9 @@ static int run_backward(const BwdArgs& a) {
     GCCB_LAUNCH(kred, grid, 256, 0, a.stream, 1, node_off_v, B, z2, (const float*)dh, sa, P + a.lay.bna_w[l],
                 P + a.lay.bna_b[l], sb, P + a.lay.bnb_w[l], P + a.lay.bnb_b[l], d.bn_eps,
                 (const double*)rB, rA);
+#ifndef GCCB_EMU
+    if (l + 2 <= d.L - 2) cudaStreamWaitEvent(main_s, ev_side[l + 2], 0);   // g1/dz2[l&1] free again
+#endif
     {
       auto k = gin_bwd_gemm2_kernel<H>;
       size_t sm = ((size_t)GCCB_TILE_ROWS * (H + 1) + (size_t)GCCB_KC * (H + 4) + 2 * 16 * H + 16 * H) * 4;
@@ -643,25 +666,32 @@ static int run_backward(const BwdArgs& a) {
       GCCB_LAUNCH(k, grid, 256, sm, a.stream, node_off_v, B, z1, g1, s1, P + a.lay.bn1_w[l], P + a.lay.bn1_b[l],
                   d.bn_eps, (const double*)r1, P + a.lay.w1[l], inf, da);
     }
-    // weight gradients: dW2 = dz2^T x1 (x1 = relu(bn1(z1))), dW1 = dz1^T a
+#ifndef GCCB_EMU
+    cudaEventRecord(ev_main[l], main_s);
+    cudaStreamWaitEvent((cudaStream_t)side, ev_main[l], 0);
+#endif
+    // weight gradients (side stream): dW2 = dz2^T x1 (x1 = relu(bn1(z1))), dW1 = dz1^T a
     {
       dim3 gr(GCCB_WG_CHUNKS, ((H + 63) / 64) * ((H + 63) / 64));
-      GCCB_LAUNCH(gin_wgrad_kernel, gr, 256, 0, a.stream, node_off_v, B, H, H, (const float*)dz2, z1, s1,
+      GCCB_LAUNCH(gin_wgrad_kernel, gr, 256, 0, side, node_off_v, B, H, H, (const float*)dz2, z1, s1,
                   P + a.lay.bn1_w[l], P + a.lay.bn1_b[l], d.bn_eps, part);
-      GCCB_LAUNCH(gin_wgrad_reduce_kernel, (H * H + H + 255) / 256, 256, 0, a.stream, H, H, H,
+      GCCB_LAUNCH(gin_wgrad_reduce_kernel, (H * H + H + 255) / 256, 256, 0, side, H, H, H,
                   (const float*)part, G + a.lay.w2[l], G + a.lay.b2[l]);
       dim3 gr1(GCCB_WG_CHUNKS, ((H + 63) / 64) * ((KQ1 + 63) / 64));
-      GCCB_LAUNCH(gin_wgrad_kernel, gr1, 256, 0, a.stream, node_off_v, B, H, KQ1, (const float*)g1, a_l,
+      GCCB_LAUNCH(gin_wgrad_kernel, gr1, 256, 0, side, node_off_v, B, H, KQ1, (const float*)g1, a_l,
                   (const double*)nullptr, (const float*)nullptr, (const float*)nullptr, d.bn_eps, part);
-      GCCB_LAUNCH(gin_wgrad_reduce_kernel, (H * KQ1 + H + 255) / 256, 256, 0, a.stream, H, KQ1, inf,
+      GCCB_LAUNCH(gin_wgrad_reduce_kernel, (H * KQ1 + H + 255) / 256, 256, 0, side, H, KQ1, inf,
                   (const float*)part, G + a.lay.w1[l], G + a.lay.b1[l]);
     }
-    GCCB_LAUNCH(gin_bn_grads_kernel, (H + 127) / 128, 128, 0, a.stream, H, (const double*)rB,
+    GCCB_LAUNCH(gin_bn_grads_kernel, (H + 127) / 128, 128, 0, side, H, (const double*)rB,
                 G + a.lay.bnb_w[l], G + a.lay.bnb_b[l]);
-    GCCB_LAUNCH(gin_bn_grads_kernel, (H + 127) / 128, 128, 0, a.stream, H, (const double*)rA,
+    GCCB_LAUNCH(gin_bn_grads_kernel, (H + 127) / 128, 128, 0, side, H, (const double*)rA,
                 G + a.lay.bna_w[l], G + a.lay.bna_b[l]);
-    GCCB_LAUNCH(gin_bn_grads_kernel, (H + 127) / 128, 128, 0, a.stream, H, (const double*)r1,
+    GCCB_LAUNCH(gin_bn_grads_kernel, (H + 127) / 128, 128, 0, side, H, (const double*)r1,
                 G + a.lay.bn1_w[l], G + a.lay.bn1_b[l]);
+#ifndef GCCB_EMU
+    cudaEventRecord(ev_side[l], (cudaStream_t)side);
+#endif
   }
   // layer-0 input gradient -> degree embedding
   auto kdh0 = gin_bwd_dh_kernel<GCCB_DINP>;
@@ -673,6 +703,10 @@ static int run_backward(const BwdArgs& a) {
     gccb::ensure_dyn_smem(k, sm);
     GCCB_LAUNCH(k, 64, 256, sm, a.stream, d, node_off_v, B, sub_deg, (const float*)dh, G + a.lay.emb);
   }
+#ifndef GCCB_EMU
+  cudaEventRecord(ev_join, (cudaStream_t)side);
+  cudaStreamWaitEvent(main_s, ev_join, 0);
+#endif
   return check_launch("gccb_gin_backward");
 }
 

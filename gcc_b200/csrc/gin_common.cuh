@@ -23,6 +23,7 @@ struct ActsLayout {
   size_t x0;                                   // float [node_cap][64]
   size_t a[GCCB_MAX_L], z1[GCCB_MAX_L], z2[GCCB_MAX_L], h[GCCB_MAX_L];
   size_t stats;                                // double [L-1][3][2][H]  column sums / sums of squares
+  size_t pool_acc;                             // double [L][B][PW] sum-pooling accumulators (follow stats: one memset)
   size_t pooled;                               // float [L][B][PW]
   size_t score;                                // float [B][H]  (pre-normalisation)
   size_t feat;                                 // float [B][H]
@@ -44,6 +45,7 @@ inline ActsLayout make_acts_layout(const GinDims& d, int B, int node_cap) {
   }
   a.stats = take((size_t)(d.L - 1) * 3 * 2 * d.H * 8);
   a.PW = d.H > GCCB_DINP ? d.H : GCCB_DINP;
+  a.pool_acc = take((size_t)d.L * B * a.PW * 8);
   a.pooled = take((size_t)d.L * B * a.PW * 4);
   a.score = take((size_t)B * d.H * 4);
   a.feat = take((size_t)B * d.H * 4);
@@ -129,6 +131,71 @@ __device__ __forceinline__ void bn_prepare(const double* __restrict__ sums, int 
     sc_s[c] = g * invstd;
     sh_s[c] = beta[c] - (float)mean * g * invstd;
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// acc[j] += sum over edges e in [beg, end) of src[indices[e]][lane + 32 j]: one warp, lanes across
+// the feature dimension (one coalesced row read per neighbour), eight neighbour rows in flight.
+#ifndef GCCB_HUB_DEG
+#define GCCB_HUB_DEG 256      // rows with more neighbours are split across the warps of the CTA
+#endif
+template <int W>
+__device__ __forceinline__ void gather_range(const float* __restrict__ src, const int32_t* __restrict__ indices,
+                                             int beg, int end, int lane, float (&acc)[(W + 31) / 32]) {
+  constexpr int PER = (W + 31) / 32;
+  int e = beg;
+  for (; e + 7 < end; e += 8) {
+    int u[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] = indices[e + k];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int c = lane + 32 * j;
+      if (c < W) {
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = src[(size_t)u[k] * W + c];
+        acc[j] += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+      }
+    }
+  }
+  for (; e < end; ++e) {
+    const int u = indices[e];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int c = lane + 32 * j;
+      if (c < W) acc[j] += src[(size_t)u * W + c];
+    }
+  }
+}
+
+// Hub row: the 8 warps of a 256-thread CTA each gather a contiguous eighth of the neighbour list;
+// partial sums meet in `scratch` [8][W]; on return (after the internal barriers) every thread
+// c < W holds the full neighbour sum of column c in the return value.  All 256 threads must call.
+template <int W>
+__device__ __forceinline__ float gather_hub(const float* __restrict__ src, const int32_t* __restrict__ indices,
+                                            int beg, int end, float* scratch) {
+  constexpr int PER = (W + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int len = end - beg, per = (len + 7) / 8;
+  const int b = beg + warp * per, e = min(b + per, end);
+  float acc[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) acc[j] = 0.f;
+  gather_range<W>(src, indices, b, e > b ? e : b, lane, acc);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int c = lane + 32 * j;
+    if (c < W) scratch[warp * W + c] = acc[j];
+  }
+  __syncthreads();
+  float s = 0.f;
+  if ((int)threadIdx.x < W) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += scratch[w * W + threadIdx.x];
+  }
+  __syncthreads();
+  return s;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -55,7 +55,10 @@ gin_agg_gemm1_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_
   constexpr int LDA = KIN + 1;
   float* As = smem;                          // [64][KIN+1]
   float* Ws = As + GCCB_TILE_ROWS * LDA;     // [KC][H+4]
-  float* red = Ws + GCCB_KC * (H + 4);       // [2][16][H]
+  float* red = Ws + GCCB_KC * (H + 4);       // [2][16][H]; also the hub-row scratch [8][KIN]
+  __shared__ int hub_rows[GCCB_TILE_ROWS];
+  __shared__ int n_hub;
+  static_assert(8 * KIN <= 2 * 16 * H, "hub scratch must fit in the statistics scratch");
   const int N = node_off_v[B];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;
@@ -63,7 +66,10 @@ gin_agg_gemm1_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_
   for (int tile = blockIdx.x; tile * GCCB_TILE_ROWS < N; tile += gridDim.x) {
     const int row0 = tile * GCCB_TILE_ROWS;
     __syncthreads();                                   // As free (previous tile consumed)
-    // gather / segmented reduce: one warp per row, lanes across the feature dimension
+    // gather / segmented reduce: one warp per row, lanes across the feature dimension; hub rows
+    // (a seed's row in a large ego-net has n-1 neighbours) are deferred and split across the CTA
+    if (tid == 0) n_hub = 0;
+    __syncthreads();
     for (int rr = warp; rr < GCCB_TILE_ROWS; rr += 8) {
       const int r = row0 + rr;
       constexpr int PER = (KIN + 31) / 32;
@@ -72,32 +78,16 @@ gin_agg_gemm1_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_
       for (int j = 0; j < PER; ++j) acc[j] = 0.f;
       if (r < N) {
         const int beg = indptr[r], end = indptr[r + 1];
+        if (end - beg > GCCB_HUB_DEG) {
+          if (lane == 0) hub_rows[atomicAdd(&n_hub, 1)] = rr;
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
           int c = lane + 32 * j;
           if (c < KIN) acc[j] = (1.0f + eps_gin) * h[(size_t)r * KIN + c];
         }
-        int e = beg;
-        for (; e + 3 < end; e += 4) {                     // four neighbour rows in flight
-          const int u0 = indices[e], u1 = indices[e + 1], u2 = indices[e + 2], u3 = indices[e + 3];
-#pragma unroll
-          for (int j = 0; j < PER; ++j) {
-            int c = lane + 32 * j;
-            if (c < KIN) {
-              float x0 = h[(size_t)u0 * KIN + c], x1 = h[(size_t)u1 * KIN + c];
-              float x2 = h[(size_t)u2 * KIN + c], x3 = h[(size_t)u3 * KIN + c];
-              acc[j] += (x0 + x1) + (x2 + x3);
-            }
-          }
-        }
-        for (; e < end; ++e) {
-          const int u = indices[e];
-#pragma unroll
-          for (int j = 0; j < PER; ++j) {
-            int c = lane + 32 * j;
-            if (c < KIN) acc[j] += h[(size_t)u * KIN + c];
-          }
-        }
+        gather_range<KIN>(h, indices, beg, end, lane, acc);
       }
 #pragma unroll
       for (int j = 0; j < PER; ++j) {
@@ -106,6 +96,16 @@ gin_agg_gemm1_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_
           As[rr * LDA + c] = acc[j];
           if (r < N) a_out[(size_t)r * KIN + c] = acc[j];
         }
+      }
+    }
+    __syncthreads();
+    for (int hi = 0; hi < n_hub; ++hi) {
+      const int rr = hub_rows[hi], r = row0 + rr;
+      const float s = gather_hub<KIN>(h, indices, indptr[r], indptr[r + 1], red);
+      if (tid < KIN) {
+        const float v = (1.0f + eps_gin) * h[(size_t)r * KIN + tid] + s;
+        As[rr * LDA + tid] = v;
+        a_out[(size_t)r * KIN + tid] = v;
       }
     }
     __syncthreads();
@@ -234,65 +234,97 @@ gin_bn_tail_kernel(int mode, const int32_t* __restrict__ node_off_v, int B,
   }
 }
 
+// Sum pooling of every layer's node features (SumPooling, gin.py:213-232), parallel over 64-row
+// tiles so that a 3,000-node ego-net does not serialise on one CTA: each thread owns a column and a
+// run of consecutive rows, accumulates while the graph id stays the same and flushes with a float64
+// atomic (same policy as the BatchNorm statistics).  pool_acc is zeroed with the statistics.
+template <int H>
+__global__ void __launch_bounds__(256)
+gin_pool_kernel(int L, const int32_t* __restrict__ node_off_v, int B, const int32_t* __restrict__ graph_id,
+                const float* __restrict__ x0, const float* const* __restrict__ h_layers, int PW,
+                double* __restrict__ pool_acc) {
+  __shared__ int gid[GCCB_TILE_ROWS];
+  const int N = node_off_v[B];
+  const int tid = threadIdx.x;
+  for (int tile = blockIdx.x; tile * GCCB_TILE_ROWS < N; tile += gridDim.x) {
+    const int row0 = tile * GCCB_TILE_ROWS;
+    __syncthreads();
+    if (tid < GCCB_TILE_ROWS) gid[tid] = row0 + tid < N ? graph_id[row0 + tid] : -1;
+    __syncthreads();
+    for (int l = 0; l < L; ++l) {
+      const int W = l == 0 ? GCCB_DINP : H;
+      const float* src = l == 0 ? x0 : h_layers[l - 1];
+      const int RG = 256 / W > 0 ? 256 / W : 1;          // row groups; threads beyond RG*W idle
+      const int c = tid % W, rg = tid / W;
+      if (rg >= RG) continue;
+      const int per = GCCB_TILE_ROWS / RG;
+      const int rb = rg * per;
+      int g_run = gid[rb];
+      float acc = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < per; ++k) {
+        const int g = gid[rb + k];
+        if (g < 0) break;
+        const float v = src[(size_t)(row0 + rb + k) * W + c];
+        if (g != g_run) {
+          atomicAdd(&pool_acc[((size_t)l * B + g_run) * PW + c], (double)acc);
+          acc = 0.f;
+          g_run = g;
+        }
+        acc += v;
+      }
+      if (g_run >= 0) atomicAdd(&pool_acc[((size_t)l * B + g_run) * PW + c], (double)acc);
+    }
+  }
+}
+
 // K5: SumPooling per graph for every layer's representation, the prediction heads with
 // dropout, the layer sum and the final L2 normalisation (gin.py:222-232, graph_encoder.py:195-196).
 // grid = B (one CTA per graph), block = 256.
 template <int H>
 __global__ void __launch_bounds__(256)
 gin_pool_predict_kernel(GinDims d, const int32_t* __restrict__ node_off_v, int B,
-                        const float* __restrict__ x0, const float* const* __restrict__ h_layers,
+                        const double* __restrict__ pool_acc,
                         const float* __restrict__ params, const int64_t* __restrict__ wp_off,
                         const int64_t* __restrict__ bp_off, int PW, uint64_t drop_key,
                         uint64_t drop_step, int drop_layer_base, uint32_t keep_thresh,
                         float* __restrict__ pooled, float* __restrict__ score_out,
                         float* __restrict__ feat_out, float* __restrict__ pooled_user) {
   constexpr int MAXW = H > GCCB_DINP ? H : GCCB_DINP;
-  GCCB_DYN_SMEM(float, wt);                // [MAXW][H + 1] transposed head weight
-  __shared__ float part[4][MAXW];
   __shared__ float pl[MAXW];
   __shared__ float score[H];
   __shared__ float red_s[8];
   const int g = blockIdx.x, tid = threadIdx.x;
   if (node_off_v[B] < 0) return;
-  const int r0 = node_off_v[g], r1 = node_off_v[g + 1];
   for (int o = tid; o < H; o += 256) score[o] = 0.f;
   __syncthreads();
   for (int l = 0; l < d.L; ++l) {
     const int W = l == 0 ? GCCB_DINP : H;                 // stored width
     const int inf = l == 0 ? d.din : H;                   // in_features of the head
-    const float* src = l == 0 ? x0 : h_layers[l - 1];
-    // segment sum: thread (c, rg) with c < W, rg in 0..RG-1, four rows in flight per thread
-    const int RG = 256 / W >= 4 ? 4 : (256 / W > 0 ? 256 / W : 1);
-    const int c = tid % W, rg = tid / W;
-    if (rg < RG) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      int r = r0 + rg;
-      for (; r + 3 * RG < r1; r += 4 * RG) {
-        s0 += src[(size_t)r * W + c]; s1 += src[(size_t)(r + RG) * W + c];
-        s2 += src[(size_t)(r + 2 * RG) * W + c]; s3 += src[(size_t)(r + 3 * RG) * W + c];
-      }
-      for (; r < r1; r += RG) s0 += src[(size_t)r * W + c];
-      part[rg][c] = (s0 + s1) + (s2 + s3);
-    }
-    // stage the head's weight transposed: wt[k][o] = Wp[o][k]  (coalesced global reads)
     const float* Wp = params + wp_off[l];
     const float* bp = params + bp_off[l];
-    for (int idx = tid; idx < H * inf; idx += 256) {
-      const int o = idx / inf, k2 = idx - o * inf;
-      wt[k2 * (H + 1) + o] = Wp[idx];
-    }
     __syncthreads();
     for (int cc = tid; cc < W; cc += 256) {
-      float s = 0.f;
-      for (int j = 0; j < RG; ++j) s += part[j][cc];
+      const float s = (float)pool_acc[((size_t)l * B + g) * PW + cc];
       pl[cc] = s;
       pooled[((size_t)l * B + g) * PW + cc] = s;
       if (pooled_user && l > 0) pooled_user[((size_t)(l - 1) * B + g) * H + cc] = s;   // all_outputs[1:]
     }
     __syncthreads();
-    for (int o = tid; o < H; o += 256) {
-      float s = bp[o];
-      for (int k = 0; k < inf; ++k) s = fmaf(pl[k], wt[k * (H + 1) + o], s);
+    // head GEMV straight from L2 (16 KB per layer, read once per CTA): four lanes share an output,
+    // lane q takes k = q, q+4, ... (the four reads of a step are 16 contiguous bytes)
+    for (int o0 = 0; o0 < H; o0 += 64) {
+      const int o = o0 + (tid >> 2), kq = tid & 3;
+      float s = 0.f;
+      const float* wrow = Wp + (size_t)(o < H ? o : 0) * inf;
+      if (o < H) {
+#pragma unroll 8
+        for (int k = kq; k < inf; k += 4) s = fmaf(pl[k], wrow[k], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (kq != 0 || o >= H) continue;
+      s += bp[o];
       if (drop_layer_base >= 0) {                          // Dropout(p) in train mode, Philox mask
         const uint32_t e = (uint32_t)(g * H + o);
         u32x4 w = philox_at(drop_key, drop_step, e >> 2, 0, (uint32_t)(drop_layer_base + l),
@@ -361,7 +393,9 @@ static int run_forward(const FwdArgs& a) {
   const int tiles = (cap + GCCB_TILE_ROWS - 1) / GCCB_TILE_ROWS;
   const int grid = tiles < 592 ? tiles : 592;            // 4 waves of 148 SMs at most
   const int use_running = a.bn_train ? 0 : 1, upd = a.bn_train ? 1 : 0;
-  cudaMemsetAsync(stats, 0, (size_t)(d.L - 1) * 3 * 2 * H * sizeof(double), (cudaStream_t)a.stream);
+  // BatchNorm statistics and the pooling accumulators are adjacent: one memset
+  cudaMemsetAsync(stats, 0, a.al.pool_acc + (size_t)d.L * B * a.al.PW * sizeof(double) - a.al.stats,
+                  (cudaStream_t)a.stream);
   GCCB_LAUNCH(gin_build_x0_kernel, grid, 256, 0, a.stream, d, node_off_v, B, pos_v, sub_deg, graph_id,
               a.params + a.lay.emb, x0);
   const float* hin = x0;
@@ -407,10 +441,12 @@ static int run_forward(const FwdArgs& a) {
     hin = hout;
   }
   const uint32_t keep = (uint32_t)fmin((1.0 - (double)d.drop_p) * 4294967296.0, 4294967295.0);
+  double* pool_acc = (double*)(a.acts + a.al.pool_acc);
+  auto kpl = gin_pool_kernel<H>;
+  GCCB_LAUNCH(kpl, grid, 256, 0, a.stream, d.L, node_off_v, B, graph_id, (const float*)x0, a.d_hptrs, a.al.PW,
+              pool_acc);
   auto kp = gin_pool_predict_kernel<H>;
-  const size_t sm_pool = (size_t)(H > GCCB_DINP ? H : GCCB_DINP) * (H + 1) * sizeof(float);
-  gccb::ensure_dyn_smem(kp, sm_pool);
-  GCCB_LAUNCH(kp, B, 256, sm_pool, a.stream, d, node_off_v, B, x0, a.d_hptrs, a.params, a.d_offs, a.d_offs + 8,
+  GCCB_LAUNCH(kp, B, 256, 0, a.stream, d, node_off_v, B, (const double*)pool_acc, a.params, a.d_offs, a.d_offs + 8,
               a.al.PW, a.drop_key, a.drop_step, a.drop_base, keep, (float*)(a.acts + a.al.pooled),
               (float*)(a.acts + a.al.score), a.feat, a.pooled_user);
   return check_launch("gccb_gin_forward");

@@ -172,6 +172,101 @@ infonce_partial_kernel(const float* __restrict__ q, const float* __restrict__ me
 }
 
 // merge partials with the positive logit; loss_i, dq_i; stats[0] += loss_i/B, stats[1] += l_pos/B
+// Tiled variant for d in {32, 64, 128, 256}: 32 query rows x CK = 32*KPT keys per CTA (4x fewer
+// passes over the queue than the 8-row kernel), register tiles for both products.  Warp w owns
+// rows 4w..4w+3; lane owns keys lane + 32t (logits) and columns lane + 32u (accumulator).
+// dyn smem: qs[32][d] | ms[CK][d+1] | ps[32][CK].  Same partial-record layout as above.
+#define GCCB_NCE_RB2 32
+template <int KPT, int DU>
+__global__ void __launch_bounds__(256)
+infonce_partial_tiled_kernel(const float* __restrict__ q, const float* __restrict__ mem, int B, int K,
+                             float invT, float* __restrict__ part) {
+  constexpr int CK = 32 * KPT, d = 32 * DU, RB = GCCB_NCE_RB2;
+  GCCB_DYN_SMEM(float, smem);
+  float* qs = smem;
+  float* ms = qs + RB * d;
+  float* ps = ms + (size_t)CK * (d + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.y * RB, j0 = blockIdx.x * CK;
+  const int nk = min(CK, K - j0);
+  for (int idx = tid; idx < RB * d; idx += 256) {
+    const int i = i0 + idx / d;
+    qs[idx] = i < B ? q[(size_t)i * d + idx % d] : 0.f;
+  }
+  for (int idx = tid; idx < CK * d; idx += 256) {
+    const int j = idx / d, c = idx - j * d;
+    ms[j * (d + 1) + c] = j < nk ? mem[(size_t)(j0 + j) * d + c] : 0.f;
+  }
+  __syncthreads();
+  float lg[4][KPT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int t = 0; t < KPT; ++t) lg[i][t] = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < d; ++c) {
+    float qv[4], kv[KPT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qv[i] = qs[(warp * 4 + i) * d + c];
+#pragma unroll
+    for (int t = 0; t < KPT; ++t) kv[t] = ms[(lane + 32 * t) * (d + 1) + c];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int t = 0; t < KPT; ++t) lg[i][t] = fmaf(qv[i], kv[t], lg[i][t]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp * 4 + i;
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int t = 0; t < KPT; ++t) {
+      lg[i][t] = lane + 32 * t < nk ? lg[i][t] * invT : -3.0e38f;
+      mx = fmaxf(mx, lg[i][t]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < KPT; ++t) {
+      const float p = lane + 32 * t < nk ? expf(lg[i][t] - mx) : 0.f;
+      ps[r * CK + lane + 32 * t] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0 && i0 + r < B) {
+      float* rec = part + ((size_t)blockIdx.x * B + i0 + r) * (d + 2);
+      rec[0] = mx;
+      rec[1] = sum;
+    }
+  }
+  __syncwarp();                                        // ps rows of this warp are read by this warp only
+  float ac[4][DU];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int u = 0; u < DU; ++u) ac[i][u] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < nk; ++j) {
+    float pv[4], mv[DU];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pv[i] = ps[(warp * 4 + i) * CK + j];
+#pragma unroll
+    for (int u = 0; u < DU; ++u) mv[u] = ms[j * (d + 1) + lane + 32 * u];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int u = 0; u < DU; ++u) ac[i][u] = fmaf(pv[i], mv[u], ac[i][u]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp * 4 + i;
+    if (i0 + r >= B) continue;
+    float* rec = part + ((size_t)blockIdx.x * B + i0 + r) * (d + 2) + 2;
+#pragma unroll
+    for (int u = 0; u < DU; ++u) rec[lane + 32 * u] = ac[i][u];
+  }
+}
+
 // grid = B, block 128 (threads over d)
 __global__ void __launch_bounds__(128)
 infonce_merge_kernel(const float* __restrict__ q, const float* __restrict__ k,
@@ -287,7 +382,12 @@ e2e_grads_kernel(const float* __restrict__ q, const float* __restrict__ k, const
   }
 }
 
-static int infonce_ck(int d) { int ck = 16384 / d; return ck < 32 ? 32 : (ck > 256 ? 256 : ck); }
+static bool infonce_tiled(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
+static int infonce_ck(int d) {
+  if (infonce_tiled(d)) return d <= 128 ? 128 : 64;
+  int ck = 16384 / d;
+  return ck < 32 ? 32 : (ck > 256 ? 256 : ck);
+}
 
 }  // namespace gccb
 
@@ -347,12 +447,28 @@ extern "C" int gccb_infonce_fused(const float* q, const float* k, const float* m
   }
   const int ck = infonce_ck(d);
   const int nch = (K + ck - 1) / ck;
-  const size_t smem = ((size_t)GCCB_NCE_RB * d + (size_t)ck * (d + 1) + (size_t)GCCB_NCE_RB * ck) * 4;
-  auto kp = infonce_partial_kernel;
-  gccb::ensure_dyn_smem(kp, smem);
   cudaMemsetAsync(stats, 0, 2 * sizeof(float), (cudaStream_t)stream);
-  dim3 grid(nch, (B + GCCB_NCE_RB - 1) / GCCB_NCE_RB);
-  GCCB_LAUNCH(kp, grid, 256, smem, stream, q, memory, B, d, K, ck, 1.0f / T, (float*)workspace);
+  if (infonce_tiled(d)) {
+    const size_t smem = ((size_t)GCCB_NCE_RB2 * d + (size_t)ck * (d + 1) + (size_t)GCCB_NCE_RB2 * ck) * 4;
+    dim3 grid(nch, (B + GCCB_NCE_RB2 - 1) / GCCB_NCE_RB2);
+#define GCCB_NCE_TILED(KPT, DU)                                                              \
+  do {                                                                                       \
+    auto kt = infonce_partial_tiled_kernel<KPT, DU>;                                         \
+    gccb::ensure_dyn_smem(kt, smem);                                                         \
+    GCCB_LAUNCH(kt, grid, 256, smem, stream, q, memory, B, K, 1.0f / T, (float*)workspace); \
+  } while (0)
+    if (d == 32) GCCB_NCE_TILED(4, 1);
+    else if (d == 64) GCCB_NCE_TILED(4, 2);
+    else if (d == 128) GCCB_NCE_TILED(4, 4);
+    else GCCB_NCE_TILED(2, 8);
+#undef GCCB_NCE_TILED
+  } else {
+    const size_t smem = ((size_t)GCCB_NCE_RB * d + (size_t)ck * (d + 1) + (size_t)GCCB_NCE_RB * ck) * 4;
+    auto kp = infonce_partial_kernel;
+    gccb::ensure_dyn_smem(kp, smem);
+    dim3 grid(nch, (B + GCCB_NCE_RB - 1) / GCCB_NCE_RB);
+    GCCB_LAUNCH(kp, grid, 256, smem, stream, q, memory, B, d, K, ck, 1.0f / T, (float*)workspace);
+  }
   GCCB_LAUNCH(infonce_merge_kernel, B, 128, 0, stream, q, k, (const float*)workspace, B, d, nch, 1.0f / T,
               stats, dq);
   return check_launch("gccb_infonce_fused");

@@ -369,8 +369,7 @@ __device__ __forceinline__ void write_features(int n, int k, int pos_dim, int no
 // (one-sided on the SPD matrix L + 2I keeps eigenVECTOR accuracy for close eigenvalues -- paths,
 // rings -- where an fp32 two-sided rotation sequence loses it as eps * rotations / gap; fp64 would
 // too be accurate but runs at a small fraction of the fp32 rate on this part)
-__global__ void __launch_bounds__(256)
-posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts,
+__device__ __forceinline__ void posenc_jacobi_item(const int item, const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts,
                      int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
                      const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
                      const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
@@ -381,8 +380,7 @@ posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __rest
   __shared__ float dinv[GCCB_EIG_SMALL];
   __shared__ int sel[32];
   __shared__ float sgn[32];
-  if ((int)blockIdx.x >= counts[0]) return;
-  const int slot = worklist[blockIdx.x];
+  const int slot = worklist[item];
   const int view = slot / B, g = slot - view * B;
   const int noff = node_off[view * (B + 1) + g];
   const int n = node_off[view * (B + 1) + g + 1] - noff;
@@ -458,6 +456,20 @@ posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __rest
   const int* selc = sel;
   write_features(n, k, pos_dim, normalize, sgn, out,
                  [&](int c, int r) { const int j = selc[c]; return Gc[(size_t)j * ld + r] / mu[j]; });
+}
+
+__global__ void __launch_bounds__(256)
+posenc_jacobi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts,
+                     int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
+                     const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
+                     const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
+                     float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags,
+                     int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res) {
+  // persistent over the work list: the grid is sized for the typical count, not for 2B
+  for (int item = blockIdx.x; item < counts[0]; item += gridDim.x) {
+    posenc_jacobi_item(item, worklist, counts, B, node_cap, edge_cap, node_off, b_indptr, b_indices, sub_deg, pos_dim, normalize, pos, eigvals, flags, dbg_iters, dbg_res);
+    __syncthreads();
+  }
 }
 
 // ---- solver (2): Chebyshev-filtered subspace iteration, any n > 64 -------------------------------
@@ -553,8 +565,7 @@ __device__ __forceinline__ void column_sums(int n, float* part /*[32][48]*/, flo
 // random accesses never leave the SM (ego-nets of 480 < n <= 1000 nodes).
 // cls selects the work list; blockDim.x = 256 or 1024.
 template <int MODE, int NT>
-__global__ void __launch_bounds__(NT)
-posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts, int cls,
+__device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts, int cls,
                     int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
                     const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
                     const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
@@ -578,8 +589,7 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
   __shared__ float sgn[32];
   float* Ws = WT;
   float (*tile)[32][CB + 1] = reinterpret_cast<float (*)[32][CB + 1]>(WT);
-  if ((int)blockIdx.x >= counts[cls]) return;
-  const int slot = worklist[(size_t)cls * 2 * B + blockIdx.x];
+  const int slot = worklist[(size_t)cls * 2 * B + item];
   const int view = slot / B, g = slot - view * B;
   const int noff = node_off[view * (B + 1) + g];
   const int n = node_off[view * (B + 1) + g + 1] - noff;
@@ -826,6 +836,22 @@ posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restr
   const float* Xf = X;
   write_features(n, k, pos_dim, normalize, sgn, out,
                  [&](int c, int r) { return Xf[(size_t)r * ld + (k - 1 - c)]; });
+}
+
+template <int MODE, int NT>
+__global__ void __launch_bounds__(NT)
+posenc_chfsi_kernel(const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts, int cls,
+                    int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
+                    const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
+                    const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
+                    float* __restrict__ blocks /* [2][2*node_cap*48] */, float* __restrict__ dinv_g /* [2*node_cap] */,
+                    float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags,
+                    int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res, long long* __restrict__ dbg_phase) {
+  // persistent over the work list: the grid is sized for the typical count, not for 2B
+  for (int item = blockIdx.x; item < counts[cls]; item += gridDim.x) {
+    posenc_chfsi_item<MODE, NT>(item, worklist, counts, cls, B, node_cap, edge_cap, node_off, b_indptr, b_indices, sub_deg, pos_dim, normalize, blocks, dinv_g, pos, eigvals, flags, dbg_iters, dbg_res, dbg_phase);
+    __syncthreads();
+  }
 }
 
 
@@ -1356,29 +1382,10 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   // The size classes are independent: fork them over side streams (event fork/join, legal inside
   // CUDA-graph capture) so that the few long-running large ego-nets overlap the many small ones.
 #ifndef GCCB_EMU
-  // one set of side streams per caller stream (several batches may be in flight on different
-  // caller streams; sharing one set would serialise their size classes)
-  struct SideSet { cudaStream_t key; bool used; cudaStream_t side[5]; cudaEvent_t ev_fork, ev_join[5]; };
-  static SideSet sets[8];
-  static int nsets = 0;
-  SideSet* ss = nullptr;
-  for (int i = 0; i < nsets; ++i)
-    if (sets[i].key == (cudaStream_t)stream) ss = &sets[i];
-  if (!ss) {
-    ss = &sets[nsets < 8 ? nsets++ : 7];                   // beyond 8 caller streams: share the last set
-    if (!ss->used) {
-      for (int i = 0; i < 5; ++i) {
-        cudaStreamCreateWithFlags(&ss->side[i], cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&ss->ev_join[i], cudaEventDisableTiming);
-      }
-      cudaEventCreateWithFlags(&ss->ev_fork, cudaEventDisableTiming);
-      ss->used = true;
-    }
-    ss->key = (cudaStream_t)stream;
-  }
-  cudaStream_t* side = ss->side;
-  cudaEvent_t ev_fork = ss->ev_fork;
-  cudaEvent_t* ev_join = ss->ev_join;
+  StreamKit* kit = stream_kit((cudaStream_t)stream, 0);   // per caller stream: batches in flight do not serialise
+  cudaStream_t* side = kit->side;
+  cudaEvent_t ev_fork = kit->ev[5];
+  cudaEvent_t* ev_join = kit->ev;
   cudaStream_t main_s = (cudaStream_t)stream;
   cudaEventRecord(ev_fork, main_s);
   for (int i = 0; i < 5; ++i) cudaStreamWaitEvent(side[i], ev_fork, 0);
@@ -1388,9 +1395,13 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
 #endif
 #define GCCB_PE_ARGS(cls) worklist, counts, cls, B, batch->node_cap, batch->edge_cap, batch->node_off, batch->indptr, \
     batch->indices, batch->sub_deg, pos_dim, normalize, blocks, dinv, pos, eigvals, batch->flags, dbg_iters, dbg_res, dbg_phase
-  GCCB_LAUNCH(kgiant, 2 * B, 1024, 0, s_giant, GCCB_PE_ARGS(5));
+  // grids are sized for the typical population of each class (persistent loops take the rest): an
+  // idle CTA of these kernels still has to win 1024 thread slots / up to 188 KB of shared memory
+  // just to exit, which costs concurrent kernels dearly
+  auto capped = [&](int limit) { return 2 * B < limit ? 2 * B : limit; };
+  GCCB_LAUNCH(kgiant, capped(8), 1024, 0, s_giant, GCCB_PE_ARGS(5));
   {
-    const int items = 2 * B < 32 ? 2 * B : 32;           // persistent over the work list
+    const int items = capped(8);                         // clusters; persistent over the work list
 #ifndef GCCB_EMU
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CLUSTER * items); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = s_d;
@@ -1410,10 +1421,10 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
                 eigvals, batch->flags, dbg_iters, dbg_res, dbg_phase);
 #endif
   }
-  GCCB_LAUNCH(kbig, 2 * B, 1024, s_c, s_big, GCCB_PE_ARGS(3));
-  GCCB_LAUNCH(kmid, 2 * B, 256, s_b, s_mid2, GCCB_PE_ARGS(2));
-  GCCB_LAUNCH(kmid, 2 * B, 256, s_a, s_mid1, GCCB_PE_ARGS(1));
-  GCCB_LAUNCH(ksmall, 2 * B, 256, 0, s_small, worklist, counts, B, batch->node_cap, batch->edge_cap,
+  GCCB_LAUNCH(kbig, capped(148), 1024, s_c, s_big, GCCB_PE_ARGS(3));
+  GCCB_LAUNCH(kmid, capped(148 * 2), 256, s_b, s_mid2, GCCB_PE_ARGS(2));
+  GCCB_LAUNCH(kmid, capped(148 * 3), 256, s_a, s_mid1, GCCB_PE_ARGS(1));
+  GCCB_LAUNCH(ksmall, capped(148), 256, 0, s_small, worklist, counts, B, batch->node_cap, batch->edge_cap,
               batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, pos, eigvals,
               batch->flags, dbg_iters, dbg_res);
 #ifndef GCCB_EMU

@@ -26,7 +26,7 @@ from .parallel import StepExchange, first_sample_id
 class PretrainEngine:
     def __init__(self, dataset, model, model_ema, contrast, moco=True, learning_rate=0.005,
                  betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, clip_norm=1.0, alpha=0.999,
-                 nce_t=0.07, rank=0, world_size=1, process_group=None, prefetch=2):
+                 nce_t=0.07, rank=0, world_size=1, process_group=None, prefetch=2, train_sms=None):
         _lib.require_device()
         self.lib = _lib.get()
         self.ds, self.model, self.model_ema, self.contrast = dataset, model, model_ema, contrast
@@ -52,6 +52,17 @@ class PretrainEngine:
         self.dq = torch.zeros(B, H, **f32)
         self.dk = torch.zeros(B, H, **f32)
         self.pooled = torch.zeros(max(L - 1, 1), B, H, **f32)
+        self.pooled_k = torch.zeros(max(L - 1, 1), B, H, **f32)
+        # Optional SM partition (CUDA green contexts, gccb_partition_*): the training kernels get
+        # `train_sms` SMs of their own, the sampler / eigensolver run-ahead the rest.
+        self.partition = None
+        if train_sms and prefetch:
+            part = C.c_void_p()
+            _lib.check(self.lib.gccb_partition_create(dev.index or 0, int(train_sms), C.byref(part)),
+                       "gccb_partition_create")
+            self.partition = part
+            self.partition_sms = (self.lib.gccb_partition_sm_count(part, 0), self.lib.gccb_partition_sm_count(part, 1))
+        self.aux_stream = self._new_stream(0, -1)      # key encoder, concurrent with the query encoder
         cap = dataset.node_cap
         acts_bytes = self.lib.gccb_gin_acts_bytes(C.byref(model.cfg), B, cap)
         self.acts_q = torch.empty(acts_bytes, dtype=torch.uint8, device=dev)
@@ -87,16 +98,25 @@ class PretrainEngine:
             self.depth = S + 1
             self.bufs = [ds.buffers] + [BatchBuffers(B, ds.node_cap, ds.edge_cap, ds.buffers.pos_dim,
                                                      ds.graph.max_budget, dev) for _ in range(S)]
-            self.data_streams = [torch.cuda.Stream(device=dev, priority=0) for _ in range(S)]
+            self.data_streams = [self._new_stream(1, 0) for _ in range(S)]
             self.ready = [torch.cuda.Event() for _ in range(self.depth)]
             self.consumed = [torch.cuda.Event() for _ in range(self.depth)]
             self.prepared = 0                          # batches issued to the data streams so far
             # the training kernels are short and dependent: a high-priority stream lets their CTAs
             # go ahead of the queued sampler / eigensolver CTAs whenever an SM slot frees up
-            self.train_stream = torch.cuda.Stream(device=dev, priority=-1)
+            self.train_stream = self._new_stream(0, -1)
         self.cur_buf = dataset.buffers
 
     # -------------------------------------------------------------------------------------------
+    def _new_stream(self, group, priority):
+        """A stream of SM group `group` (0 training, 1 data) when partitioned, else a torch stream."""
+        if self.partition is None:
+            return torch.cuda.Stream(device=self.dev, priority=priority)
+        raw = C.c_void_p()
+        _lib.check(self.lib.gccb_partition_stream(self.partition, group, priority, C.byref(raw)),
+                   "gccb_partition_stream")
+        return torch.cuda.ExternalStream(raw.value, device=self.dev)
+
     def _hyper(self, lr):
         self.adam_t += 1
         b1, b2 = self.betas
@@ -176,12 +196,19 @@ class PretrainEngine:
             self.count_acc += buf.counters.double().sum(0)
         gq, gk = BatchedSubgraphs(buf, 0), BatchedSubgraphs(buf, 1)
         step = self.global_step
+        if self.moco:
+            # the key encoder (model_ema, its own weights and running statistics) is independent of
+            # the query encoder until the head: run it on a second stream
+            cur = torch.cuda.current_stream(self.dev)
+            self.aux_stream.wait_stream(cur)
+            with torch.cuda.stream(self.aux_stream):
+                ema._run_forward(gk, False, drop_step=0, drop_base=-1, acts=self.acts_k, feat=self.feat_k,
+                                 pooled=self.pooled_k, bn_train=True)
         _, _, saved_q = model._run_forward(gq, True, drop_step=step, drop_base=0, acts=self.acts_q,
                                            feat=self.feat_q, pooled=self.pooled, bn_train=True)
         self.grads.zero_()
         if self.moco:
-            ema._run_forward(gk, False, drop_step=0, drop_base=-1, acts=self.acts_k, feat=self.feat_k,
-                             pooled=self.pooled, bn_train=True)
+            cur.wait_stream(self.aux_stream)
             _lib.check(lib.gccb_infonce_fused(_lib.dptr(self.feat_q), _lib.dptr(self.feat_k),
                                               _lib.dptr(self.contrast.memory), B, H, self.K, self.T,
                                               _lib.dptr(self.stats), _lib.dptr(self.dq),

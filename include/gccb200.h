@@ -213,6 +213,19 @@ int gccb_clip_adam_ema(float* p, float* g, float* m, float* v, float* p_ema, int
 int gccb_sum_ranks(const float* gathered, int32_t world, int64_t stride, int64_t n, float* out,
                    gccb_stream_t stream);
 
+/* ---- SM partitioning (new; no reference counterpart) ---------------------------------------------
+ * Split the device's SMs into two CUDA green contexts: group 0 gets `first_sms` SMs (rounded up to
+ * the hardware granularity), group 1 the rest.  Streams created from a group launch only on its
+ * SMs; library-internal side streams (gccb_posenc size classes, gccb_gin_backward weight
+ * gradients) are created inside the caller stream's group.  PretrainEngine puts the training
+ * kernels on group 0 and the sampler / eigensolver run-ahead on group 1 so that the short training
+ * kernels never queue behind long-lived eigensolver CTAs.  Setup-time calls (they allocate driver
+ * objects that live until process exit); needs a CUDA 12.4+ driver. */
+typedef struct gccb_partition gccb_partition_t;
+int gccb_partition_create(int32_t device, int32_t first_sms, gccb_partition_t** out);
+int32_t gccb_partition_sm_count(const gccb_partition_t* p, int32_t which);
+int gccb_partition_stream(gccb_partition_t* p, int32_t which, int32_t priority, gccb_stream_t* out);
+
 #ifdef __cplusplus
 }
 #endif

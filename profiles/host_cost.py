@@ -31,10 +31,17 @@ ema.load_state_dict(model.state_dict())
 model, ema = model.to(dev), ema.to(dev)
 with contextlib.redirect_stdout(sys.stderr):
     contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
-eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=int(sys.argv[1]) if len(sys.argv) > 1 else 2)
+eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=int(sys.argv[1]) if len(sys.argv) > 1 else 2,
+                     train_sms=int(sys.argv[2]) if len(sys.argv) > 2 else None)
 for _ in range(5):
     eng.step(lr=0.005)
 torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(6):
+    eng.step(lr=0.005)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print("host enqueue, empty launch queue: %.3f ms/step" % (1e3 * (t1 - t0) / 6))
 N = 40
 t0 = time.perf_counter()
 for _ in range(N):

@@ -28,7 +28,7 @@ def build(force=False):
         obj = os.path.join(OUT, os.path.basename(src) + ".o")
         if force or not os.path.exists(obj) or any(
                 os.path.getmtime(obj) < os.path.getmtime(d) for d in [src] + hdrs):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-DGCCB_EMU", "-I", HERE,
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-DGCCB_EMU", "-DGCCB_HUB_DEG=3", "-I", HERE,
                                    "-x", "c++", "-c", src, "-o", obj])
             relink = True
         objs.append(obj)
