@@ -35,15 +35,15 @@ CONFIGS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--train-sms", type=int, default=0,
                     help="SMs reserved for the training kernels (green-context partition); 0 = shared")
-    ap.add_argument("--prefetch", type=int, default=2, choices=[1, 2, 3, 4],
+    ap.add_argument("--prefetch", type=int, default=3, choices=[1, 2, 3, 4],
                     help="batches the sampler/eigensolver streams run ahead of the training stream")
     return ap.parse_args()
 
@@ -353,7 +353,7 @@ def run_ours(args, cfg):
                 "frac": achieved / peak_gbs, "traffic": None,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_step": alg_bytes, "ms_per_launch_group": samp_ms,
-                "note": "latency-bound at 512 ego-nets/step (12 MB of traffic); see DESIGN.md"}
+                "note": "latency-bound at 512 ego-nets/step (tens of MB per launch group); see DESIGN.md"}
     try:
         roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[
             "sampler_group_dram_bytes_per_step"]

@@ -22,6 +22,10 @@ def get():
     """The bound library handle; builds nothing, falls back to nothing."""
     global _lib
     if _lib is None:
+        path = os.environ.get("GCCB200_LIB", LIB_PATH)     # developer knob: A/B a differently-tuned build
+        if path != LIB_PATH:
+            _lib = _capi.bind(ctypes.CDLL(path))
+            return _lib
         if not os.path.exists(LIB_PATH):
             raise GccbError(
                 "libgccb200.so not found at %s -- build it with `python -m gcc_b200.csrc.build` "

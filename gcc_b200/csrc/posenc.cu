@@ -41,8 +41,14 @@ namespace gccb {
 #define GCCB_CF_DEG 8              // degree of the later iterations (gain T_8(3) ~ 7e5 < 1/eps_fp32)
 #define GCCB_CF_NSM_A 96            // shared-memory block classes: n <= 96 (3 CTAs/SM) and
 #define GCCB_CF_NSM 160            //   n <= 160 (2 CTAs/SM),
-#define GCCB_CF_NSM_C 480          //   n <= 480 (1 CTA of 1024 threads per SM);
-#define GCCB_CF_NSM_D 3840         //   n <= 3840: cluster of 8 CTAs (DSMEM); larger: L2 workspace
+#define GCCB_CF_NSM_C 384          //   n <= 384 (one GCCB_BIG_NT-thread CTA; 150 KB + 30 KB static leave room
+                                   //   for a 46 KB training CTA on the same SM);
+#define GCCB_CF_NSM_D1 1536        //   n <= 1536: cluster of 8 CTAs (DSMEM), 192-row slabs (75 KB per CTA);
+#define GCCB_CF_NSM_D 3584         //   n <= 3584: cluster of 8 CTAs, 448-row slabs; larger: L2 workspace
+#define GCCB_EIG_NCLASS 7
+#ifndef GCCB_BIG_NT
+#define GCCB_BIG_NT 512            // threads of the large-ego-net CTAs: 512 x 64 registers leave half of
+#endif                             // the SM's register file to concurrent kernels (these CTAs live for ms)
 #define GCCB_CF_MAXIT 8
 #define GCCB_CF_TOL 4.0e-5f        // max residual ||L x - theta x|| over the wanted pairs
 #define GCCB_CF_STAG 2.0e-3f       // accepted when the residual stops halving below this: ego-nets whose
@@ -57,10 +63,11 @@ namespace gccb {
 #endif
 #define GCCB_TICK(k) do { if (threadIdx.x == 0) { long long t_ = GCCB_CLK(); ph[k] += t_ - t_last; t_last = t_; } } while (0)
 
-// class 0: n <= 64 (dense Jacobi); 1, 2, 3: ChFSI with shared-memory blocks; 4: ChFSI with L2 blocks
+// class 0: n <= 64 (dense Jacobi); 1, 2, 3: ChFSI with shared-memory blocks; 4, 5: ChFSI on a cluster;
+// 6: ChFSI with L2 blocks
 __device__ __forceinline__ int eig_class(int n) {
   return n <= GCCB_EIG_SMALL ? 0 : n <= GCCB_CF_NSM_A ? 1 : n <= GCCB_CF_NSM ? 2 : n <= GCCB_CF_NSM_C ? 3 :
-         n <= GCCB_CF_NSM_D ? 4 : 5;
+         n <= GCCB_CF_NSM_D1 ? 4 : n <= GCCB_CF_NSM_D ? 5 : 6;
 }
 
 // Work lists: worklist[c][i] = slot.  One CTA, deterministic order.  grid = 1, block = 256.
@@ -69,7 +76,7 @@ posenc_classify_kernel(const int64_t* __restrict__ counters, const int32_t* __re
                        int B, int32_t* __restrict__ worklist, int32_t* __restrict__ counts) {
   __shared__ int scan_scratch[33];
   const int tid = threadIdx.x;
-  int base[6] = {0, 0, 0, 0, 0, 0};
+  int base[GCCB_EIG_NCLASS] = {0};
   for (int s0 = 0; s0 < 2 * B; s0 += 256) {
     int slot = s0 + tid;
     int cls = -1;
@@ -78,14 +85,14 @@ posenc_classify_kernel(const int64_t* __restrict__ counters, const int32_t* __re
       if (node_off[view * (B + 1) + B] >= 0) cls = eig_class((int)counters[(size_t)slot * 4]);
     }
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
+    for (int c = 0; c < GCCB_EIG_NCLASS; ++c) {
       int tot;
       int ex = block_scan_excl(cls == c ? 1 : 0, scan_scratch, &tot);
       if (cls == c) worklist[(size_t)c * 2 * B + base[c] + ex] = slot;
       base[c] += tot;
     }
   }
-  if (tid < 6) counts[tid] = base[tid];
+  if (tid < GCCB_EIG_NCLASS) counts[tid] = base[tid];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1332,8 +1339,10 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
 
 using namespace gccb;
 
-// workspace: worklist[6][2B] | counts[6] | iters[2B] (ints) | pad | res[2B] | dinv[2*node_cap] | blocks[2][2*node_cap*49] (floats)
-static size_t posenc_ws_ints(int B) { return (((size_t)6 * 2 * B + 6 + 2 * B) + 63) & ~(size_t)63; }
+// workspace: worklist[7][2B] | counts[7] | iters[2B] (ints) | pad | res[2B] | dinv[2*node_cap] | blocks[2][2*node_cap*49] (floats)
+static size_t posenc_ws_ints(int B) {
+  return (((size_t)GCCB_EIG_NCLASS * 2 * B + GCCB_EIG_NCLASS + 2 * B) + 63) & ~(size_t)63;
+}
 
 extern "C" size_t gccb_posenc_workspace(int32_t batch, int32_t node_cap) {
   return posenc_ws_ints(batch) * sizeof(int32_t) +
@@ -1354,8 +1363,8 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
     return GCCB_ERR_CAPACITY;
   }
   int32_t* worklist = (int32_t*)workspace;
-  int32_t* counts = worklist + (size_t)6 * 2 * B;
-  int32_t* dbg_iters = counts + 6;                       // per slot: ChFSI outer iterations (Jacobi: -sweeps)
+  int32_t* counts = worklist + (size_t)GCCB_EIG_NCLASS * 2 * B;
+  int32_t* dbg_iters = counts + GCCB_EIG_NCLASS;                       // per slot: ChFSI outer iterations (Jacobi: -sweeps)
   float* dbg_res = (float*)((int32_t*)workspace + posenc_ws_ints(B));      // per slot: final residual
   float* dinv = dbg_res + (size_t)2 * B;
   float* blocks = dinv + (size_t)2 * batch->node_cap;
@@ -1368,14 +1377,15 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
 #else
   constexpr int CLUSTER = 1;                             // the emulator runs the same kernel with one CTA
 #endif
-  auto khuge = posenc_chfsi_cluster_kernel<1024, CLUSTER>;
-  auto kbig = posenc_chfsi_kernel<1, 1024>;
+  auto khuge = posenc_chfsi_cluster_kernel<GCCB_BIG_NT, CLUSTER>;
+  auto kbig = posenc_chfsi_kernel<1, GCCB_BIG_NT>;
   auto kmid = posenc_chfsi_kernel<1, 256>;
   auto ksmall = posenc_jacobi_kernel;
   const size_t s_a = (size_t)2 * GCCB_CF_NSM_A * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_b = (size_t)2 * GCCB_CF_NSM * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_c = (size_t)2 * GCCB_CF_NSM_C * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_d = (size_t)2 * ((GCCB_CF_NSM_D + CLUSTER - 1) / CLUSTER) * (GCCB_CF_B + 1) * sizeof(float);
+  const size_t s_d1 = (size_t)2 * ((GCCB_CF_NSM_D1 + CLUSTER - 1) / CLUSTER) * (GCCB_CF_B + 1) * sizeof(float);
   gccb::ensure_dyn_smem(kmid, s_b);
   gccb::ensure_dyn_smem(kbig, s_c);
   gccb::ensure_dyn_smem(khuge, s_d);
@@ -1399,29 +1409,34 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   // idle CTA of these kernels still has to win 1024 thread slots / up to 188 KB of shared memory
   // just to exit, which costs concurrent kernels dearly
   auto capped = [&](int limit) { return 2 * B < limit ? 2 * B : limit; };
-  GCCB_LAUNCH(kgiant, capped(8), 1024, 0, s_giant, GCCB_PE_ARGS(5));
-  {
-    const int items = capped(8);                         // clusters; persistent over the work list
+  GCCB_LAUNCH(kgiant, capped(8), 1024, 0, s_giant, GCCB_PE_ARGS(6));
+  // two cluster launches: 192-row slabs (class 4) and 448-row slabs (class 5, same stream as the
+  // L2 fallback: both are rare); persistent over their work lists
+  for (int pass = 0; pass < 2; ++pass) {
+    const int cls = pass == 0 ? 4 : 5;
+    const size_t smem = pass == 0 ? s_d1 : s_d;
+    const int items = capped(pass == 0 ? 8 : 4);
+    gccb_stream_t st = pass == 0 ? s_huge : s_giant;
 #ifndef GCCB_EMU
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CLUSTER * items); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = s_d;
-    cfg.stream = (cudaStream_t)s_huge;
+    cfg.gridDim = dim3(CLUSTER * items); cfg.blockDim = dim3(GCCB_BIG_NT); cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     ++gccb::g_launch_count;
-    cudaLaunchKernelEx(&cfg, khuge, (const int32_t*)worklist, (const int32_t*)counts, 4, B, batch->node_cap,
+    cudaLaunchKernelEx(&cfg, khuge, (const int32_t*)worklist, (const int32_t*)counts, cls, B, batch->node_cap,
                        batch->edge_cap, (const int32_t*)batch->node_off, (const int32_t*)batch->indptr,
                        (const int32_t*)batch->indices, (const int32_t*)batch->sub_deg, pos_dim, normalize, dinv, pos,
                        eigvals, batch->flags, dbg_iters, dbg_res, dbg_phase);
 #else
-    GCCB_LAUNCH(khuge, items, 1024, s_d, s_huge, worklist, counts, 4, B, batch->node_cap, batch->edge_cap,
+    GCCB_LAUNCH(khuge, items, GCCB_BIG_NT, smem, st, worklist, counts, cls, B, batch->node_cap, batch->edge_cap,
                 batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, dinv, pos,
                 eigvals, batch->flags, dbg_iters, dbg_res, dbg_phase);
 #endif
   }
-  GCCB_LAUNCH(kbig, capped(148), 1024, s_c, s_big, GCCB_PE_ARGS(3));
+  GCCB_LAUNCH(kbig, capped(148), GCCB_BIG_NT, s_c, s_big, GCCB_PE_ARGS(3));
   GCCB_LAUNCH(kmid, capped(148 * 2), 256, s_b, s_mid2, GCCB_PE_ARGS(2));
   GCCB_LAUNCH(kmid, capped(148 * 3), 256, s_a, s_mid1, GCCB_PE_ARGS(1));
   GCCB_LAUNCH(ksmall, capped(148), 256, 0, s_small, worklist, counts, B, batch->node_cap, batch->edge_cap,

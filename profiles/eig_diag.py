@@ -30,7 +30,7 @@ for rep in range(3):
     print("posenc ms", ev[0].elapsed_time(ev[1]))
 ws = buf.ws_posenc
 ints = ws.view(torch.int32)
-NC = 6
+NC = 7
 ni = (((NC * 2 * B + NC + 2 * B) + 63) // 64) * 64
 iters = ints[NC * 2 * B + NC: NC * 2 * B + NC + 2 * B].cpu().numpy()
 res = ws[ni * 4: ni * 4 + 2 * B * 4].view(torch.float32).cpu().numpy()

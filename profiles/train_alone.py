@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""GPU diagnostic: the training part of the step alone (no sampler / eigensolver in flight), on the
+whole GPU or inside a green-context partition of N SMs."""
+import contextlib
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from gcc_b200.contrastive.memory_moco import MemoryMoCo  # noqa: E402
+from gcc_b200.datasets.graph_dataset import LoadBalanceGraphDataset  # noqa: E402
+from gcc_b200.engine import PretrainEngine  # noqa: E402
+from gcc_b200.models import GraphEncoder  # noqa: E402
+
+cfg = bench.CONFIGS["c2"]
+dev = torch.device("cuda")
+g = bench.make_graph_device(cfg, dev)
+B, L, H, K = cfg["batch"], cfg["layers"], cfg["hidden"], cfg["K"]
+ds = LoadBalanceGraphDataset(rw_hops=cfg["rw_hops"], restart_prob=0.8, dgl_graphs_file=g, batch_size=B, seed=0)
+
+
+def mk():
+    return GraphEncoder(positional_embedding_size=32, max_degree=512, degree_embedding_size=16, output_dim=H,
+                        node_hidden_dim=H, num_layers=L, norm=True, gnn_model="gin", degree_input=True)
+
+
+model, ema = mk(), mk()
+ema.load_state_dict(model.state_dict())
+model, ema = model.to(dev), ema.to(dev)
+with contextlib.redirect_stdout(sys.stderr):
+    contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
+sms = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=2, train_sms=sms or None)
+for _ in range(4):
+    eng.step(lr=0.005)
+torch.cuda.synchronize()
+N = 30
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+with torch.cuda.stream(eng.train_stream):
+    for _ in range(3):
+        eng._step(0.005, None, True)
+    e0.record()
+    for _ in range(N):
+        eng._step(0.005, None, True)
+    e1.record()
+torch.cuda.synchronize()
+print("train part alone, train_sms=%s: %.3f ms/step" % (sms or "all", e0.elapsed_time(e1) / N))
+# the data part alone on its streams (two batches in flight, nothing training)
+eng.timing = []
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0.record()
+for s_ in eng.data_streams:
+    s_.wait_stream(torch.cuda.current_stream())
+for i in range(N):
+    eng.prepared = 10 + i                      # bypass the consumed-slot waits: nothing consumes here
+    eng._prepare(None)
+for s_ in eng.data_streams:
+    torch.cuda.current_stream().wait_stream(s_)
+t1.record()
+torch.cuda.synchronize()
+print("data part alone (S=2 in flight): %.3f ms/batch" % (t0.elapsed_time(t1) / N))
