@@ -47,17 +47,3 @@ with torch.cuda.stream(eng.train_stream):
     e1.record()
 torch.cuda.synchronize()
 print("train part alone, train_sms=%s: %.3f ms/step" % (sms or "all", e0.elapsed_time(e1) / N))
-# the data part alone on its streams (two batches in flight, nothing training)
-eng.timing = []
-t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-t0.record()
-for s_ in eng.data_streams:
-    s_.wait_stream(torch.cuda.current_stream())
-for i in range(N):
-    eng.prepared = 10 + i                      # bypass the consumed-slot waits: nothing consumes here
-    eng._prepare(None)
-for s_ in eng.data_streams:
-    torch.cuda.current_stream().wait_stream(s_)
-t1.record()
-torch.cuda.synchronize()
-print("data part alone (S=2 in flight): %.3f ms/batch" % (t0.elapsed_time(t1) / N))
