@@ -56,19 +56,21 @@ Drv* drv() {
 }
 }  // namespace
 
-// A side stream that launches where `like` launches: inside the same green context if `like`
-// belongs to one, an ordinary non-blocking stream otherwise.
+// A side stream that launches where and how `like` launches: same priority, and inside the same
+// green context if `like` belongs to one.
 cudaStream_t create_stream_like(cudaStream_t like) {
+  int prio = 0;
+  if (cudaStreamGetPriority(like, &prio) != cudaSuccess) { cudaGetLastError(); prio = 0; }
   Drv* d = drv();
   if (d->ok && like) {
     CUgreenCtx g = nullptr;
     if (d->StreamGetGreenCtx((CUstream)like, &g) == CUDA_SUCCESS && g) {
       CUstream s = nullptr;
-      if (d->GreenCtxStreamCreate(&s, g, CU_STREAM_NON_BLOCKING, 0) == CUDA_SUCCESS) return (cudaStream_t)s;
+      if (d->GreenCtxStreamCreate(&s, g, CU_STREAM_NON_BLOCKING, prio) == CUDA_SUCCESS) return (cudaStream_t)s;
     }
   }
   cudaStream_t s = nullptr;
-  cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio);   // same scheduling priority as the caller's stream
   return s;
 }
 }  // namespace gccb
