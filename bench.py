@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--train-sms", type=int, default=0,
                     help="SMs reserved for the training kernels (green-context partition); 0 = shared")
-    ap.add_argument("--prefetch", type=int, default=3, choices=[1, 2, 3, 4],
+    ap.add_argument("--prefetch", type=int, default=4, choices=[1, 2, 3, 4, 5, 6],
                     help="batches the sampler/eigensolver streams run ahead of the training stream")
     return ap.parse_args()
 
@@ -463,6 +463,7 @@ def emit(line):
 
 def main():
     global _REAL_STDOUT
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # see gcc_b200/__init__.py (before CUDA starts)
     args = parse()
     cfg = CONFIGS[args.config]
     sys.stdout.flush()

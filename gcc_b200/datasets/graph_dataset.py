@@ -48,16 +48,18 @@ def load_graphs(spec):
     raise TypeError("unsupported graph spec %r" % (spec,))
 
 
-def budget_for_degree(deg, rw_hops, restart_prob):
-    """max_nodes_per_seed, gcc/datasets/graph_dataset.py:113-124 (same arithmetic)."""
-    return max(rw_hops, int(((deg ** 0.75) * math.e / (math.e - 1) / restart_prob) + 0.5))
+def budget_for_degree(deg, rw_hops, restart_prob, exponent=0.75):
+    """max_nodes_per_seed: gcc/datasets/graph_dataset.py:113-124 (pretraining loader, deg^0.75) or
+    :243-254 (GraphDataset family used by generate.py / finetuning, plain degree) -- same arithmetic."""
+    d = (deg ** 0.75) if exponent == 0.75 else deg
+    return max(rw_hops, int((d * math.e / (math.e - 1) / restart_prob) + 0.5))
 
 
 class DeviceGraph:
     """Parent CSR + sampler tables in HBM (built once; the reference re-loads graphs per worker,
     graph_dataset.py:23-30)."""
 
-    def __init__(self, graph, rw_hops, restart_prob, key, device):
+    def __init__(self, graph, rw_hops, restart_prob, key, device, budget_exponent=0.75):
         as_t = lambda x, dt: (x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))).to(
             device=device, dtype=dt).contiguous()
         self.indptr = as_t(graph.indptr, torch.int64)
@@ -72,7 +74,7 @@ class DeviceGraph:
         uniq = torch.unique(deg).cpu().numpy()
         table = np.zeros(self.max_degree + 1, dtype=np.int32)
         for d in uniq:
-            table[d] = budget_for_degree(int(d), rw_hops, restart_prob)
+            table[d] = budget_for_degree(int(d), rw_hops, restart_prob, budget_exponent)
         table = np.maximum.accumulate(table)          # unused degrees: any value; keep monotone
         self.max_budget = int(table.max())
         p = deg.double() ** 0.75                       # graph_dataset.py:86-87
@@ -239,3 +241,46 @@ class LoadBalanceGraphDataset(torch.utils.data.IterableDataset):
         for _ in range(self.total // self.batch_size):
             buf = self.sample_batch()
             yield BatchedSubgraphs(buf, 0), BatchedSubgraphs(buf, 1)
+
+
+class NodeClassificationDataset:
+    """generate.py's dataset (graph_dataset.py:279-309 on top of GraphDataset :218-275): item idx is
+    NODE idx of one graph, seeds are taken in order (no sampling), both views walk from the seed
+    (step_dist [1,0,0]) with budget max(rw_hops, int(deg*e/(e-1)/restart + 0.5)) -- plain degree,
+    unlike the pretraining loader.  `dataset` is a CSRGraph or an .npz path (the reference's
+    downloaded datasets need the network / DGL).  Iterating yields batched (graph_q, graph_k, count)
+    with `count` valid pairs (the last batch is padded with the last node)."""
+
+    def __init__(self, dataset, rw_hops=64, subgraph_size=64, restart_prob=0.8,
+                 positional_embedding_size=32, step_dist=[1.0, 0.0, 0.0], device="cuda", seed=0,
+                 batch_size=256, node_cap=None, edge_cap=None):
+        assert positional_embedding_size > 1
+        if list(step_dist) != [1.0, 0.0, 0.0]:
+            raise NotImplementedError("only step_dist=[1,0,0] (generate.py never sets another)")
+        self.rw_hops, self.subgraph_size, self.restart_prob = rw_hops, subgraph_size, restart_prob
+        self.positional_embedding_size, self.step_dist = positional_embedding_size, step_dist
+        graph, _ = load_graphs(dataset)
+        self.device = torch.device(device)
+        _lib.require_device()
+        self.graph = DeviceGraph(graph, rw_hops, restart_prob, int(seed), self.device, budget_exponent=1.0)
+        self.length = self.total = self.graph.num_nodes
+        self.batch_size = B = int(min(batch_size, self.length))
+        mb = self.graph.max_budget
+        self.node_cap = int(node_cap or (B * min(mb + HOPCAP, 320) + mb + HOPCAP))
+        self.edge_cap = int(edge_cap or self.node_cap * 16)
+        self.buffers = BatchBuffers(B, self.node_cap, self.edge_cap, positional_embedding_size, mb, self.device)
+        self._sampler = LoadBalanceGraphDataset.sample_batch
+
+    def __len__(self):
+        return self.length
+
+    def __iter__(self):
+        B = self.batch_size
+        for start in range(0, self.length, B):
+            count = min(B, self.length - start)
+            seeds = torch.arange(start, start + B, device=self.device).clamp_(max=self.length - 1)
+            buf = self._sampler(self, first_sample=start, seeds=seeds)
+            buf.check_flags()
+            yield BatchedSubgraphs(buf, 0), BatchedSubgraphs(buf, 1), count
+
+    posenc = LoadBalanceGraphDataset.posenc

@@ -5,10 +5,11 @@ import contextlib
 import os
 import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gcc_b200  # noqa: F401  (sets CUDA_DEVICE_MAX_CONNECTIONS before CUDA starts)
 import torch
 from torch.profiler import ProfilerActivity, profile
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from gcc_b200.contrastive.memory_moco import MemoryMoCo  # noqa: E402
 from gcc_b200.datasets.graph_dataset import LoadBalanceGraphDataset  # noqa: E402

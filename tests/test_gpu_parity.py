@@ -456,3 +456,58 @@ def test_engine_prefetch_matches_serial():
             assert np.array_equal(o0[v, :n0[v, -1]], o1[v, :n1[v, -1]])
         assert np.allclose(l0, l1, rtol=1e-4), (l0, l1)
         assert np.allclose(p0, p1, atol=2e-3), np.abs(p0 - p1).max()
+
+
+def test_generate_eval_mode_embeddings_match_oracle():
+    """generate.py:33-53 -- (f(q) + f(k)) / 2 with eval-mode BatchNorm, seeds = every node in order,
+    budget from the plain degree (graph_dataset.py:243-254): walks bit-exact, embeddings <= 1e-3."""
+    from gcc_b200.datasets import synthetic
+    from gcc_b200.datasets.graph_dataset import NodeClassificationDataset, budget_for_degree
+    from gcc_b200.models import GraphEncoder
+    from oracle import model as om
+    from oracle import rwr as orwr
+    torch.manual_seed(3)
+    g = synthetic.erdos_renyi(150, 600, seed=4)
+    ds = NodeClassificationDataset(g, rw_hops=24, restart_prob=0.8, batch_size=64, seed=11)
+    model = GraphEncoder(positional_embedding_size=32, max_degree=512, degree_embedding_size=16, output_dim=64,
+                         node_hidden_dim=64, num_layers=3, norm=True, gnn_model="gin", degree_input=True)
+    sd = model.state_dict()
+    for k_, v in sd.items():                               # non-trivial running statistics
+        if k_.endswith("running_mean"):
+            v.copy_(torch.randn_like(v) * 0.1)
+        elif k_.endswith("running_var"):
+            v.copy_(torch.rand_like(v) + 0.5)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    P = {k_: v.detach().cpu().double() for k_, v in model.state_dict().items()}
+    deg = np.diff(g.indptr)
+    bt = np.array([budget_for_degree(d, 24, 0.8, exponent=1.0) for d in range(int(deg.max()) + 1)], np.int32)
+    got, want = [], []
+    for gq, gk, count in ds:
+        B = gq.batch_size
+        with torch.no_grad():
+            got.append(((model(gq) + model(gk)) / 2)[:count].cpu().numpy())
+        buf = ds.buffers
+        seeds = buf.seeds.cpu().numpy()
+        sids = buf.sample_ids.cpu().numpy()
+        ref = orwr.rwr_batch(g.indptr, g.indices, 11, sids, seeds, bt, orwr.restart_threshold(0.8),
+                             int(bt.max()) + 65, 1 << 16)
+        feats = []
+        for v in (0, 1):
+            noff = buf.node_off[v].cpu().numpy().astype(np.int64)
+            n = int(noff[B])
+            orig = buf.orig_id[v].cpu().numpy()
+            for gi in range(B):
+                assert np.array_equal(orig[noff[gi]:noff[gi + 1]], ref[2 * gi + v]["subv"])
+            seed_flag = np.zeros(n, np.int64)
+            seed_flag[noff[:B]] = 1
+            f, _, _ = om.gin_encoder_forward(
+                P, buf.indptr[v, :n + 1].cpu().numpy().astype(np.int64),
+                buf.indices[v, :int(buf.edge_off[v, B])].cpu().numpy().astype(np.int64),
+                buf.pos[v, :n].cpu().double(), seed_flag, buf.sub_deg[v, :n].cpu().numpy(), noff,
+                num_layers=3, bn_train=False)
+            feats.append(f.detach().numpy())
+        want.append(((feats[0] + feats[1]) / 2)[:count])
+    got, want = np.concatenate(got), np.concatenate(want)
+    assert got.shape == (150, 64)
+    assert np.allclose(got, want, rtol=1e-3, atol=1e-4), np.abs(got - want).max()
