@@ -371,7 +371,8 @@ def run_ours(args, cfg):
     n_e2e = max(args.steps // 2, 5)
     host_seeds = torch.from_numpy(np.searchsorted(cdf_host, rs.random_sample((n_e2e + 2, B)), side="right")
                                   .clip(max=len(cdf_host) - 1).astype(np.int64)).pin_memory()
-    loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+    loss_ring = torch.zeros(4, 4, dtype=torch.float32).pin_memory()
+    done = [torch.cuda.Event() for _ in range(4)]
     seeds_ring = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(4)]
     for i in range(2):
         seeds_ring[i & 3].copy_(host_seeds[i], non_blocking=True)
@@ -379,11 +380,17 @@ def run_ours(args, cfg):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    e2e_losses = []
     for i in range(n_e2e):
         seeds_ring[i & 3].copy_(host_seeds[2 + i], non_blocking=True)   # seeds of the batch prepared this step
         eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i & 3])
-        loss_host.copy_(eng.stats, non_blocking=True)
-        torch.cuda.current_stream().synchronize()           # the reference's .item() per step (train.py:420-422)
+        loss_ring[i & 3].copy_(eng.stats, non_blocking=True)            # D2H of this step's loss / prob / grad norm
+        done[i & 3].record()
+        if i >= 1:          # the reference's .item() per step (train.py:420-422), read one step late so that the
+            done[(i - 1) & 3].synchronize()                             # host enqueues step i while step i-1 runs
+            e2e_losses.append(float(loss_ring[(i - 1) & 3][0]))
+    done[(n_e2e - 1) & 3].synchronize()
+    e2e_losses.append(float(loss_ring[(n_e2e - 1) & 3][0]))
     e1.record()
     barrier()
     t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -406,7 +413,7 @@ def run_ours(args, cfg):
             "pairs_per_sec": value / 2.0,
             "e2e": {"value": e2e_value, "unit": "subgraphs/sec", "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": 16, "steps": n_e2e,
-                    "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step (trains batch t, prepares batch t+1 from these seeds) -> stats D2H + sync"},
+                    "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step (trains batch t, prepares a later batch from these seeds) -> stats D2H every step, host waits for the previous step's copy"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "clocks": clk, "roofline": roofline, "eigensolver": eig, "phases_ms": phases,
             "loss": stats["loss"], "grad_norm": stats["grad_norm"]}

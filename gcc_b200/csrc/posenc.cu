@@ -46,6 +46,12 @@ namespace gccb {
 #define GCCB_CF_NSM_D1 1536        //   n <= 1536: cluster of 8 CTAs (DSMEM), 192-row slabs (75 KB per CTA);
 #define GCCB_CF_NSM_D 3584         //   n <= 3584: cluster of 8 CTAs, 448-row slabs; larger: L2 workspace
 #define GCCB_EIG_NCLASS 7
+#ifndef GCCB_CAP_MID1
+#define GCCB_CAP_MID1 (148 * 3)     // persistent grid of the n <= 96 class (3 CTAs per SM)
+#endif
+#ifndef GCCB_CAP_MID2
+#define GCCB_CAP_MID2 (148 * 2)     // persistent grid of the n <= 160 class (2 CTAs per SM)
+#endif
 #ifndef GCCB_BIG_NT
 #define GCCB_BIG_NT 512            // threads of the large-ego-net CTAs: 512 x 64 registers leave half of
 #endif                             // the SM's register file to concurrent kernels (these CTAs live for ms)
@@ -1461,8 +1467,8 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
 #endif
   }
   GCCB_LAUNCH(kbig, capped(148), GCCB_BIG_NT, s_c, s_big, GCCB_PE_ARGS(3));
-  GCCB_LAUNCH(kmid, capped(148 * 2), 256, s_b, s_mid2, GCCB_PE_ARGS(2));
-  GCCB_LAUNCH(kmid, capped(148 * 3), 256, s_a, s_mid1, GCCB_PE_ARGS(1));
+  GCCB_LAUNCH(kmid, capped(GCCB_CAP_MID2), 256, s_b, s_mid2, GCCB_PE_ARGS(2));
+  GCCB_LAUNCH(kmid, capped(GCCB_CAP_MID1), 256, s_a, s_mid1, GCCB_PE_ARGS(1));
   GCCB_LAUNCH(ksmall, capped(148), 256, 0, s_small, worklist, counts, B, batch->node_cap, batch->edge_cap,
               batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, pos, eigvals,
               batch->flags, dbg_iters, dbg_res);

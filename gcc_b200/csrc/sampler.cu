@@ -59,8 +59,10 @@ __device__ __forceinline__ bool adj_find(const int32_t* __restrict__ indices, in
 // A hub row (parent degree >> ego-net size) is not streamed: each ego-net vertex is looked up in the
 // hub's sorted neighbour list instead (n log deg probes instead of deg reads).
 #define GCCB_REVERSE_FACTOR 16
+#ifndef GCCB_ST
 #define GCCB_ST 1024           // threads per CTA of the walk / fill kernels: hub ego-nets (thousands of
                                // vertices, ~1e5..1e6 neighbour probes) are the tail of these kernels
+#endif
 #define GCCB_SW (GCCB_ST / 32)
 
 // Pass 1: walk + sort/unique + induced-degree count.  grid = 2B, block = GCCB_ST.
