@@ -291,10 +291,16 @@ __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64
         if (p > q) { int t = p; p = q; q = t; }
         float c = 1.0f, s = 0.f;
         const float app = A[p * LD + p], aqq = A[q * LD + q], apq = A[q * LD + p];
-        if (fabsf(apq) > tol * sqrtf(fabsf(app * aqq))) {
-          const float zeta = (aqq - app) / (2.0f * apq);
-          const float t = (zeta >= 0.f ? 1.0f : -1.0f) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
-          c = 1.0f / sqrtf(1.0f + t * t);
+        // (diagonal of G = H + 2I lies in [1, 3]: the arithmetic mean is as good a scale as the geometric one)
+        if (fabsf(apq) > tol * 0.5f * (fabsf(app) + fabsf(aqq))) {
+          // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = d / (2 apq), without dividing by apq;
+          // fast division / reciprocal square root: this dependent chain is on the critical path of
+          // every round, and a 2-ulp rotation error is far below the Ritz tolerance
+          const float d = aqq - app;
+          const float two_apq = 2.0f * apq;
+          const float den = fabsf(d) + __fsqrt_rn(fmaf(d, d, two_apq * two_apq));
+          const float t = __fdividef(d >= 0.f ? two_apq : -two_apq, den);
+          c = rsqrtf(fmaf(t, t, 1.0f));
           s = c * t;
           rotated = 1;
           rot_round = 1;
@@ -699,11 +705,17 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
       // dots of column j with all columns (itself included) come from one pass over the rows;
       // ||y - Q Q^T y||^2 = y.y - sum r_i^2, so neither the test nor the norm needs another reduction
       float nrm2 = 0.f;
+      bool scaled = false;
       for (int pass = 0; pass < 2; ++pass) {
         const float* Xc = X;
         column_sums(n, part, rdot, rr2, j, [&](int r, int c) { return Xc[(size_t)r * ld + c] * Xc[(size_t)r * ld + j]; });
         const float yy = rdot[j];
         const float rr = rr2[0] + rr2[1];
+        nrm2 = yy - rr;
+        // little was removed: this is the last pass, so the column is normalised while it is in hand
+        // (norm from the same Pythagoras identity; relative error <= 2 eps when nrm2 > yy / 2)
+        scaled = nrm2 > 0.5f * yy && nrm2 > 1e-30f;
+        const float sc = scaled ? 1.0f / sqrtf(nrm2) : 1.0f;
         for (int r = tid; r < n; r += NT) {
           float* row = X + (size_t)r * ld;
           float v0 = row[j], v1 = 0.f;
@@ -713,20 +725,21 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
             v1 = fmaf(-rdot[i + 1], row[i + 1], v1);
           }
           if (i < j) v0 = fmaf(-rdot[i], row[i], v0);
-          row[j] = v0 + v1;
+          row[j] = (v0 + v1) * sc;
         }
-        nrm2 = yy - rr;
         __syncthreads();
-        if (nrm2 > 0.5f * yy) break;                     // little was removed: no second pass needed
+        if (nrm2 > 0.5f * yy) break;                     // no second pass needed
       }
-      if (!(nrm2 > 1e-30f)) {                            // cancellation: measure the norm directly
-        const float* Xc = X;
-        column_sums(n, part, rdot, rr2, 0, [&](int r, int c) { return c == j ? Xc[(size_t)r * ld + j] * Xc[(size_t)r * ld + j] : 0.f; });
-        nrm2 = rdot[j];
+      if (!scaled) {
+        if (!(nrm2 > 1e-30f)) {                          // cancellation: measure the norm directly
+          const float* Xc = X;
+          column_sums(n, part, rdot, rr2, 0, [&](int r, int c) { return c == j ? Xc[(size_t)r * ld + j] * Xc[(size_t)r * ld + j] : 0.f; });
+          nrm2 = rdot[j];
+        }
+        const float inv = nrm2 > 1e-30f ? 1.0f / sqrtf(nrm2) : 0.f;
+        for (int r = tid; r < n; r += NT) X[(size_t)r * ld + j] *= inv;
+        __syncthreads();
       }
-      const float inv = nrm2 > 1e-30f ? 1.0f / sqrtf(nrm2) : 0.f;
-      for (int r = tid; r < n; r += NT) X[(size_t)r * ld + j] *= inv;
-      __syncthreads();
     }
     GCCB_TICK(1);
     // ---- Z = L Q (into Y), H = Q^T Z ----------------------------------------------------------------
@@ -1170,11 +1183,15 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
     // ---- CGS2 over the cluster --------------------------------------------------------------------
     for (int j = 0; j < CB; ++j) {
       float nrm2 = 0.f;
+      bool scaled = false;
       for (int pass = 0; pass < 2; ++pass) {
         const float* Xc = X;
         cl_column_sums(C, rdot, rr2, j, [&](int rl, int c) { return Xc[(size_t)rl * ld + c] * Xc[(size_t)rl * ld + j]; });
         const float yy = rdot[j];
         const float rr = rr2[0] + rr2[1];
+        nrm2 = yy - rr;
+        scaled = nrm2 > 0.5f * yy && nrm2 > 1e-30f;      // last pass: normalise in the same sweep
+        const float sc = scaled ? 1.0f / sqrtf(nrm2) : 1.0f;
         for (int rl = tid; rl < nloc; rl += NT) {
           float* row = X + (size_t)rl * ld;
           float v0 = row[j], v1 = 0.f;
@@ -1184,20 +1201,21 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
             v1 = fmaf(-rdot[i + 1], row[i + 1], v1);
           }
           if (i < j) v0 = fmaf(-rdot[i], row[i], v0);
-          row[j] = v0 + v1;
+          row[j] = (v0 + v1) * sc;
         }
-        nrm2 = yy - rr;
         __syncthreads();
         if (nrm2 > 0.5f * yy) break;                     // identical decision on every CTA (same rdot bits)
       }
-      if (!(nrm2 > 1e-30f)) {
-        const float* Xc = X;
-        cl_column_sums(C, rdot, rr2, 0, [&](int rl, int c) { return c == j ? Xc[(size_t)rl * ld + j] * Xc[(size_t)rl * ld + j] : 0.f; });
-        nrm2 = rdot[j];
+      if (!scaled) {
+        if (!(nrm2 > 1e-30f)) {
+          const float* Xc = X;
+          cl_column_sums(C, rdot, rr2, 0, [&](int rl, int c) { return c == j ? Xc[(size_t)rl * ld + j] * Xc[(size_t)rl * ld + j] : 0.f; });
+          nrm2 = rdot[j];
+        }
+        const float inv = nrm2 > 1e-30f ? 1.0f / sqrtf(nrm2) : 0.f;
+        for (int rl = tid; rl < nloc; rl += NT) X[(size_t)rl * ld + j] *= inv;
+        __syncthreads();
       }
-      const float inv = nrm2 > 1e-30f ? 1.0f / sqrtf(nrm2) : 0.f;
-      for (int rl = tid; rl < nloc; rl += NT) X[(size_t)rl * ld + j] *= inv;
-      __syncthreads();
     }
     GCCB_TICK(1);
     // ---- Z = L Q, H = Q^T Z (partial per CTA, summed over the cluster) -------------------------------
