@@ -182,86 +182,6 @@ __device__ __forceinline__ int jacobi_onesided(float* G, float* nrm, int n, int 
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Cyclic two-sided Jacobi for a small symmetric matrix in shared memory (m <= 64): A (m x m,
-// column-major, leading dimension LD, odd LD -> conflict-free) is diagonalised, V accumulates the
-// eigenvectors (columns).  Round-robin ordering: the m/2 disjoint rotations of a round are each
-// derived by ONE thread from three scalars (no dot products, no shuffles), then the whole block
-// applies them -- columns of A and V, then rows of A.  A must have a positive diagonal (callers
-// pass L + 2I or H + 2I): the skip test is relative to sqrt(a_pp a_qq).  Returns sweeps used.
-template <int THREADS, class T>
-__device__ __forceinline__ int jacobi_twosided(T* A, T* V, T* cs /*[64]*/, int* pq /*[32]*/, int m, int LD) {
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < m * m; idx += THREADS) {
-    const int j = idx / m, i = idx - j * m;
-    V[j * LD + i] = i == j ? (T)1 : (T)0;
-  }
-  const int mm = m + (m & 1), half = mm >> 1;
-  __syncthreads();
-  int sweep = 0;
-  for (; sweep < GCCB_EIG_MAXSWEEP; ++sweep) {
-    int rotated = 0;
-    for (int r = 0; r < mm - 1; ++r) {
-      int rot_round = 0;
-      if (tid < half) {
-        int p, q;
-        if (tid == 0) { p = mm - 1; q = r; }
-        else { p = (r + tid) % (mm - 1); q = (r + mm - 1 - tid) % (mm - 1); }
-        if (p > q) { int t = p; p = q; q = t; }
-        T c = (T)1, s = (T)0;
-        if (q < m) {
-          const T app = A[p * LD + p], aqq = A[q * LD + q], apq = A[q * LD + p];
-          const T tol = sizeof(T) == 8 ? (T)1e-14 : (T)1.0e-6;
-          if (fabs(apq) > tol * sqrt(fabs(app * aqq))) {
-            const T zeta = (aqq - app) / ((T)2 * apq);
-            const T t = (zeta >= (T)0 ? (T)1 : (T)-1) / (fabs(zeta) + sqrt((T)1 + zeta * zeta));
-            c = (T)1 / sqrt((T)1 + t * t);
-            s = c * t;
-            rotated = 1;
-            rot_round = 1;
-          }
-        } else {
-          p = q = -1;                                  // bye
-        }
-        cs[2 * tid] = c; cs[2 * tid + 1] = s; pq[tid] = (p & 0xffff) | (q << 16);
-      }
-      if (!__syncthreads_or(rot_round)) continue;         // nothing to rotate in this round
-      // columns: A <- A J, V <- V J      (item = pair, row)
-      for (int item = tid; item < half * m; item += THREADS) {
-        const int pr = item / m, i = item - pr * m;
-        const int code = pq[pr];
-        const int q = code >> 16;
-        if (q < 0) continue;
-        const int p = code & 0xffff;
-        const T c = cs[2 * pr], s = cs[2 * pr + 1];
-        if (s == (T)0) continue;
-        T x = A[p * LD + i], y = A[q * LD + i];
-        A[p * LD + i] = c * x - s * y;
-        A[q * LD + i] = s * x + c * y;
-        x = V[p * LD + i]; y = V[q * LD + i];
-        V[p * LD + i] = c * x - s * y;
-        V[q * LD + i] = s * x + c * y;
-      }
-      __syncthreads();
-      // rows: A <- J^T A                 (item = pair, column)
-      for (int item = tid; item < half * m; item += THREADS) {
-        const int pr = item / m, j = item - pr * m;
-        const int code = pq[pr];
-        const int q = code >> 16;
-        if (q < 0) continue;
-        const int p = code & 0xffff;
-        const T c = cs[2 * pr], s = cs[2 * pr + 1];
-        if (s == (T)0) continue;
-        const T x = A[j * LD + p], y = A[j * LD + q];
-        A[j * LD + p] = c * x - s * y;
-        A[j * LD + q] = s * x + c * y;
-      }
-      __syncthreads();
-    }
-    if (!__syncthreads_or(rotated)) break;
-  }
-  return sweep;
-}
 
 // Two-sided Jacobi specialised for the even-order Ritz problem (m = 48): per round ONE thread per pair
 // derives (c, s); then every thread applies BOTH sides of the similarity transform to whole 2 x 2
@@ -579,9 +499,7 @@ __device__ __forceinline__ void column_sums(int n, float* part /*[32][48]*/, flo
 }
 
 // MODE 1: both n x 48 blocks live in dynamic shared memory (ld = 49, conflict-free); MODE 0: both in
-// the L2-resident workspace (ld = 48); MODE 2: X in shared memory, Y in the workspace -- the filter
-// then keeps the block that is GATHERED from in shared memory and swaps rows after every step, so
-// random accesses never leave the SM (ego-nets of 480 < n <= 1000 nodes).
+// the L2-resident workspace (ego-nets too large even for the cluster kernel).
 // cls selects the work list; blockDim.x = 256 or 1024.
 template <int MODE, int NT>
 __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t* __restrict__ worklist, const int32_t* __restrict__ counts, int cls,
@@ -632,9 +550,6 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
   if (MODE == 1) {
     X = dynsm;
     Y = dynsm + (size_t)n * LD;
-  } else if (MODE == 2) {
-    X = dynsm;
-    Y = blocks + ((size_t)view * node_cap + noff) * LD;
   } else {
     X = blocks + ((size_t)view * node_cap + noff) * LD;                // n x 48 (ld 49), row-major
     Y = X + (size_t)2 * node_cap * LD;
@@ -662,31 +577,6 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
       const float sigma1 = sigma;
       spmm_cheb(S, X, Y, ld, sigma1 / e, cen, 0.f);                           // Y1
       __syncthreads();
-      if (MODE == 2) {
-        // cur must stay in shared memory: swap rows X <-> Y (now X = Y1 = cur, Y = prev)
-        for (int r = warp; r < n; r += NW) {
-          const size_t o = (size_t)r * ld + lane;
-          float a = X[o], b = Y[o], a1 = 0.f, b1 = 0.f;
-          if (hi) { a1 = X[o + 32]; b1 = Y[o + 32]; }
-          X[o] = b; Y[o] = a;
-          if (hi) { X[o + 32] = b1; Y[o + 32] = a1; }
-        }
-        __syncthreads();
-        for (int i = 2; i <= deg; ++i) {
-          const float sigma2 = 1.0f / (2.0f / sigma1 - sigma);
-          spmm_cheb(S, X, Y, ld, 2.0f * sigma2 / e, cen, sigma * sigma2);     // new overwrites prev (in Y)
-          __syncthreads();
-          for (int r = warp; r < n; r += NW) {                                // swap: X = new, Y = old cur
-            const size_t o = (size_t)r * ld + lane;
-            float a = X[o], b = Y[o], a1 = 0.f, b1 = 0.f;
-            if (hi) { a1 = X[o + 32]; b1 = Y[o + 32]; }
-            X[o] = b; Y[o] = a;
-            if (hi) { X[o + 32] = b1; Y[o + 32] = a1; }
-          }
-          __syncthreads();
-          sigma = sigma2;
-        }
-      } else {
       float* cur = Y; float* prev = X;
       for (int i = 2; i <= deg; ++i) {
         const float sigma2 = 1.0f / (2.0f / sigma1 - sigma);
@@ -696,7 +586,6 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
         sigma = sigma2;
       }
       X = cur; Y = prev;                                 // filtered block in X, Y is scratch
-      }
     }
     GCCB_TICK(0);
     // ---- CGS2: orthonormalise the columns of X in place (row-major: all dots of a column at once)
