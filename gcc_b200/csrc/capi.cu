@@ -28,9 +28,9 @@ int check_launch(const char* what) {
 }
 
 #ifndef GCCB_EMU
-cudaStream_t create_stream_like(cudaStream_t like);        // partition.cu
+cudaStream_t create_stream_like(cudaStream_t like, bool lowest_priority);   // partition.cu
 
-StreamKit* stream_kit(cudaStream_t caller, int family) {
+StreamKit* stream_kit(cudaStream_t caller, int family, bool lowest_priority) {
   static StreamKit kits[16];
   static int nkits = 0;
   static std::mutex mu;
@@ -40,7 +40,7 @@ StreamKit* stream_kit(cudaStream_t caller, int family) {
   StreamKit* k;
   if (nkits < 16) {
     k = &kits[nkits++];
-    for (int i = 0; i < 5; ++i) k->side[i] = create_stream_like(caller);   // same green context as the caller
+    for (int i = 0; i < 5; ++i) k->side[i] = create_stream_like(caller, lowest_priority);   // same green context as the caller
     for (int i = 0; i < 24; ++i) cudaEventCreateWithFlags(&k->ev[i], cudaEventDisableTiming);
   } else {
     k = &kits[15];                                        // more caller streams than kits: share the last one

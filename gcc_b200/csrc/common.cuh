@@ -28,7 +28,7 @@ struct StreamKit {
   cudaStream_t side[5];
   cudaEvent_t ev[24];
 };
-StreamKit* stream_kit(cudaStream_t caller, int family);
+StreamKit* stream_kit(cudaStream_t caller, int family, bool lowest_priority = false);
 }  // namespace gccb
 #endif
 

@@ -58,9 +58,9 @@ Drv* drv() {
 
 // A side stream that launches where and how `like` launches: same priority, and inside the same
 // green context if `like` belongs to one.
-cudaStream_t create_stream_like(cudaStream_t like) {
+cudaStream_t create_stream_like(cudaStream_t like, bool lowest_priority) {
   int prio = 0;
-  if (cudaStreamGetPriority(like, &prio) != cudaSuccess) { cudaGetLastError(); prio = 0; }
+  if (lowest_priority || cudaStreamGetPriority(like, &prio) != cudaSuccess) { cudaGetLastError(); prio = 0; }
   Drv* d = drv();
   if (d->ok && like) {
     CUgreenCtx g = nullptr;

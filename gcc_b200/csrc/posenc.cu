@@ -1329,7 +1329,9 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   // The size classes are independent: fork them over side streams (event fork/join, legal inside
   // CUDA-graph capture) so that the few long-running large ego-nets overlap the many small ones.
 #ifndef GCCB_EMU
-  StreamKit* kit = stream_kit((cudaStream_t)stream, 0);   // per caller stream: batches in flight do not serialise
+  // per caller stream: batches in flight do not serialise.  The size-class kernels are long-lived and go to
+  // lowest-priority streams whatever the caller's priority (a caller may run its short sampler kernels high)
+  StreamKit* kit = stream_kit((cudaStream_t)stream, 0, true);
   cudaStream_t* side = kit->side;
   cudaEvent_t ev_fork = kit->ev[5];
   cudaEvent_t* ev_join = kit->ev;
