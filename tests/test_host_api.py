@@ -47,6 +47,21 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "cuda_emu.h" not in src or f == "common.cuh"      # emu include is #ifdef-guarded
+    for f in ("train.py", "generate.py"):                                # the CLIs are product code too
+        src = open(os.path.join(ROOT, f)).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_generation_budget_uses_the_plain_degree():
+    """GraphDataset.__getitem__ (graph_dataset.py:243-254): max(rw_hops, int(deg*e/(e-1)/restart + 0.5)),
+    no deg^0.75 -- unlike the pretraining loader (:113-124)."""
+    import math
+    from gcc_b200.datasets.graph_dataset import budget_for_degree
+    for deg in (1, 3, 17, 64, 500, 4096):
+        for hops, rp in ((64, 0.8), (256, 0.8), (16, 0.5)):
+            want = max(hops, int((deg * math.e / (math.e - 1) / rp) + 0.5))
+            assert budget_for_degree(deg, hops, rp, exponent=1.0) == want
+            assert budget_for_degree(deg, hops, rp) == max(hops, int(((deg ** 0.75) * math.e / (math.e - 1) / rp) + 0.5))
 
 
 def test_param_layout_matches_c_layout_and_reference_state_dict():
