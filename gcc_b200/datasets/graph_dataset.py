@@ -59,7 +59,7 @@ class DeviceGraph:
     """Parent CSR + sampler tables in HBM (built once; the reference re-loads graphs per worker,
     graph_dataset.py:23-30)."""
 
-    def __init__(self, graph, rw_hops, restart_prob, key, device, budget_exponent=0.75):
+    def __init__(self, graph, rw_hops, restart_prob, key, device, budget_exponent=0.75, budget_cap=None):
         as_t = lambda x, dt: (x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))).to(
             device=device, dtype=dt).contiguous()
         self.indptr = as_t(graph.indptr, torch.int64)
@@ -76,6 +76,8 @@ class DeviceGraph:
         for d in uniq:
             table[d] = budget_for_degree(int(d), rw_hops, restart_prob, budget_exponent)
         table = np.maximum.accumulate(table)          # unused degrees: any value; keep monotone
+        if budget_cap:                                 # capacity knob (sampler sweeps on graphs with huge hubs);
+            table = np.minimum(table, int(budget_cap))  # deviates from the reference formula above the cap
         self.max_budget = int(table.max())
         p = deg.double() ** 0.75                       # graph_dataset.py:86-87
         p = p / p.sum()
@@ -157,7 +159,7 @@ class LoadBalanceGraphDataset(torch.utils.data.IterableDataset):
     def __init__(self, rw_hops=64, restart_prob=0.8, positional_embedding_size=32,
                  step_dist=[1.0, 0.0, 0.0], num_workers=1, dgl_graphs_file="./data/small.bin",
                  num_samples=10000, num_copies=1, graph_transform=None, aug="rwr", num_neighbors=5,
-                 device="cuda", seed=0, batch_size=32, node_cap=None, edge_cap=None):
+                 device="cuda", seed=0, batch_size=32, node_cap=None, edge_cap=None, budget_cap=None):
         super(LoadBalanceGraphDataset).__init__()
         assert sum(step_dist) == 1.0
         assert positional_embedding_size > 1
@@ -190,7 +192,7 @@ class LoadBalanceGraphDataset(torch.utils.data.IterableDataset):
         self.seed = int(seed)
         self.batch_size = int(batch_size)
         _lib.require_device()
-        self.graph = DeviceGraph(graph, rw_hops, restart_prob, self.seed, self.device)
+        self.graph = DeviceGraph(graph, rw_hops, restart_prob, self.seed, self.device, budget_cap=budget_cap)
         B = self.batch_size
         mb = self.graph.max_budget
         self.node_cap = int(node_cap or (B * min(mb + HOPCAP, 320) + mb + HOPCAP))

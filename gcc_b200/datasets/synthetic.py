@@ -150,3 +150,46 @@ def chung_lu_device(n=1_000_000, n_pairs=20_000_000, exponent=0.5, seed=0, devic
     indptr = torch.zeros(n2 + 1, dtype=torch.int64, device=device)
     torch.cumsum(deg, 0, out=indptr[1:])
     return CSRGraph(indptr, d.to(torch.int32), n2, "chunglu_dev_n%d_p%d" % (n, n_pairs))
+
+
+def rmat_device(scale=24, n_pairs=200_000_000, abcd=(0.57, 0.19, 0.19, 0.05), seed=0, device="cuda"):
+    """RMAT graph generated with torch on `device` (setup, not the timed path): 2^scale candidate
+    vertices, n_pairs sampled (src, dst) pairs by recursive quadrant choice, then the x2dgl.py:40-62
+    invariants -- self loops dropped, symmetrised, de-duplicated, zero-degree vertices removed and
+    ids compacted.  BASELINE config 5 (10M-node / 200M-pair RMAT) is scale=24."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    a, b, c, _ = abcd
+    n = 1 << scale
+    keys = []
+    left, chunk = n_pairs, 1 << 24
+    while left > 0:
+        m = min(left, chunk)
+        src = torch.zeros(m, dtype=torch.int64, device=device)
+        dst = torch.zeros(m, dtype=torch.int64, device=device)
+        for _bit in range(scale):
+            r = torch.rand(m, generator=gen, device=device)
+            sbit = (r >= a + b).long()                          # quadrants c, d: lower half of the rows
+            dbit = (((r >= a) & (r < a + b)) | (r >= a + b + c)).long()   # quadrants b, d: right half
+            src = (src << 1) | sbit
+            dst = (dst << 1) | dbit
+        keep = src != dst
+        src, dst = src[keep], dst[keep]
+        keys.append(src * n + dst)
+        keys.append(dst * n + src)
+        left -= m
+    key = torch.unique(torch.cat(keys), sorted=True)
+    del keys
+    s, d = key // n, key % n
+    del key
+    deg = torch.bincount(s, minlength=n)
+    del s
+    alive = deg > 0
+    n2 = int(alive.sum())
+    remap = torch.cumsum(alive.long(), 0) - 1
+    d = remap[d].to(torch.int32)
+    deg = deg[alive]
+    indptr = torch.zeros(n2 + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=indptr[1:])
+    return CSRGraph(indptr, d, n2, "rmat_dev_s%d_p%d" % (scale, n_pairs))
