@@ -29,6 +29,9 @@ CONFIGS = {
     # name: nodes, pairs, batch, K, layers, hidden, rw_hops
     "c2": dict(nodes=1_000_000, pairs=20_000_000, batch=256, K=16384, layers=5, hidden=64, rw_hops=256),
     "small": dict(nodes=50_000, pairs=500_000, batch=64, K=1024, layers=5, hidden=64, rw_hops=64),
+    # BASELINE config 4 shapes (K=65536, hid=256, batch 1024) in fp32: the kernels are SIMT fp32 in round 1,
+    # the bf16 tensor-core variant is future work -- a capability / stress run, not the headline line
+    "c4": dict(nodes=1_000_000, pairs=20_000_000, batch=1024, K=65536, layers=5, hidden=256, rw_hops=256),
 }
 
 
