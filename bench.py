@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--train-sms", type=int, default=0,
                     help="SMs reserved for the training kernels (green-context partition); 0 = shared")
-    ap.add_argument("--prefetch", type=int, default=6, choices=[1, 2, 3, 4, 5, 6, 8],
+    ap.add_argument("--prefetch", type=int, default=4, choices=[1, 2, 3, 4, 5, 6, 8],
                     help="batches the sampler/eigensolver streams run ahead of the training stream")
     return ap.parse_args()
 

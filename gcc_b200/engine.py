@@ -26,7 +26,7 @@ from .parallel import StepExchange, first_sample_id
 class PretrainEngine:
     def __init__(self, dataset, model, model_ema, contrast, moco=True, learning_rate=0.005,
                  betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, clip_norm=1.0, alpha=0.999,
-                 nce_t=0.07, rank=0, world_size=1, process_group=None, prefetch=6, train_sms=None):
+                 nce_t=0.07, rank=0, world_size=1, process_group=None, prefetch=4, train_sms=None):
         _lib.require_device()
         self.lib = _lib.get()
         self.ds, self.model, self.model_ema, self.contrast = dataset, model, model_ema, contrast
@@ -87,9 +87,9 @@ class PretrainEngine:
         # Loader run-ahead (the reference's DataLoader workers prepare later batches while the
         # model trains on batch t, train.py:577-586): sampler + eigensolver of batches t+1..t+S run
         # on S data streams into a ring of S+1 batch buffers and overlap this step's encoder.  The
-        # eigensolver's critical path is a few very large ego-nets, so S=6 batches in flight fill
+        # eigensolver's critical path is a few very large ego-nets, so S=4 batches in flight fill
         # the SMs that one batch leaves idle.  prefetch=0 runs everything on the caller's stream.
-        self.prefetch = 6 if prefetch is True else int(prefetch)
+        self.prefetch = 4 if prefetch is True else int(prefetch)
         self.count_acc = None                          # optional float64[4]: sums of buf.counters
         self.timing = None                             # optional list collecting per-batch events
         self.timing_main = None                        # same for the training stream
