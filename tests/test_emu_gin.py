@@ -185,3 +185,27 @@ def test_moco_head_and_optimiser_vs_oracle():
     gathered = rng.normal(size=(3, 40)).astype(np.float32); outs = np.zeros(32, np.float32)
     assert Lb.gccb_sum_ranks(ptr(gathered), 3, 40, 32, ptr(outs), None) == 0
     assert np.allclose(outs, gathered[:, :32].sum(0), rtol=1e-6)
+
+
+@pytest.mark.parametrize("B,d,K", [(37, 32, 300), (5, 64, 129), (33, 128, 64), (9, 256, 200)])
+def test_fused_infonce_tiled_kernel_ragged_shapes(B, d, K):
+    """The tiled InfoNCE kernel (d in {32, 64, 128, 256}: 32 query rows x 128 / 64 keys per CTA) with
+    row counts and queue sizes that are not multiples of its tiles, against memory_moco.py:26-53 +
+    criterions.py:12-17 (oracle)."""
+    Lb = lib()
+    rng = np.random.default_rng(B * 1000 + d)
+    T = 0.07
+    q = rng.normal(size=(B, d)).astype(np.float32); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    k = rng.normal(size=(B, d)).astype(np.float32); k /= np.linalg.norm(k, axis=1, keepdims=True)
+    mem = rng.uniform(-1, 1, (K, d)).astype(np.float32); mem /= np.linalg.norm(mem, axis=1, keepdims=True)
+    tq = torch.from_numpy(q).double().requires_grad_(True)
+    out_o = om.moco_logits(tq, torch.from_numpy(k).double(), torch.from_numpy(mem).double(), T)
+    loss_o = om.nce_softmax_loss(out_o)
+    (dq_o,) = torch.autograd.grad(loss_o, tq)
+    stats = np.zeros(2, np.float32); dq = np.zeros_like(q)
+    ws = np.zeros(Lb.gccb_infonce_workspace(B, d, K), np.uint8)
+    rc = Lb.gccb_infonce_fused(ptr(q), ptr(k), ptr(mem), B, d, K, T, ptr(stats), ptr(dq), ptr(ws), ws.nbytes, None)
+    assert rc == 0, Lb.gccb_last_error()
+    assert np.isclose(stats[0], float(loss_o), rtol=2e-5), (stats[0], float(loss_o))
+    assert np.isclose(stats[1], out_o[:, 0].mean().item(), rtol=2e-5)
+    assert np.allclose(dq, dq_o.numpy(), rtol=2e-4, atol=2e-6), np.abs(dq - dq_o.numpy()).max()
