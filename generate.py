@@ -20,71 +20,80 @@ from gcc_b200.datasets import synthetic
 from gcc_b200.datasets.graph_dataset import NodeClassificationDataset
 from gcc_b200.models import GraphEncoder
 
+# checkpoint["opt"] attribute -> GraphEncoder keyword (train.py:601-620 builds the model from these)
+ENCODER_KWARGS = {
+    "positional_embedding_size": "positional_embedding_size", "max_node_freq": "max_node_freq",
+    "max_edge_freq": "max_edge_freq", "max_degree": "max_degree",
+    "freq_embedding_size": "freq_embedding_size", "degree_embedding_size": "degree_embedding_size",
+    "output_dim": "hidden_size", "node_hidden_dim": "hidden_size", "edge_hidden_dim": "hidden_size",
+    "num_layers": "num_layer", "num_step_set2set": "set2set_iter",
+    "num_layer_set2set": "set2set_lstm_layer", "gnn_model": "model", "norm": "norm",
+}
+
 
 def test_moco(train_loader, model, opt):
-    """generate.py:33-53."""
+    """Embedding of every item: mean of the two views' eval-mode features (generate.py:33-53)."""
     model.eval()
-    emb_list = []
-    for graph_q, graph_k, count in train_loader:
-        bsz = graph_q.batch_size
-        with torch.no_grad():
-            feat_q = model(graph_q)
-            feat_k = model(graph_k)
-        assert feat_q.shape == (bsz, opt.hidden_size)
-        emb_list.append(((feat_q + feat_k) / 2)[:count].detach().cpu())
-    return torch.cat(emb_list)
+    chunks = []
+    with torch.no_grad():
+        for view_q, view_k, valid in train_loader:
+            pair = torch.stack([model(view_q), model(view_k)])
+            if pair.shape[1:] != (view_q.batch_size, opt.hidden_size):
+                raise RuntimeError("encoder returned %s" % (tuple(pair.shape),))
+            chunks.append(pair.mean(0)[:valid].cpu())        # the last chunk is padded: keep the valid pairs
+    return torch.cat(chunks)
 
 
-def build_graph(name, nodes, edges):
+def resolve_graph(name, nodes, edges):
+    """`--dataset`: an .npz path is passed through; synthetic-chunglu / synthetic-er are generated."""
     if name.endswith(".npz"):
         return name
-    kind = name.split("-", 1)[1] if "-" in name else "er"
-    if kind == "chunglu":
+    if name.endswith("chunglu"):
         return synthetic.chung_lu(nodes, edges, 0.5, seed=0)
     return synthetic.erdos_renyi(nodes, edges, seed=0)
 
 
 def main(args_test):
-    if not os.path.isfile(args_test.load_path):
-        raise SystemExit("=> no checkpoint found at '{}'".format(args_test.load_path))
-    print("=> loading checkpoint '{}'".format(args_test.load_path))
-    checkpoint = torch.load(args_test.load_path, map_location="cpu", weights_only=False)
-    print("=> loaded successfully '{}' (epoch {})".format(args_test.load_path, checkpoint["epoch"]))
-    args = checkpoint["opt"]
+    path = args_test.load_path
+    if not os.path.isfile(path):
+        raise SystemExit("=> no checkpoint found at '{}'".format(path))
     if not torch.cuda.is_available():
         raise SystemExit("generate.py needs a CUDA device (sm_100a); there is no CPU path")
-    torch.cuda.set_device(args_test.gpu or 0)
-    args.device = torch.device("cuda", args_test.gpu or 0)
-    train_dataset = NodeClassificationDataset(
-        dataset=build_graph(args_test.dataset, args_test.graph_nodes, args_test.graph_edges),
-        rw_hops=args.rw_hops, subgraph_size=args.subgraph_size, restart_prob=args.restart_prob,
-        positional_embedding_size=args.positional_embedding_size, device=args.device,
-        seed=getattr(args, "seed", 0), batch_size=args_test.batch_size)
-    model = GraphEncoder(
-        positional_embedding_size=args.positional_embedding_size, max_node_freq=args.max_node_freq,
-        max_edge_freq=args.max_edge_freq, max_degree=args.max_degree,
-        freq_embedding_size=args.freq_embedding_size, degree_embedding_size=args.degree_embedding_size,
-        output_dim=args.hidden_size, node_hidden_dim=args.hidden_size, edge_hidden_dim=args.hidden_size,
-        num_layers=args.num_layer, num_step_set2set=args.set2set_iter,
-        num_layer_set2set=args.set2set_lstm_layer, gnn_model=args.model, norm=args.norm,
-        degree_input=True)
-    model.load_state_dict(checkpoint["model"])
-    model = model.to(args.device)
-    del checkpoint
-    emb = test_moco(train_dataset, model, args)
-    out = os.path.join(getattr(args, "model_folder", "."), os.path.basename(args_test.dataset).replace(".npz", ""))
+    print("=> loading checkpoint '{}'".format(path))
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    print("=> loaded successfully '{}' (epoch {})".format(path, ckpt["epoch"]))
+    opt = ckpt["opt"]
+    gpu = args_test.gpu or 0
+    torch.cuda.set_device(gpu)
+    opt.device = torch.device("cuda", gpu)
+
+    encoder = GraphEncoder(degree_input=True, **{kw: getattr(opt, attr) for kw, attr in ENCODER_KWARGS.items()})
+    encoder.load_state_dict(ckpt["model"])
+    encoder = encoder.to(opt.device)
+    del ckpt
+
+    nodes = NodeClassificationDataset(
+        dataset=resolve_graph(args_test.dataset, args_test.graph_nodes, args_test.graph_edges),
+        rw_hops=opt.rw_hops, subgraph_size=opt.subgraph_size, restart_prob=opt.restart_prob,
+        positional_embedding_size=opt.positional_embedding_size, device=opt.device,
+        seed=getattr(opt, "seed", 0), batch_size=args_test.batch_size)
+    emb = test_moco(nodes, encoder, opt)
+
+    stem = os.path.basename(args_test.dataset)
+    stem = stem[:-4] if stem.endswith(".npz") else stem
+    out = os.path.join(getattr(opt, "model_folder", "."), stem)
     np.save(out, emb.numpy())
     print("saved {} embeddings of dim {} to {}.npy".format(emb.shape[0], emb.shape[1], out))
     return emb
 
 
 if __name__ == "__main__":
-    parser = argparse.ArgumentParser("argument for generation")
-    parser.add_argument("--load-path", type=str, required=True, help="path to load model")
-    parser.add_argument("--dataset", type=str, default="synthetic-er",
-                        help=".npz CSR file (indptr, indices) or synthetic-er / synthetic-chunglu")
-    parser.add_argument("--graph-nodes", type=int, default=2000)
-    parser.add_argument("--graph-edges", type=int, default=10000)
-    parser.add_argument("--batch-size", type=int, default=256)
-    parser.add_argument("--gpu", default=None, type=int, help="GPU id to use.")
-    main(parser.parse_args())
+    ap = argparse.ArgumentParser("inference export: node embeddings from a pretraining checkpoint")
+    ap.add_argument("--load-path", type=str, required=True, help="path to load model")
+    ap.add_argument("--dataset", type=str, default="synthetic-er",
+                    help=".npz CSR file (indptr, indices) or synthetic-er / synthetic-chunglu")
+    ap.add_argument("--graph-nodes", type=int, default=2000, help="size of a synthetic target graph")
+    ap.add_argument("--graph-edges", type=int, default=10000)
+    ap.add_argument("--batch-size", type=int, default=256, help="nodes encoded per launch group")
+    ap.add_argument("--gpu", default=None, type=int, help="GPU id to use.")
+    main(ap.parse_args())
