@@ -36,9 +36,17 @@ namespace gccb {
 #define GCCB_EIG_MAXSWEEP 14
 #define GCCB_EIG_TOL 1.0e-6f
 #define GCCB_CF_B 48               // ChFSI block size (>= pos_dim 32 + guard vectors)
-#define GCCB_CF_DEG0 4              // Chebyshev degree of the first outer iteration (random block:
-                                   // keep it numerically full rank for fp32 Gram-Schmidt)
-#define GCCB_CF_DEG 8              // degree of the later iterations (gain T_8(3) ~ 7e5 < 1/eps_fp32)
+#ifndef GCCB_CF_DEG0
+#define GCCB_CF_DEG0 8              // Chebyshev degree of the first outer iteration (random block: gain T_8(3) ~ 7e5
+#endif                             // keeps it numerically full rank for fp32 Gram-Schmidt; 12 does not)
+#ifndef GCCB_CF_DEG
+#define GCCB_CF_DEG 16             // degree of the later iterations: the block is Ritz-rotated by then, so each column is
+#endif                             // one (scaled) direction plus noise and Gram-Schmidt in descending order stays stable;
+                                   // measured on C2 ego-nets (fp32 model): 2.0 outer iterations instead of 3.0 at (4, 8),
+                                   // hub ego-nets 2.7 instead of 3.9; (12, 24) breaks down
+#ifndef GCCB_CF_SWEEPS0
+#define GCCB_CF_SWEEPS0 1          // Jacobi sweeps of the first Ritz solve (it only conditions the random block)
+#endif
 #define GCCB_CF_NSM_A 96            // shared-memory block classes: n <= 96 (3 CTAs/SM) and
 #define GCCB_CF_NSM 160            //   n <= 160 (2 CTAs/SM),
 #define GCCB_CF_NSM_C 384          //   n <= 384 (one GCCB_BIG_NT-thread CTA; 150 KB + 30 KB static leave room
@@ -191,81 +199,93 @@ __device__ __forceinline__ int jacobi_onesided(float* G, float* nrm, int n, int 
 // current outer residual).
 template <int NT>
 __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64]*/, int* pq /*[32]*/, int LD,
-                                              float tol) {
+                                              float tol, int max_sweeps) {
   constexpr int M = GCCB_CF_B, HALF = M / 2;
   const int tid = threadIdx.x;
+  // rl[0..nr): pairs that rotate this round, rl[HALF-1], rl[HALF-2], ...: the others; rl[HALF] = nr.
+  // Two copies alternate between rounds, so an idle round (nr == 0) costs ONE barrier: the next
+  // round's writer never touches the copy a slow reader may still be looking at.
+  __shared__ int rl2[2][HALF + 1];
   for (int idx = tid; idx < M * M; idx += NT) {
     const int j = idx / M, i = idx - j * M;
     V[j * LD + i] = i == j ? 1.0f : 0.f;
   }
   __syncthreads();
   int sweep = 0;
-  for (; sweep < GCCB_EIG_MAXSWEEP; ++sweep) {
+  for (; sweep < max_sweeps; ++sweep) {
     int rotated = 0;
     for (int r = 0; r < M - 1; ++r) {
-      int rot_round = 0;
-      if (tid < HALF) {
-        int p, q;
-        if (tid == 0) { p = M - 1; q = r; }
-        else { p = (r + tid) % (M - 1); q = (r + M - 1 - tid) % (M - 1); }
-        if (p > q) { int t = p; p = q; q = t; }
-        float c = 1.0f, s = 0.f;
-        const float app = A[p * LD + p], aqq = A[q * LD + q], apq = A[q * LD + p];
-        // (diagonal of G = H + 2I lies in [1, 3]: the arithmetic mean is as good a scale as the geometric one)
-        if (fabsf(apq) > tol * 0.5f * (fabsf(app) + fabsf(aqq))) {
-          // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = d / (2 apq), without dividing by apq;
-          // fast division / reciprocal square root: this dependent chain is on the critical path of
-          // every round, and a 2-ulp rotation error is far below the Ritz tolerance
-          const float d = aqq - app;
-          const float two_apq = 2.0f * apq;
-          const float den = fabsf(d) + __fsqrt_rn(fmaf(d, d, two_apq * two_apq));
-          const float t = __fdividef(d >= 0.f ? two_apq : -two_apq, den);
-          c = rsqrtf(fmaf(t, t, 1.0f));
-          s = c * t;
-          rotated = 1;
-          rot_round = 1;
+      int* rl = rl2[r & 1];
+      if (tid < 32) {                                      // warp 0: one lane per pair
+        bool rot = false;
+        if (tid < HALF) {
+          int p, q;
+          if (tid == 0) { p = M - 1; q = r; }
+          else { p = (r + tid) % (M - 1); q = (r + M - 1 - tid) % (M - 1); }
+          if (p > q) { int t = p; p = q; q = t; }
+          float c = 1.0f, s = 0.f;
+          const float app = A[p * LD + p], aqq = A[q * LD + q], apq = A[q * LD + p];
+          // (diagonal of G = H + 2I lies in [1, 3]: the arithmetic mean is as good a scale as the geometric one)
+          if (fabsf(apq) > tol * 0.5f * (fabsf(app) + fabsf(aqq))) {
+            // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = d / (2 apq), without dividing by apq;
+            // fast division / reciprocal square root: this dependent chain is on the critical path of
+            // every round, and a 2-ulp rotation error is far below the Ritz tolerance
+            const float d = aqq - app;
+            const float two_apq = 2.0f * apq;
+            const float den = fabsf(d) + __fsqrt_rn(fmaf(d, d, two_apq * two_apq));
+            const float t = __fdividef(d >= 0.f ? two_apq : -two_apq, den);
+            c = rsqrtf(fmaf(t, t, 1.0f));
+            s = c * t;
+            rot = true;
+          }
+          cs[2 * tid] = c; cs[2 * tid + 1] = s; pq[tid] = p | (q << 16);
         }
-        cs[2 * tid] = c; cs[2 * tid + 1] = s; pq[tid] = p | (q << 16);
+        // compact the rotating pairs: most rounds of a nearly diagonal problem rotate only a few
+        const unsigned mask = __ballot_sync(0xffffffffu, rot);
+        if (tid < HALF) {
+          const unsigned below = mask & ((1u << tid) - 1u);
+          if (rot) rl[__popc(below)] = tid;
+          else rl[HALF - 1 - (tid - __popc(below))] = tid;
+        }
+        if (tid == 0) rl[HALF] = __popc(mask);
       }
-      if (!__syncthreads_or(rot_round)) continue;
-      // A <- J^T A J on 2x2 blocks: rows (p1,q1) of pair a, columns (p2,q2) of pair b
-      constexpr int NB = HALF * HALF, ITB = (NB + NT - 1) / NT;
-#pragma unroll
-      for (int t = 0; t < ITB; ++t) {
-        const int item = tid + t * NT;
-        if (item < NB) {
-          const int pa = item / HALF, pb = item - pa * HALF;
-          const int ca = pq[pa], cb = pq[pb];
-          const int p1 = ca & 0xffff, q1 = ca >> 16, p2 = cb & 0xffff, q2 = cb >> 16;
-          const float c1 = cs[2 * pa], s1 = cs[2 * pa + 1], c2 = cs[2 * pb], s2 = cs[2 * pb + 1];
-          float a = A[p2 * LD + p1], b = A[q2 * LD + p1], c_ = A[p2 * LD + q1], d = A[q2 * LD + q1];
-          // columns: [x y] -> [c2 x - s2 y, s2 x + c2 y]
-          float a2 = c2 * a - s2 * b, b2 = s2 * a + c2 * b, c3 = c2 * c_ - s2 * d, d2 = s2 * c_ + c2 * d;
-          // rows: [x; y] -> [c1 x - s1 y; s1 x + c1 y]
-          A[p2 * LD + p1] = c1 * a2 - s1 * c3;
-          A[q2 * LD + p1] = c1 * b2 - s1 * d2;
-          A[p2 * LD + q1] = s1 * a2 + c1 * c3;
-          A[q2 * LD + q1] = s1 * b2 + c1 * d2;
-        }
+      __syncthreads();
+      const int nr = rl[HALF];
+      if (nr == 0) continue;
+      rotated = 1;
+      // A <- J^T A J on 2x2 blocks (rows of pair a, columns of pair b); only blocks with a rotating
+      // pair on either side change: (a in R, b any) and (a not in R, b in R)
+      const int n_first = nr * HALF, n_items = nr * (M - nr);
+      for (int item = tid; item < n_items; item += NT) {
+        int pa, pb;
+        if (item < n_first) { const int ia = item / HALF; pa = rl[ia]; pb = item - ia * HALF; }
+        else { const int it2 = item - n_first; const int ia = it2 / nr; pa = rl[HALF - 1 - ia]; pb = rl[it2 - ia * nr]; }
+        const int ca = pq[pa], cb = pq[pb];
+        const int p1 = ca & 0xffff, q1 = ca >> 16, p2 = cb & 0xffff, q2 = cb >> 16;
+        const float c1 = cs[2 * pa], s1 = cs[2 * pa + 1], c2 = cs[2 * pb], s2 = cs[2 * pb + 1];
+        float a = A[p2 * LD + p1], b = A[q2 * LD + p1], c_ = A[p2 * LD + q1], d = A[q2 * LD + q1];
+        // columns: [x y] -> [c2 x - s2 y, s2 x + c2 y]
+        float a2 = c2 * a - s2 * b, b2 = s2 * a + c2 * b, c3 = c2 * c_ - s2 * d, d2 = s2 * c_ + c2 * d;
+        // rows: [x; y] -> [c1 x - s1 y; s1 x + c1 y]
+        A[p2 * LD + p1] = c1 * a2 - s1 * c3;
+        A[q2 * LD + p1] = c1 * b2 - s1 * d2;
+        A[p2 * LD + q1] = s1 * a2 + c1 * c3;
+        A[q2 * LD + q1] = s1 * b2 + c1 * d2;
       }
-      // V <- V J
-      constexpr int NV = HALF * M, ITV = (NV + NT - 1) / NT;
-#pragma unroll
-      for (int t = 0; t < ITV; ++t) {
-        const int item = tid + t * NT;
-        if (item < NV) {
-          const int pr = item / M, i = item - pr * M;
-          const int code = pq[pr];
-          const int p = code & 0xffff, q = code >> 16;
-          const float c = cs[2 * pr], s = cs[2 * pr + 1];
-          const float x = V[p * LD + i], y = V[q * LD + i];
-          V[p * LD + i] = c * x - s * y;
-          V[q * LD + i] = s * x + c * y;
-        }
+      // V <- V J: only the columns of rotating pairs
+      for (int item = tid; item < nr * M; item += NT) {
+        const int ir = item / M, i = item - ir * M;
+        const int pr = rl[ir];
+        const int code = pq[pr];
+        const int p = code & 0xffff, q = code >> 16;
+        const float c = cs[2 * pr], s = cs[2 * pr + 1];
+        const float x = V[p * LD + i], y = V[q * LD + i];
+        V[p * LD + i] = c * x - s * y;
+        V[q * LD + i] = s * x + c * y;
       }
       __syncthreads();
     }
-    if (!__syncthreads_or(rotated)) break;
+    if (!rotated) break;
   }
   return sweep;
 }
@@ -702,7 +722,7 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
     }
     GCCB_TICK(2);
     // ---- 48 x 48 Ritz problem: two-sided Jacobi, eigenvectors in Ws (tiles are dead now) ----------
-    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f);   // the first block is random: no need for more
+    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0 : GCCB_EIG_MAXSWEEP);   // the first block is random: one sweep conditions it
     GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
@@ -1167,7 +1187,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       __syncthreads();
     }
     GCCB_TICK(2);
-    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f);   // redundant per CTA, bit-identical
+    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0 : GCCB_EIG_MAXSWEEP);   // redundant per CTA, bit-identical
     GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
