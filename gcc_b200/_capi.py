@@ -66,12 +66,15 @@ _PROTOS = {
     "gccb_infonce_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "gccb_infonce_fused": (C.c_int, [p, p, p, C.c_int32, C.c_int32, C.c_int32, C.c_float, p, p,
                                      p, C.c_size_t, p]),
-    "gccb_moco_enqueue": (C.c_int, [p, p, C.c_int32, C.c_int32, C.c_int32, p, p]),
+    "gccb_moco_enqueue": (C.c_int, [p, p, C.c_int32, C.c_int32, C.c_int32, p, C.c_int32, C.c_int64, p, C.c_int32, p]),
     "gccb_e2e_nce": (C.c_int, [p, p, C.c_int32, C.c_int32, C.c_float, p, p, p, p, C.c_size_t, p]),
     "gccb_clip_adam_ema": (C.c_int, [p, p, p, p, p, C.c_int64, C.c_int64, p, C.c_float,
                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                     C.c_float, p, p, p]),
-    "gccb_sum_ranks": (C.c_int, [p, C.c_int32, C.c_int64, C.c_int64, p, p]),
+                                     C.c_float, p, p, p, C.c_int32, p]),
+    "gccb_sum_ranks": (C.c_int, [p, C.c_int32, C.c_int64, C.c_int64, p, C.c_int64, p, p]),
+    "gccb_tc_gemm_bf16": (C.c_int, [p, p, C.c_int32, C.c_int32, C.c_int32, p, p, C.c_float, p, p, C.c_int32, p,
+                                    C.c_int32, p, p]),
+    "gccb_cast_bf16": (C.c_int, [p, C.c_int32, C.c_int32, C.c_int32, p, C.c_int32, C.c_int32, C.c_int32, p, p]),
     "gccb_partition_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "gccb_partition_sm_count": (C.c_int32, [p, C.c_int32]),
     "gccb_partition_stream": (C.c_int, [p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),

@@ -81,7 +81,7 @@ class MemoryMoCo(nn.Module):
             idx = self._sync_index()
             kk = k.contiguous().float()
             _lib.check(lib.gccb_moco_enqueue(_lib.dptr(self.memory), _lib.dptr(kk), batchSize,
-                                             self.inputSize, self.queueSize, _lib.dptr(idx),
+                                             self.inputSize, self.queueSize, _lib.dptr(idx), 1, 0, None, 0,
                                              _lib.stream_ptr()), "gccb_moco_enqueue")
             self.index = (self.index + batchSize) % self.queueSize
         return out

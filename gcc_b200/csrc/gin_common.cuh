@@ -116,7 +116,7 @@ __device__ __forceinline__ void bn_prepare(const double* __restrict__ sums, int 
       mean = sums[c] / n;
       var = sums[H + c] / n - mean * mean;
       if (var < 0.0) var = 0.0;
-      if (update_running && running && blockIdx.x == 0) {
+      if (update_running && running && blockIdx.x == 0 && N > 0) {   // an empty (overflowed) view leaves them alone
         double unb = N > 1 ? var * n / (n - 1.0) : var;
         running[c] = (float)((1.0 - momentum) * running[c] + momentum * mean);
         running[H + c] = (float)((1.0 - momentum) * running[H + c] + momentum * unb);

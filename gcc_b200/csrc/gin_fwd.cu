@@ -295,7 +295,13 @@ gin_pool_predict_kernel(GinDims d, const int32_t* __restrict__ node_off_v, int B
   __shared__ float score[H];
   __shared__ float red_s[8];
   const int g = blockIdx.x, tid = threadIdx.x;
-  if (node_off_v[B] < 0) return;
+  if (node_off_v[B] < 0) {                               // view published empty: defined (zero) outputs, the
+    for (int o = tid; o < H; o += 256) {                 // optimiser / enqueue skip the step (gccb200.h)
+      score_out[(size_t)g * H + o] = 0.f;
+      feat_out[(size_t)g * H + o] = 0.f;
+    }
+    return;
+  }
   for (int o = tid; o < H; o += 256) score[o] = 0.f;
   __syncthreads();
   for (int l = 0; l < d.L; ++l) {
@@ -478,11 +484,12 @@ namespace gccb {
 // fills the device tables (layer-output pointers, head offsets) with a tiny kernel so that no
 // host->device copy (and no pinned staging) is needed and the call stays graph-capturable
 __global__ void gin_fill_tables_kernel(char* acts, ActsLayout al, gccb_gin_layout_t lay, int L,
-                                       const float** hptrs, int64_t* offs, int64_t* nbt) {
+                                       const float** hptrs, int64_t* offs, int64_t* nbt,
+                                       const int32_t* n_valid) {
   int t = threadIdx.x;
   if (t < L - 1) hptrs[t] = (const float*)(acts + al.h[t]);
   if (t < 8) { offs[t] = lay.wp[t]; offs[8 + t] = lay.bp[t]; }
-  if (nbt && t < 3 * (L - 1)) nbt[t] += 1;      // BatchNorm.num_batches_tracked (train mode)
+  if (nbt && *n_valid >= 0 && t < 3 * (L - 1)) nbt[t] += 1;      // BatchNorm.num_batches_tracked (train mode)
 }
 }  // namespace gccb
 
@@ -514,7 +521,8 @@ extern "C" int gccb_gin_forward(const gccb_gin_cfg_t* cfg, const gccb_batch_t* b
   a.d_hptrs = (const float**)tail;
   a.d_offs = (int64_t*)(tail + 8 * sizeof(void*));
   GCCB_LAUNCH(gin_fill_tables_kernel, 1, 32, 0, stream, (char*)acts, a.al, a.lay, a.d.L, a.d_hptrs, a.d_offs,
-              bn_train ? num_batches_tracked : (int64_t*)nullptr);
+              bn_train ? num_batches_tracked : (int64_t*)nullptr,
+              (const int32_t*)(batch->node_off + (size_t)view * (batch->batch + 1) + batch->batch));
   switch (a.d.H) {
     case 32: return run_forward<32>(a);
     case 64: return run_forward<64>(a);

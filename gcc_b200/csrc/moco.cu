@@ -306,17 +306,24 @@ infonce_merge_kernel(const float* __restrict__ q, const float* __restrict__ k,
   }
 }
 
+// `parts` blocks of B keys each, part r at k + r * part_stride (one rank's keys inside the gathered
+// exchange buffer): all ranks' keys go in with one launch, in rank order (identical queues).
 __global__ void moco_enqueue_kernel(float* __restrict__ mem, const float* __restrict__ k, int B, int d,
-                                    int K, const int64_t* __restrict__ index_dev) {
+                                    int K, const int64_t* __restrict__ index_dev, int parts, int64_t part_stride,
+                                    const int32_t* __restrict__ skip_word, int32_t skip_mask) {
+  if (skip_word && (*skip_word & skip_mask)) return;   // step skipped (empty view): the queue keeps its keys
   const int64_t base = *index_dev;
-  const int total = B * d;
+  const int per = B * d, total = parts * per;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    int i = idx / d, c = idx - i * d;
-    int64_t row = (base + i) % K;                       // torch.fmod(arange(B) + index, K)
-    mem[(size_t)row * d + c] = k[idx];
+    const int r = idx / per, w = idx - r * per;
+    const int i = w / d, c = w - i * d;
+    int64_t row = (base + (int64_t)r * B + i) % K;      // torch.fmod(arange(B) + index, K)
+    mem[(size_t)row * d + c] = k[(size_t)r * part_stride + w];
   }
 }
-__global__ void moco_advance_kernel(int64_t* index_dev, int B, int K) {
+__global__ void moco_advance_kernel(int64_t* index_dev, int B, int K, const int32_t* __restrict__ skip_word,
+                                    int32_t skip_mask) {
+  if (skip_word && (*skip_word & skip_mask)) return;
   if (threadIdx.x == 0 && blockIdx.x == 0) *index_dev = (*index_dev + B) % K;
 }
 
@@ -475,14 +482,17 @@ extern "C" int gccb_infonce_fused(const float* q, const float* k, const float* m
 }
 
 extern "C" int gccb_moco_enqueue(float* memory, const float* k, int32_t B, int32_t d, int32_t K,
-                                 int64_t* index_dev, gccb_stream_t stream) {
-  if (!memory || !k || !index_dev || B <= 0 || d <= 0 || K <= 0) {
+                                 int64_t* index_dev, int32_t parts, int64_t part_stride,
+                                 const int32_t* skip_word, int32_t skip_mask, gccb_stream_t stream) {
+  if (!memory || !k || !index_dev || B <= 0 || d <= 0 || K <= 0 || parts < 1 || (parts > 1 && part_stride < (int64_t)B * d)) {
     set_last_error("gccb_moco_enqueue: bad argument");
     return GCCB_ERR_BADARG;
   }
-  GCCB_LAUNCH(moco_enqueue_kernel, (B * d + 255) / 256, 256, 0, stream, memory, k, B, d, K,
-              (const int64_t*)index_dev);
-  GCCB_LAUNCH(moco_advance_kernel, 1, 32, 0, stream, index_dev, B, K);
+  int blocks = (parts * B * d + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  GCCB_LAUNCH(moco_enqueue_kernel, blocks, 256, 0, stream, memory, k, B, d, K, (const int64_t*)index_dev, parts,
+              part_stride, skip_word, skip_mask);
+  GCCB_LAUNCH(moco_advance_kernel, 1, 32, 0, stream, index_dev, parts * B, K, skip_word, skip_mask);
   return check_launch("gccb_moco_enqueue");
 }
 

@@ -34,7 +34,10 @@ adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
                 float* __restrict__ v, float* __restrict__ p_ema, int64_t n_live, int64_t n_all,
                 const float* __restrict__ hyper, float beta1, float beta2, float eps, float wd,
                 float clip_norm, float alpha, float grad_scale, const double* __restrict__ sumsq,
-                float* __restrict__ grad_norm_out) {
+                float* __restrict__ grad_norm_out, const int32_t* __restrict__ skip_word, int32_t skip_mask) {
+  // a batch whose view was published empty (capacity overflow) must not move the weights: the whole
+  // update (Adam moments, parameters, momentum encoder) is a no-op for that step
+  if (skip_word && (*skip_word & skip_mask)) return;
   const float total = (float)sqrt(*sumsq);
   float coef = 1.0f;
   if (clip_norm > 0.f) {                                  // clip_grad_norm_: coef = max_norm/(norm+1e-6), clamped to 1
@@ -62,7 +65,12 @@ adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
 
 __global__ void __launch_bounds__(256)
 sum_ranks_kernel(const float* __restrict__ gathered, int world, int64_t stride, int64_t n,
-                 float* __restrict__ out) {
+                 float* __restrict__ out, int64_t flag_index, int32_t* __restrict__ any_flag_out) {
+  if (any_flag_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    int f = 0;
+    for (int r = 0; r < world; ++r) f |= gathered[(size_t)r * stride + flag_index] != 0.f;
+    *any_flag_out = f;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < world; ++r) s += gathered[(size_t)r * stride + i];   // fixed rank order
@@ -77,7 +85,8 @@ using namespace gccb;
 extern "C" int gccb_clip_adam_ema(float* p, float* g, float* m, float* v, float* p_ema, int64_t n_live,
                                   int64_t n_all, const float* hyper, float beta1, float beta2, float eps,
                                   float weight_decay, float clip_norm, float alpha, float grad_scale,
-                                  float* grad_norm_out, double* workspace, gccb_stream_t stream) {
+                                  float* grad_norm_out, double* workspace, const int32_t* skip_word,
+                                  int32_t skip_mask, gccb_stream_t stream) {
   if (!p || !g || !m || !v || !hyper || !workspace || n_live <= 0 || n_all < n_live) {
     set_last_error("gccb_clip_adam_ema: bad argument");
     return GCCB_ERR_BADARG;
@@ -90,18 +99,18 @@ extern "C" int gccb_clip_adam_ema(float* p, float* g, float* m, float* v, float*
   if (blocks2 > 1184) blocks2 = 1184;
   GCCB_LAUNCH(adam_ema_kernel, blocks2, 256, 0, stream, p, (const float*)g, m, v, p_ema, n_live, n_all, hyper,
               beta1, beta2, eps, weight_decay, clip_norm, alpha, grad_scale, (const double*)workspace,
-              grad_norm_out);
+              grad_norm_out, skip_word, skip_mask);
   return check_launch("gccb_clip_adam_ema");
 }
 
 extern "C" int gccb_sum_ranks(const float* gathered, int32_t world, int64_t stride, int64_t n, float* out,
-                              gccb_stream_t stream) {
+                              int64_t flag_index, int32_t* any_flag_out, gccb_stream_t stream) {
   if (!gathered || !out || world <= 0 || n <= 0 || stride < n) {
     set_last_error("gccb_sum_ranks: bad argument");
     return GCCB_ERR_BADARG;
   }
   int blocks = (int)((n + 255) / 256);
   if (blocks > 1184) blocks = 1184;
-  GCCB_LAUNCH(sum_ranks_kernel, blocks, 256, 0, stream, gathered, world, stride, n, out);
+  GCCB_LAUNCH(sum_ranks_kernel, blocks, 256, 0, stream, gathered, world, stride, n, out, flag_index, any_flag_out);
   return check_launch("gccb_sum_ranks");
 }

@@ -1,0 +1,509 @@
+// tc_gemm.cu -- the path's dense contraction on Blackwell tensor cores (tcgen05 + TMEM + TMA).
+//
+//   D[M x N] = alpha * A[M x K] . B[N x K]^T (+ bias[N])      A, B bf16 (K-major), fp32 accumulate
+//
+// Every GEMM-shaped product of the hot path at hidden >= 128 goes through this kernel:
+//   GIN MLP Linear1 / Linear2          (gcc/models/gin.py:107-116; z = x W^T + b, BatchNorm statistics
+//                                       of z fused into the epilogue -- gin.py:115 needs the column
+//                                       mean / variance over all N rows)
+//   their input gradients dX = dZ . W  (B operand = W^T kept as a second bf16 copy)
+//   weight gradients dW = dZ^T . X     (operands transposed once, split-K over the rows)
+//   MoCo logits q . queue^T            (gcc/contrastive/memory_moco.py:33-44) and dq = P . queue
+// Design (one CTA per SM, persistent over 128-row output tiles):
+//   warp 0    TMA producer: cp.async.bulk.tensor 2-D boxes (128 x 64 of A, BN x 64 of B, 128-byte
+//             swizzle) into a 4-stage shared-memory ring, completion on mbarriers;
+//   warp 1    allocates TMEM and issues tcgen05.mma.cta_group::1.kind::f16 (M 128, N = BN, K 16) from
+//             one elected lane; tcgen05.commit releases the ring slot / publishes the accumulator;
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / scale, fp32 and/or bf16
+//             stores, column sums and sums of squares (float64 atomics, like the SIMT kernels).
+//   Two accumulator stages in TMEM (2 x BN <= 512 columns): the epilogue of tile t overlaps the
+//   MMAs of tile t+1.
+// Shared-memory operand layout = the canonical K-major SWIZZLE_128B layout (8-row groups 1024 B apart),
+// which is exactly what a TMA box with CU_TENSOR_MAP_SWIZZLE_128B writes.
+#include "common.cuh"
+
+#ifndef GCCB_EMU
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace gccb {
+namespace tc {
+
+constexpr int BM = 128, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int EPI_THREADS = 128, THREADS = 64 + EPI_THREADS;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Spin on a phase parity.  A protocol bug would otherwise hang the GPU until the driver's watchdog:
+// after ~2 s of spinning the kernel traps (the launch then fails loudly instead).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint64_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1ull << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
+// [0,14), leading byte offset (unused for swizzled K-major) = 1 in [16,30), stride byte offset
+// (8-row group pitch, 1024 B) >> 4 in [32,46), version 1 in [46,48), layout type 2 = SWIZZLE_128B in [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1 << 4), a/b_format BF16 (1 << 7, 1 << 10), K-major both
+// (bits 15, 16 = 0), n_dim = N >> 3 at bit 17, m_dim = M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct GemmArgs {
+  int M_cap, N, K, ldo;
+  const int32_t* m_dev;       // optional: number of valid rows (device)
+  const float* bias;          // [N] or null
+  float alpha;
+  float* out_f32;             // [M_cap][ldo] (or [splits][M_cap][ldo] partials when splits > 1) or null
+  __nv_bfloat16* out_bf16;    // [M_cap][ldo] or null
+  double* colstats;           // [2][N] (sum, sum of squares of the stored values) or null
+  int splits;
+};
+
+template <int BN>
+struct Smem {
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_F = 128 * 33;                 // epilogue transpose buffer (floats)
+  static constexpr size_t TOTAL = 1024 + (size_t)STAGES * STAGE_BYTES + STAGE_F * 4 + 2 * 32 * 4 * 4 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  using S = Smem<BN>;
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = base;                                       // [STAGES][A | B]
+  float* stage_t = (float*)(base + (size_t)STAGES * S::STAGE_BYTES);   // [128][33]
+  float* colpart = stage_t + S::STAGE_F;                              // [2][4][32]
+  uint64_t* bars = (uint64_t*)(colpart + 2 * 4 * 32);
+  uint64_t* full = bars;                 // [STAGES]   TMA -> MMA
+  uint64_t* empty = bars + STAGES;       // [STAGES]   MMA -> TMA
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]        MMA -> epilogue
+  uint64_t* tempty = bars + 2 * STAGES + 2;   // [2]   epilogue -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = g.m_dev ? min(max(*g.m_dev, 0), g.M_cap) : g.M_cap;
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = g.N / BN;
+  const int kb_total = g.K / BK;
+  const int split = blockIdx.y;
+  const int kb_per = (kb_total + g.splits - 1) / g.splits;
+  const int kb0 = split * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+  const int nkb = max(kb1 - kb0, 0);
+  const int num_tiles = m_tiles * n_tiles;
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_THREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                       // TMEM allocation: one full warp; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      // ===== TMA producer ============================================================================
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char* sa = tiles + (size_t)stage * S::STAGE_BYTES;
+            mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+            tma_load_2d(sa, &map_a, kb * BK, mt * BM, &full[stage]);
+            tma_load_2d(sa + S::A_BYTES, &map_b, kb * BK, nt * BN, &full[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer (one elected lane) ===========================================================
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(tiles + (size_t)stage * S::STAGE_BYTES);
+            const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advancing 16 elements (32 B) along K inside the 128-byte swizzle atom = +32 B on the start address
+              umma_bf16(d_tmem, umma_desc(sa + k * UMMA_K * 2), umma_desc(sb + k * UMMA_K * 2), idesc,
+                        (uint32_t)((kb | k) != 0));
+            }
+            umma_commit(&empty[stage]);                    // ring slot free once these MMAs have read it
+            if (kb == nkb - 1) umma_commit(&tfull[acc]);   // accumulator complete
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    } else {
+      // ===== epilogue warps 2..5: TMEM lanes 32 * (warp % 4) .. +31 ====================================
+      const int ew = warp & 3;                              // TMEM lane group this warp may access
+      const int et = threadIdx.x - 64;                      // 0..127
+      const int row_in_tile = ew * 32 + lane;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      float* outf = g.out_f32 ? g.out_f32 + (size_t)split * g.M_cap * g.ldo : nullptr;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int row = mt * BM + row_in_tile;
+        const bool row_ok = row < M;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int col0 = nt * BN + c0;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]) * g.alpha;
+            if (g.bias) x += g.bias[col0 + j];
+            v[j] = row_ok ? x : 0.f;
+          }
+          if (row_ok) {
+            if (outf) {
+              float4* dst = reinterpret_cast<float4*>(outf + (size_t)row * g.ldo + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (g.out_bf16) {
+              uint4* dst = reinterpret_cast<uint4*>(g.out_bf16 + (size_t)row * g.ldo + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+                u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+                dst[j] = u;
+              }
+            }
+          }
+          if (g.colstats) {
+            // column sums over the 128 rows of the tile: transpose through shared memory (row pitch 33:
+            // conflict-free both ways), 4 row groups x 32 columns, then one float64 atomic per column
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stage_t[row_in_tile * 33 + j] = v[j];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int cc = et & 31, rq = et >> 5;
+            float s = 0.f, q = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const float x = stage_t[(rq * 32 + rr) * 33 + cc];
+              s += x;
+              q = fmaf(x, x, q);
+            }
+            colpart[(0 * 4 + rq) * 32 + cc] = s;
+            colpart[(1 * 4 + rq) * 32 + cc] = q;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < 64) {
+              const int which = et >> 5;
+              const float t = colpart[(which * 4 + 0) * 32 + cc] + colpart[(which * 4 + 1) * 32 + cc] +
+                              colpart[(which * 4 + 2) * 32 + cc] + colpart[(which * 4 + 3) * 32 + cc];
+              atomicAdd(&g.colstats[(size_t)which * g.N + col0 + cc], (double)t);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// out[r][c] = alpha * sum_s part[s][r][c] (+ bias[c]) ; optional bf16 copy.   grid-stride, float4
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_kernel(const float* __restrict__ part, int splits, int M_cap, int N, int ldo,
+                        const int32_t* __restrict__ m_dev, float alpha, const float* __restrict__ bias,
+                        float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  const int M = m_dev ? min(max(*m_dev, 0), M_cap) : M_cap;
+  const size_t total = (size_t)M * N;
+  const size_t stride = (size_t)M_cap * ldo;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / N), c = (int)(idx - (size_t)r * N);
+    const size_t o = (size_t)r * ldo + c;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += part[(size_t)sp * stride + o];     // fixed order: deterministic
+    s *= alpha;
+    if (bias) s += bias[c];
+    if (out_f32) out_f32[o] = s;
+    if (out_bf16) out_bf16[o] = __float2bfloat16_rn(s);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows][cols] -> boxes of [box_rows][64], 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_last_error("tc_gemm: cuTensorMapEncodeTiled is not available"); return GCCB_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("tc_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r); return GCCB_ERR_CUDA; }
+  return GCCB_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
+  auto k = tc_gemm_kernel<BN>;
+  const size_t smem = Smem<BN>::TOTAL;
+  gccb::ensure_dyn_smem(k, smem);
+  const int m_tiles = (g.M_cap + BM - 1) / BM, tiles = m_tiles * (g.N / BN);
+  int gx = sm_count() / g.splits;
+  if (gx < 1) gx = 1;
+  if (gx > tiles) gx = tiles;
+  dim3 grid(gx, g.splits);
+  ++gccb::g_launch_count;
+  k<<<grid, THREADS, smem, stream>>>(ma, mb, g);
+  return GCCB_OK;
+}
+
+// Internal entry used by the GIN / MoCo tensor-core paths and by gccb_tc_gemm_bf16.
+// splits > 1: `scratch` must hold splits * M_cap * ldo floats; the partial sums are reduced in a fixed order.
+int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32_t* m_dev, const float* bias,
+              float alpha, float* out_f32, void* out_bf16, int ldo, double* colstats, int splits, float* scratch,
+              cudaStream_t stream) {
+  if (!A || !B || M_cap <= 0 || N <= 0 || K <= 0 || (K % BK) || (N % 32) || ldo < N || (ldo % 8) || splits < 1 ||
+      (!out_f32 && !out_bf16)) {
+    set_last_error("tc_gemm: bad argument (need K %% 64 == 0, N %% 32 == 0, ldo %% 8 == 0)");
+    return GCCB_ERR_BADARG;
+  }
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
+  if (splits > K / BK) splits = K / BK;
+  {                                         // no empty split: every partial buffer is written
+    const int kb_total = K / BK, per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + per - 1) / per;
+  }
+  if (splits > 1 && (!scratch || colstats)) {
+    set_last_error("tc_gemm: split-K needs a scratch buffer and cannot fuse column statistics");
+    return GCCB_ERR_BADARG;
+  }
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, M_cap, K, BM);
+  if (rc) return rc;
+  rc = make_map(&mb, B, N, K, BN);
+  if (rc) return rc;
+  GemmArgs g;
+  g.M_cap = M_cap; g.N = N; g.K = K; g.ldo = ldo; g.m_dev = m_dev; g.splits = splits;
+  if (splits > 1) {
+    g.bias = nullptr; g.alpha = 1.0f; g.out_f32 = scratch; g.out_bf16 = nullptr; g.colstats = nullptr;
+  } else {
+    g.bias = bias; g.alpha = alpha; g.out_f32 = out_f32; g.out_bf16 = (__nv_bfloat16*)out_bf16; g.colstats = colstats;
+  }
+  switch (BN) {
+    case 256: launch<256>(ma, mb, g, stream); break;
+    case 128: launch<128>(ma, mb, g, stream); break;
+    case 64: launch<64>(ma, mb, g, stream); break;
+    default: launch<32>(ma, mb, g, stream); break;
+  }
+  if (splits > 1) {
+    const size_t total = (size_t)M_cap * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+    GCCB_LAUNCH(tc_splitk_reduce_kernel, blocks, 256, 0, stream, (const float*)scratch, splits, M_cap, N, ldo, m_dev,
+                alpha, bias, out_f32, (__nv_bfloat16*)out_bf16);
+  }
+  return check_launch("tc_gemm");
+}
+
+// fp32 -> bf16 (optionally transposed): dst[c][r] or dst[r][c], zero padded to [rows_pad][cols_pad]
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int lds, __nv_bfloat16* __restrict__ dst,
+                 int rows_pad, int cols_pad, int transpose, const int32_t* __restrict__ rows_dev) {
+  __shared__ float tile[32][33];
+  const int R = rows_dev ? min(max(*rows_dev, 0), rows) : rows;
+  if (!transpose) {
+    const size_t total = (size_t)rows_pad * cols_pad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+      const int r = (int)(idx / cols_pad), c = (int)(idx - (size_t)r * cols_pad);
+      dst[idx] = __float2bfloat16_rn(r < R && c < cols ? src[(size_t)r * lds + c] : 0.f);
+    }
+    return;
+  }
+  // dst is [cols_pad][rows_pad]: 32 x 32 tiles through shared memory (coalesced both ways)
+  const int tr = (rows_pad + 31) / 32, tcn = (cols_pad + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  for (int t = blockIdx.x; t < tr * tcn; t += gridDim.x) {
+    const int r0 = (t / tcn) * 32, c0 = (t % tcn) * 32;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, c = c0 + tx;
+      tile[i][tx] = (r < R && c < cols) ? src[(size_t)r * lds + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (c < cols_pad && r < rows_pad) dst[(size_t)c * rows_pad + r] = __float2bfloat16_rn(tile[tx][i]);
+    }
+  }
+}
+
+int cast_bf16(const float* src, int rows, int cols, int lds, void* dst, int rows_pad, int cols_pad, int transpose,
+              const int32_t* rows_dev, cudaStream_t stream) {
+  const size_t total = (size_t)rows_pad * cols_pad;
+  int blocks = (int)((total + 1023) / 1024);
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  if (blocks < 1) blocks = 1;
+  GCCB_LAUNCH(cast_bf16_kernel, blocks, 256, 0, stream, src, rows, cols, lds, (__nv_bfloat16*)dst, rows_pad, cols_pad,
+              transpose, rows_dev);
+  return check_launch("cast_bf16");
+}
+
+}  // namespace tc
+}  // namespace gccb
+
+using namespace gccb;
+
+extern "C" int gccb_tc_gemm_bf16(const void* A, const void* B, int32_t M_cap, int32_t N, int32_t K,
+                                 const int32_t* m_dev, const float* bias, float alpha, float* out_f32,
+                                 void* out_bf16, int32_t ldo, double* colstats, int32_t splits, float* scratch,
+                                 gccb_stream_t stream) {
+  return tc::gemm_bf16(A, B, M_cap, N, K, m_dev, bias, alpha, out_f32, out_bf16, ldo, colstats, splits, scratch,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int gccb_cast_bf16(const float* src, int32_t rows, int32_t cols, int32_t lds, void* dst, int32_t rows_pad,
+                              int32_t cols_pad, int32_t transpose, const int32_t* rows_dev, gccb_stream_t stream) {
+  if (!src || !dst || rows < 0 || cols <= 0 || lds < cols || rows_pad < rows || cols_pad < cols) {
+    set_last_error("gccb_cast_bf16: bad argument");
+    return GCCB_ERR_BADARG;
+  }
+  return tc::cast_bf16(src, rows, cols, lds, dst, rows_pad, cols_pad, transpose, rows_dev, (cudaStream_t)stream);
+}
+
+#else   // GCCB_EMU: the CPU emulator cannot run tcgen05 / TMA; the entry points report it
+extern "C" int gccb_tc_gemm_bf16(const void*, const void*, int32_t, int32_t, int32_t, const int32_t*, const float*,
+                                 float, float*, void*, int32_t, double*, int32_t, float*, gccb_stream_t) {
+  gccb::set_last_error("tc_gemm: tensor-core path is not available under the CPU emulator");
+  return GCCB_ERR_ARCH;
+}
+extern "C" int gccb_cast_bf16(const float*, int32_t, int32_t, int32_t, void*, int32_t, int32_t, int32_t,
+                              const int32_t*, gccb_stream_t) {
+  gccb::set_last_error("cast_bf16: not available under the CPU emulator");
+  return GCCB_ERR_ARCH;
+}
+#endif

@@ -18,7 +18,7 @@ import math
 
 import torch
 
-from . import _lib
+from . import _capi, _lib
 from .datasets.data_util import BatchedSubgraphs
 from .parallel import StepExchange, first_sample_id
 
@@ -39,7 +39,13 @@ class PretrainEngine:
         self.B, self.H, self.L = B, H, L
         f32 = dict(dtype=torch.float32, device=dev)
         n_live = model.n_live
-        self.grads = torch.zeros(n_live, **f32)
+        self.xch = None
+        if world_size > 1:
+            # data-parallel exchange: ONE all-gather per step of [keys | gradient | stats].  The
+            # key encoder, the backward and the loss kernels write straight into the send buffer: no packing
+            self.xch = StepExchange(B, H, n_live, world_size, dev, process_group)
+            self.payload = self.xch.payload
+        self.grads = self.xch.grads_send if self.xch else torch.zeros(n_live, **f32)
         self.adam_m = torch.zeros(n_live, **f32)
         self.adam_v = torch.zeros(n_live, **f32)
         self.adam_t = 0
@@ -47,10 +53,12 @@ class PretrainEngine:
         # ring of pinned slots: the host enqueues several steps ahead of the device, and an async H2D copy
         # reads its pinned source when it EXECUTES, so each step needs a slot of its own
         self.hyper_host = torch.zeros(256, 4, dtype=torch.float32).pin_memory()
-        self.stats = torch.zeros(4, **f32)            # loss, prob, grad_norm(pre-clip), unused
+        # loss, prob, grad_norm(pre-clip), overflow marker of this rank's batch (multi-GPU skip protocol)
+        self.stats = self.xch.stats_send if self.xch else torch.zeros(4, **f32)
         self.norm_ws = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.any_skip = torch.zeros(1, dtype=torch.int32, device=dev)
         self.feat_q = torch.zeros(B, H, **f32)
-        self.feat_k = torch.zeros(B, H, **f32)
+        self.feat_k = self.xch.keys_send if self.xch else torch.zeros(B, H, **f32)
         self.dq = torch.zeros(B, H, **f32)
         self.dk = torch.zeros(B, H, **f32)
         self.pooled = torch.zeros(max(L - 1, 1), B, H, **f32)
@@ -78,11 +86,8 @@ class PretrainEngine:
         self.index_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.index_dev.fill_(contrast.index)
         self.global_step = 0
-        if world_size > 1:
-            self.xch = StepExchange(B, H, n_live, world_size, dev, process_group)
-            self.payload = self.xch.payload
-            if moco and K % (world_size * B) != 0:
-                raise ValueError("queue size must be a multiple of world_size*batch (identical queues)")
+        if world_size > 1 and moco and K % (world_size * B) != 0:
+            raise ValueError("queue size must be a multiple of world_size*batch (identical queues)")
         self.launches_per_step = None
         # Loader run-ahead (the reference's DataLoader workers prepare later batches while the
         # model trains on batch t, train.py:577-586): sampler + eigensolver of batches t+1..t+S run
@@ -229,15 +234,20 @@ class PretrainEngine:
         if self.prefetch and not _presampled:
             self.consumed[self.global_step % self.depth].record()
         grads, scale = self.grads, 1.0
+        # a batch published empty (capacity overflow; the flag is raised for the host) must not train:
+        # Adam / EMA / enqueue skip the step on the device, the flags reach the host in read_stats()
+        OVERFLOW = _capi.FLAG_NODE_OVERFLOW | _capi.FLAG_EDGE_OVERFLOW
+        skip_word, skip_mask = _lib.dptr(buf.flags), OVERFLOW
         if self.world > 1:
             # the ONE collective of the step: keys + gradients + stats, then a fixed-rank-order sum
             n_live = model.n_live
-            self.xch.pack(self.feat_k, self.grads, self.stats)
+            self.stats[3:4].copy_((buf.flags & OVERFLOW).float())
             gathered = self.xch.all_gather()
             _lib.check(lib.gccb_sum_ranks(C.c_void_p(gathered.data_ptr() + self.xch.grad_offset_bytes()),
-                                          self.world, self.payload, n_live, _lib.dptr(self.grads), st),
-                       "gccb_sum_ranks")
+                                          self.world, self.payload, n_live, _lib.dptr(self.grads),
+                                          n_live + 3, _lib.dptr(self.any_skip), st), "gccb_sum_ranks")
             scale = 1.0 / self.world
+            skip_word, skip_mask = _lib.dptr(self.any_skip), -1     # every replica skips the same steps
         self._hyper(lr)
         _lib.check(lib.gccb_clip_adam_ema(_lib.dptr(model.flat_params), _lib.dptr(grads),
                                           _lib.dptr(self.adam_m), _lib.dptr(self.adam_v),
@@ -245,19 +255,16 @@ class PretrainEngine:
                                           model.n_live, model._n_all, _lib.dptr(self.hyper), self.betas[0],
                                           self.betas[1], self.eps, self.wd, self.clip,
                                           self.alpha if self.moco else -1.0, scale,
-                                          C.c_void_p(self.stats.data_ptr() + 8), _lib.dptr(self.norm_ws), st),
+                                          C.c_void_p(self.stats.data_ptr() + 8), _lib.dptr(self.norm_ws),
+                                          skip_word, skip_mask, st),
                    "gccb_clip_adam_ema")
         if self.moco:
-            if self.world > 1:
-                for r in range(self.world):     # rank order -> identical queues on every rank
-                    _lib.check(lib.gccb_moco_enqueue(_lib.dptr(self.contrast.memory),
-                                                     C.c_void_p(self.xch.gathered.data_ptr() + 4 * r * self.payload),
-                                                     B, H, self.K, _lib.dptr(self.index_dev), st),
-                               "gccb_moco_enqueue")
-            else:
-                _lib.check(lib.gccb_moco_enqueue(_lib.dptr(self.contrast.memory), _lib.dptr(self.feat_k),
-                                                 B, H, self.K, _lib.dptr(self.index_dev), st),
-                           "gccb_moco_enqueue")
+            # all ranks' keys in rank order with one launch -> identical queues on every rank
+            src = self.xch.gathered if self.world > 1 else self.feat_k
+            _lib.check(lib.gccb_moco_enqueue(_lib.dptr(self.contrast.memory), _lib.dptr(src), B, H, self.K,
+                                             _lib.dptr(self.index_dev), self.world,
+                                             self.payload if self.world > 1 else 0, skip_word, skip_mask, st),
+                       "gccb_moco_enqueue")
             self.contrast.index = (self.contrast.index + B * self.world) % self.K
         if self.timing_main is not None:
             tm[1].record()
@@ -268,7 +275,8 @@ class PretrainEngine:
         """Host sync: loss, prob (mean positive logit), pre-clip grad norm, batch sizes, flags."""
         buf = self.cur_buf
         torch.cuda.synchronize(self.dev)
-        buf.check_flags()
+        for b_ in (self.bufs if self.prefetch else [buf]):     # every buffer of the run-ahead ring, not only
+            b_.check_flags()                                   # the one the last step trained on
         s = self.stats.tolist()
         sizes = buf.node_off[:, self.B].tolist() + buf.edge_off[:, self.B].tolist()
         return dict(loss=s[0], prob=s[1], grad_norm=s[2], nodes_q=sizes[0], nodes_k=sizes[1],

@@ -24,12 +24,21 @@ class StepExchange:
         self.payload = batch * dim + n_live + 4
         self.send = torch.zeros(self.payload, dtype=torch.float32, device=device)
         self.gathered = torch.zeros(world_size, self.payload, dtype=torch.float32, device=device)
+        kd = batch * dim
+        # the producers write in place: views of the send buffer
+        self.keys_send = self.send[:kd].view(batch, dim)
+        self.grads_send = self.send[kd:kd + n_live]
+        self.stats_send = self.send[kd + n_live:]
 
     def pack(self, keys, grads, stats):
+        """Copy into the send buffer (only needed when the producers did not write the views above)."""
         kd = self.B * self.d
-        self.send[:kd].copy_(keys.reshape(-1))
-        self.send[kd:kd + self.n_live].copy_(grads)
-        self.send[kd + self.n_live:].copy_(stats)
+        if keys.data_ptr() != self.keys_send.data_ptr():
+            self.send[:kd].copy_(keys.reshape(-1))
+        if grads.data_ptr() != self.grads_send.data_ptr():
+            self.send[kd:kd + self.n_live].copy_(grads)
+        if stats.data_ptr() != self.stats_send.data_ptr():
+            self.send[kd + self.n_live:].copy_(stats)
 
     def all_gather(self):
         if self.send.is_cuda:

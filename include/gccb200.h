@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GCCB_VERSION 100 /* round 1 */
+#define GCCB_VERSION 200 /* round 2 */
 
 typedef void* gccb_stream_t; /* cudaStream_t */
 
@@ -189,9 +189,15 @@ int gccb_infonce_fused(const float* q, const float* k, const float* memory, int3
                        int32_t d, int32_t K, float T, float* stats, float* dq, void* workspace,
                        size_t workspace_bytes, gccb_stream_t stream);
 /* FIFO enqueue (memory_moco.py:55-61): memory[(index+i) % K] = k[i]; the write pointer is
- * a device int64 (*index_dev) advanced by B (mod K).                                    */
+ * a device int64 (*index_dev) advanced by parts*B (mod K).  parts > 1: `parts` blocks of B keys,
+ * block r at k + r*part_stride floats (every rank's keys inside the gathered exchange buffer, in
+ * rank order -> identical queues on all ranks).  skip_word (optional, device): the call is a no-op
+ * when (*skip_word & skip_mask) != 0 -- pass gccb_batch_t.flags with
+ * GCCB_FLAG_NODE_OVERFLOW|GCCB_FLAG_EDGE_OVERFLOW so that a batch published empty never reaches
+ * the queue.                                                                                      */
 int gccb_moco_enqueue(float* memory, const float* k, int32_t B, int32_t d, int32_t K,
-                      int64_t* index_dev, gccb_stream_t stream);
+                      int64_t* index_dev, int32_t parts, int64_t part_stride,
+                      const int32_t* skip_word, int32_t skip_mask, gccb_stream_t stream);
 /* E2E head (train.py:397-401, criterions.py:27-33): out = k q^T / T, CE vs arange;
  * returns loss, mean diagonal logit, dq and dk.                                          */
 int gccb_e2e_nce(const float* q, const float* k, int32_t B, int32_t d, float T, float* stats,
@@ -203,15 +209,40 @@ int gccb_e2e_nce(const float* q, const float* k, int32_t B, int32_t d, float T, 
  * on the first n_live floats, then moment_update (train.py:169-172,430-431) of p_ema over
  * n_all floats (alpha < 0 skips the EMA).  hyper (device, 4 floats): lr, 1-beta1^t,
  * sqrt(1-beta2^t), unused.  grad_norm_out: device float (pre-clip total norm).
- * grad_scale multiplies the gradient first (1/world for data-parallel averaging).        */
+ * grad_scale multiplies the gradient first (1/world for data-parallel averaging).
+ * skip_word / skip_mask: as for gccb_moco_enqueue -- the whole update (moments, weights, momentum
+ * encoder) is a no-op for a step whose batch was published empty.                         */
 int gccb_clip_adam_ema(float* p, float* g, float* m, float* v, float* p_ema, int64_t n_live,
                        int64_t n_all, const float* hyper, float beta1, float beta2, float eps,
                        float weight_decay, float clip_norm, float alpha, float grad_scale,
                        float* grad_norm_out, double* workspace /* 1 double */,
-                       gccb_stream_t stream);
-/* deterministic rank-ordered sum of `world` gathered gradient buffers: out = sum_r in[r]  */
+                       const int32_t* skip_word, int32_t skip_mask, gccb_stream_t stream);
+/* deterministic rank-ordered sum of `world` gathered gradient buffers: out = sum_r in[r].
+ * any_flag_out (optional, device int): set to 1 when gathered[r*stride + flag_index] != 0 for any
+ * rank r (a rank whose batch overflowed), else 0 -- the skip word of the two calls above when
+ * world > 1, so that all replicas skip the same steps and stay identical.                    */
 int gccb_sum_ranks(const float* gathered, int32_t world, int64_t stride, int64_t n, float* out,
-                   gccb_stream_t stream);
+                   int64_t flag_index, int32_t* any_flag_out, gccb_stream_t stream);
+
+/* ---- tensor-core contraction (tcgen05 + TMEM + TMA; csrc/tc_gemm.cu) ------------------------------
+ * The dense products of the path at hidden >= 128 (BASELINE config 4): the GIN MLP's Linear layers
+ * (gcc/models/gin.py:107-116) with the BatchNorm column statistics of :115 fused into the epilogue,
+ * their input / weight gradients, and the MoCo logits q.queue^T (gcc/contrastive/memory_moco.py:33-44).
+ *   out[M x N] = alpha * A[M x K] . B[N x K]^T (+ bias[N])
+ * A [M_cap][K] and B [N][K]: bf16, row-major (K contiguous), 16-byte aligned; K % 64 == 0, N % 32 == 0.
+ * m_dev (optional): device int with the number of valid rows (<= M_cap), so the row count of a sampled
+ * batch never comes back to the host.  out_f32 / out_bf16: [M_cap][ldo] (either may be NULL).
+ * colstats (optional): double [2][N], += column sums / sums of squares of the stored values over the
+ * valid rows.  splits > 1: split-K over CTAs; scratch must hold splits * M_cap * ldo floats (partials are
+ * added in a fixed order); colstats must be NULL.                                                  */
+int gccb_tc_gemm_bf16(const void* A, const void* B, int32_t M_cap, int32_t N, int32_t K,
+                      const int32_t* m_dev, const float* bias, float alpha, float* out_f32,
+                      void* out_bf16, int32_t ldo, double* colstats, int32_t splits, float* scratch,
+                      gccb_stream_t stream);
+/* fp32 [rows][lds] -> bf16 [rows_pad][cols_pad] (transpose = 0) or [cols_pad][rows_pad] (transpose = 1),
+ * zero padded; rows_dev (optional): device int, rows beyond it are written as zeros.                 */
+int gccb_cast_bf16(const float* src, int32_t rows, int32_t cols, int32_t lds, void* dst, int32_t rows_pad,
+                   int32_t cols_pad, int32_t transpose, const int32_t* rows_dev, gccb_stream_t stream);
 
 /* ---- SM partitioning (new; no reference counterpart) ---------------------------------------------
  * Split the device's SMs into two CUDA green contexts: group 0 gets `first_sms` SMs (rounded up to

@@ -166,9 +166,21 @@ def test_moco_head_and_optimiser_vs_oracle():
     # enqueue with wrap-around
     idx = np.array([K - 4], np.int64)
     mem2 = mem.copy(); tm = torch.from_numpy(mem.copy())
-    assert Lb.gccb_moco_enqueue(ptr(mem2), ptr(k), B, d, K, ptr(idx), None) == 0
+    assert Lb.gccb_moco_enqueue(ptr(mem2), ptr(k), B, d, K, ptr(idx), 1, 0, None, 0, None) == 0
     new_idx = om.moco_enqueue(tm, torch.from_numpy(k), K - 4)
     assert idx[0] == new_idx == 2 and np.array_equal(mem2, tm.numpy())
+    # a skipped step (batch published empty: overflow bits set in the flag word) leaves queue and pointer alone
+    skip = np.array([2], np.int32); mem3 = mem2.copy(); idx3 = idx.copy()
+    assert Lb.gccb_moco_enqueue(ptr(mem3), ptr(k), B, d, K, ptr(idx3), 1, 0, ptr(skip), 3, None) == 0
+    assert idx3[0] == idx[0] and np.array_equal(mem3, mem2)
+    # several ranks' keys from one gathered buffer, in rank order, one launch
+    parts, stride = 3, B * d + 7
+    gk_ = rng.normal(size=(parts, stride)).astype(np.float32)
+    idx4 = np.array([K - 3], np.int64); mem4 = mem.copy(); tm4 = torch.from_numpy(mem.copy()); ii = K - 3
+    assert Lb.gccb_moco_enqueue(ptr(mem4), ptr(gk_), B, d, K, ptr(idx4), parts, stride, None, 0, None) == 0
+    for r in range(parts):
+        ii = om.moco_enqueue(tm4, torch.from_numpy(gk_[r, :B * d].reshape(B, d).copy()), ii)
+    assert idx4[0] == ii and np.array_equal(mem4, tm4.numpy())
     # clip + Adam + EMA
     n_live, n_all = 1000, 1300
     p = rng.normal(size=n_all).astype(np.float32); g = rng.normal(size=n_live).astype(np.float32)
@@ -181,13 +193,22 @@ def test_moco_head_and_optimiser_vs_oracle():
     hyper = np.array([lr, 1 - 0.9 ** t, np.sqrt(1 - 0.999 ** t), 0], np.float32)
     gn = np.zeros(1, np.float32); wsd = np.zeros(1, np.float64)
     assert Lb.gccb_clip_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(pe), n_live, n_all, ptr(hyper), 0.9, 0.999, 1e-8,
-                                 1e-5, 1.0, 0.999, 1.0, ptr(gn), ptr(wsd), None) == 0
+                                 1e-5, 1.0, 0.999, 1.0, ptr(gn), ptr(wsd), None, 0, None) == 0
     assert np.isclose(gn[0], gn_o, rtol=1e-5)
     assert np.allclose(p, p_o, rtol=1e-5, atol=1e-6) and np.allclose(m, m_o, rtol=1e-5, atol=1e-7)
     assert np.allclose(v, v_o, rtol=1e-5, atol=1e-9) and np.allclose(pe, pe_o, rtol=1e-5, atol=1e-6)
     gathered = rng.normal(size=(3, 40)).astype(np.float32); outs = np.zeros(32, np.float32)
-    assert Lb.gccb_sum_ranks(ptr(gathered), 3, 40, 32, ptr(outs), None) == 0
-    assert np.allclose(outs, gathered[:, :32].sum(0), rtol=1e-6)
+    anyf = np.array([7], np.int32)
+    gathered[:, 35] = 0.0
+    assert Lb.gccb_sum_ranks(ptr(gathered), 3, 40, 32, ptr(outs), 35, ptr(anyf), None) == 0
+    assert np.allclose(outs, gathered[:, :32].sum(0), rtol=1e-6) and anyf[0] == 0
+    gathered[1, 35] = 2.0
+    assert Lb.gccb_sum_ranks(ptr(gathered), 3, 40, 32, ptr(outs), 35, ptr(anyf), None) == 0 and anyf[0] == 1
+    # the skip word makes the optimiser a no-op
+    snap = [x.copy() for x in (p, m, v, pe)]
+    assert Lb.gccb_clip_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(pe), n_live, n_all, ptr(hyper), 0.9, 0.999, 1e-8,
+                                 1e-5, 1.0, 0.999, 1.0, ptr(gn), ptr(wsd), ptr(anyf), -1, None) == 0
+    assert all(np.array_equal(a, b) for a, b in zip(snap, (p, m, v, pe)))
 
 
 @pytest.mark.parametrize("B,d,K", [(37, 32, 300), (5, 64, 129), (33, 128, 64), (9, 256, 200)])

@@ -21,7 +21,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert declared and declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.gccb_version() == 100
+    assert lib.gccb_version() == 200
     if not torch.cuda.is_available():
         assert lib.gccb_arch() < 0                          # no device: loud negative status, no fallback
         assert b"CUDA" in lib.gccb_last_error()
