@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--train-sms", type=int, default=0,
                     help="SMs reserved for the training kernels (green-context partition); 0 = shared")
+    ap.add_argument("--mode", default="moco", choices=["moco", "e2e"],
+                    help="moco: the headline MoCo step; e2e: the reference's E2E recipe (train.py without --moco: both "
+                         "views through the query encoder, in-batch negatives, no queue / momentum encoder)")
     ap.add_argument("--prefetch", type=int, default=4, choices=[1, 2, 3, 4, 5, 6, 8],
                     help="batches the sampler/eigensolver streams run ahead of the training stream")
     return ap.parse_args()
@@ -292,7 +295,7 @@ def run_ours(args, cfg):
     model, ema = model.to(dev), ema.to(dev)
     with contextlib.redirect_stdout(sys.stderr):           # the reference prints the queue shape; keep stdout = one JSON line
         contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
-    eng = PretrainEngine(ds, model, ema, contrast, moco=True, rank=rank, world_size=world,
+    eng = PretrainEngine(ds, model, ema, contrast, moco=args.mode == "moco", rank=rank, world_size=world,
                          prefetch=args.prefetch, train_sms=args.train_sms or None)
     lib = _lib.get()
     total_steps = 75000                                     # train.py defaults: 100 epochs x 750
@@ -320,13 +323,28 @@ def run_ours(args, cfg):
     eng.count_acc = torch.zeros(4, dtype=torch.float64, device=dev)   # algorithmic-byte counters (device side)
     eng.timing = []
     launches0 = lib.gccb_launch_count()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     ev[0].record()
     for i in range(args.steps):
         eng.step(lr=lr_at(eng.global_step))
+        step_ev[i].record()
+    # the window closes when the data path has caught up too: every step() issued one prepare (sampler +
+    # eigensolver of a later batch) on a data stream; without this wait the window would hold K training
+    # parts but only K - prefetch data parts (the pipeline was full when the clock started)
+    eng.wait_data_streams()
     ev[1].record()
     barrier()
     ms = ev[0].elapsed_time(ev[1])
+    per_step = [ev[0].elapsed_time(step_ev[0])] + [step_ev[i - 1].elapsed_time(step_ev[i]) for i in range(1, args.steps)]
+    ps = sorted(per_step)
+    med = ps[len(ps) // 2]
+    step_dist = {"p50_ms": med, "p95_ms": ps[min(len(ps) - 1, int(0.95 * len(ps)))], "max_ms": ps[-1], "min_ms": ps[0],
+                 "steps_over_2x_median": int(sum(1 for x in per_step if x > 2 * med)),
+                 "slowest_steps": sorted(range(len(per_step)), key=lambda i: -per_step[i])[:3],
+                 "drain_ms": ms - sum(per_step),
+                 "note": "CUDA-event time between consecutive steps on the training stream; drain_ms = the trailing "
+                         "data-path work included in the window after the last training step"}
     launches = lib.gccb_launch_count() - launches0
     clk = clocks.stop()
     samp_ev, eng.timing = eng.timing, None
@@ -371,7 +389,7 @@ def run_ours(args, cfg):
     # ---- e2e: host seeds (pinned) -> H2D each step, loss D2H each step ---------------------------
     cdf_host = ds.graph.cdf.cpu().numpy()
     rs = np.random.RandomState(1 + rank)
-    n_e2e = max(args.steps // 2, 5)
+    n_e2e = args.steps
     host_seeds = torch.from_numpy(np.searchsorted(cdf_host, rs.random_sample((n_e2e + 2, B)), side="right")
                                   .clip(max=len(cdf_host) - 1).astype(np.int64)).pin_memory()
     loss_ring = torch.zeros(4, 4, dtype=torch.float32).pin_memory()
@@ -394,6 +412,7 @@ def run_ours(args, cfg):
             e2e_losses.append(float(loss_ring[(i - 1) & 3][0]))
     done[(n_e2e - 1) & 3].synchronize()
     e2e_losses.append(float(loss_ring[(n_e2e - 1) & 3][0]))
+    eng.wait_data_streams()
     e1.record()
     barrier()
     t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -405,7 +424,8 @@ def run_ours(args, cfg):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(cfg, world), "config": args.config,
+            "config": {"workload": workload_name(cfg, world) + ("" if args.mode == "moco" else " [E2E head: no queue]"),
+                       "config": args.config,
                        "global_batch_pairs": B * world, "subgraphs_per_step": 2 * B * world,
                        "parallelism": "dp%d (CSR replicated, seeds sharded, one all-gather/step)" % world,
                        "l2": "inputs larger than L2: %.0f MB CSR sampled at random; no explicit flush" % (
@@ -418,6 +438,7 @@ def run_ours(args, cfg):
                     "d2h_bytes_per_step": 16, "steps": n_e2e,
                     "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step (trains batch t, prepares a later batch from these seeds) -> stats D2H every step, host waits for the previous step's copy"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "step_time": step_dist, "mode": args.mode,
             "clocks": clk, "roofline": roofline, "eigensolver": eig, "phases_ms": phases,
             "loss": stats["loss"], "grad_norm": stats["grad_norm"]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

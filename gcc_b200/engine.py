@@ -271,6 +271,15 @@ class PretrainEngine:
             self.timing_main.append(tm)
         self.global_step += 1
 
+    def wait_data_streams(self):
+        """Order the caller's current stream after everything issued so far on the run-ahead data streams
+        (no host sync).  Benchmarks close their timed window with it so that the window holds as many data
+        parts as training parts."""
+        if self.prefetch:
+            cur = torch.cuda.current_stream(self.dev)
+            for ds_ in self.data_streams:
+                cur.wait_stream(ds_)
+
     def read_stats(self):
         """Host sync: loss, prob (mean positive logit), pre-clip grad norm, batch sizes, flags."""
         buf = self.cur_buf

@@ -1,0 +1,349 @@
+"""GPU parity, round 2: the cases VERDICT r01 found uncovered -- every eigensolver size class, one full
+BASELINE-config-2 batch (1M / 20M Chung-Lu, B = 256, rw_hops 256) bit-exact against the C oracle with a
+spectral check of all 512 ego-nets, the fused InfoNCE / E2E heads at their real sizes, hidden = 256, the
+skip-step protocol under run-ahead, and replica identity on 2 GPUs."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from test_gpu_parity import _dataset, _fill_batch, _split
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# Residual bars (||L x - theta x||, unit x, evaluated in float64 on the float32 output):
+#   single-CTA classes (n <= 384): the fp32 Rayleigh-Ritz floor, 3e-4 (same bar as round 1);
+#   cluster classes (n > 384, hub ego-nets): the documented stagnation bar of posenc.cu (GCCB_CF_STAG):
+#   a near-degenerate cluster wider than the 48-column block converges only to its own spread.
+RES_SMALL, RES_HUB = 3e-4, 2.5e-3
+
+
+def _spectral(sub, u, lam, res_bar, tol_l):
+    from oracle import posenc as opos
+    n = sub["n"]
+    k = min(n - 2, 32)
+    if k <= 0:
+        assert np.all(u == 0)
+        return 0.0, 0.0
+    lap = opos.normalized_adjacency(sub["indptr"], sub["indices"], n).toarray()
+    w = np.linalg.eigvalsh(lap)[-k:]
+    assert np.allclose(lam[:k], w, atol=tol_l), (n, np.abs(lam[:k] - w).max())
+    theta, resid, ortho = opos.spectral_report(lap, u[:, :k].astype(np.float64))
+    assert resid.max() < res_bar and ortho < 1e-4, (n, resid.max(), ortho)
+    assert np.all(u[:, k:] == 0)
+    return float(resid.max()), float(ortho)
+
+
+def _posenc_raw(buf):
+    from gcc_b200 import _lib
+    lib = _lib.get()
+    _lib.check(lib.gccb_posenc(C.byref(buf.c), 32, 0, _lib.dptr(buf.pos), _lib.dptr(buf.eigvals),
+                               _lib.dptr(buf.ws_posenc), buf.ws_posenc.numel(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return buf.pos.cpu().numpy().copy(), buf.eigvals.cpu().numpy().copy()
+
+
+def test_eigensolver_every_size_class():
+    """One explicit ego-net per solver class: dense Jacobi (n 40), shared-memory ChFSI (90, 150, 300),
+    cluster ChFSI with 192- and 448-row slabs (520, 1500, 3300) and a 700-vertex star (eigenvalue 0 x 698)."""
+    from gcc_b200.datasets import synthetic
+    from gcc_b200.datasets.graph_dataset import BatchBuffers
+    graphs = [synthetic.erdos_renyi(40, 90, seed=1), synthetic.chung_lu(95, 250, seed=2),
+              synthetic.chung_lu(156, 420, seed=3), synthetic.chung_lu(320, 900, exponent=0.7, seed=4),
+              synthetic.chung_lu(560, 1500, exponent=0.8, seed=3), synthetic.chung_lu(1700, 5000, exponent=0.9, seed=4),
+              synthetic.chung_lu(3500, 9000, exponent=0.9, seed=5), synthetic.star_graph(700)]
+    subs = [dict(indptr=g.indptr.astype(np.int32), indices=g.indices.astype(np.int32), n=g.num_nodes) for g in graphs]
+    sizes = [s["n"] for s in subs]
+    cls = [0 if n <= 64 else 1 if n <= 96 else 2 if n <= 160 else 3 if n <= 384 else 4 if n <= 1536 else 5 for n in sizes]
+    assert sorted(set(cls)) == [0, 1, 2, 3, 4, 5], (sizes, cls)
+    B = 4
+    views = [subs[:4], subs[4:]]
+    N = max(sum(s["n"] for s in v) for v in views)
+    E = max(sum(len(s["indices"]) for s in v) for v in views)
+    buf = BatchBuffers(B, N + 8, E + 8, 32, 64, "cuda")
+    _fill_batch(buf, views)
+    raw, eig = _posenc_raw(buf)
+    buf.check_flags()
+    noff = buf.node_off.cpu().numpy()
+    it, res = buf.eig_debug()
+    report = []
+    for i, s in enumerate(subs):
+        v, gi = divmod(i, B)
+        bar = RES_SMALL if s["n"] <= 384 else RES_HUB
+        r, o = _spectral(s, raw[v, noff[v, gi]:noff[v, gi + 1]], eig[v * B + gi], bar, 5e-5 if s["n"] > 384 else 2e-5)
+        report.append((s["n"], int(it[v * B + gi]), r))
+    print("eigensolver classes (n, iterations, max residual):", report)
+
+
+@pytest.fixture(scope="module")
+def c2_batch():
+    """One batch of BASELINE config 2 on the device + the C oracle's answer for the same samples."""
+    from gcc_b200.datasets import synthetic
+    from gcc_b200.datasets.graph_dataset import LoadBalanceGraphDataset
+    from oracle import rwr as orwr
+    g = synthetic.chung_lu_device(1_000_000, 20_000_000, 0.5, seed=0, device="cuda")
+    B = 256
+    ds = LoadBalanceGraphDataset(rw_hops=256, restart_prob=0.8, positional_embedding_size=32, dgl_graphs_file=g,
+                                 num_samples=2000, num_workers=12, num_copies=6, batch_size=B, seed=0)
+    buf = ds.sample_batch(first_sample=0, posenc=False)
+    torch.cuda.synchronize()
+    buf.check_flags()
+    indptr, indices = g.indptr.cpu().numpy(), g.indices.cpu().numpy()
+    seeds = orwr.draw_seeds(orwr.seed_cdf(indptr), 0, range(B))
+    bt = orwr.budget_table(int(np.diff(indptr).max()), 256, 0.8)
+    want = orwr.rwr_batch(indptr, indices, 0, np.arange(B), seeds, bt, orwr.restart_threshold(0.8),
+                          int(bt.max()) + 65, 1 << 21)
+    return dict(ds=ds, buf=buf, want=want, seeds=seeds, B=B, max_budget=int(bt.max()))
+
+
+def test_c2_batch_sampler_bit_exact(c2_batch):
+    """All 512 ego-nets of a config-2 batch (walk budgets up to ~3.3k, hub rows reverse-probed): seeds,
+    vertex order, induced CSR and counters equal the C oracle's integer for integer."""
+    buf, want, B = c2_batch["buf"], c2_batch["want"], c2_batch["B"]
+    assert np.array_equal(buf.seeds.cpu().numpy(), c2_batch["seeds"])
+    cnt = buf.counters.cpu().numpy()
+    sizes = []
+    for v in (0, 1):
+        got = _split(buf, v)
+        for gi in range(B):
+            w = want[2 * gi + v]
+            assert np.array_equal(got[gi]["subv"], w["subv"]), (v, gi)
+            assert np.array_equal(got[gi]["indptr"], w["indptr"]), (v, gi)
+            assert np.array_equal(got[gi]["indices"], w["indices"]), (v, gi)
+            assert tuple(cnt[v * B + gi]) == (w["n"], w["m"], w["steps"], w["sumdeg"])
+            sizes.append(w["n"])
+    print("C2 batch: ego-net sizes mean %.1f max %d; walk budget max %d" % (np.mean(sizes), max(sizes), c2_batch["max_budget"]))
+    assert max(sizes) > 384                                # a hub ego-net (cluster eigensolver class) is present
+
+
+def test_c2_batch_posenc_spectral_every_egonet(c2_batch):
+    """Spectral parity of ALL 512 ego-nets of the batch, with the residual bar of each solver class."""
+    buf, B = c2_batch["buf"], c2_batch["B"]
+    raw, eig = _posenc_raw(buf)
+    flags = int(buf.flags.item())
+    buf.flags.zero_()
+    it, res = buf.eig_debug()
+    it, res = it.cpu().numpy(), res.cpu().numpy()
+    noff = buf.node_off.cpu().numpy()
+    worst_small = worst_hub = 0.0
+    nhub = 0
+    for v in (0, 1):
+        for gi, s in enumerate(_split(buf, v)):
+            hub = s["n"] > 384
+            r, _ = _spectral(s, raw[v, noff[v, gi]:noff[v, gi + 1]], eig[v * B + gi], RES_HUB if hub else RES_SMALL,
+                             5e-5 if hub else 2e-5)
+            if hub:
+                worst_hub, nhub = max(worst_hub, r), nhub + 1
+            else:
+                worst_small = max(worst_small, r)
+    ch = it > 0
+    print("C2 batch eigensolver: NOCONV flag %d; ChFSI iterations mean %.2f max %d; worst residual n<=384: %.2e, "
+          "hub ego-nets (%d): %.2e; kernel-side residual max %.2e" % (
+              (flags >> 3) & 1, it[ch].mean(), it.max(), worst_small, nhub, worst_hub, res.max()))
+
+
+def test_c2_batch_engine_step_matches_oracle(c2_batch):
+    """One full MoCo step (K = 16384, 5-layer GIN hid 64, B = 256) on the config-2 batch against the CPU
+    oracle step fed the same batch and positional features: loss, feat_q, pre-clip gradient norm <= 1e-3."""
+    from gcc_b200.contrastive.memory_moco import MemoryMoCo
+    from gcc_b200.engine import PretrainEngine
+    from gcc_b200.models import GraphEncoder
+    from oracle import step as ostep
+    ds, B = c2_batch["ds"], c2_batch["B"]
+    torch.manual_seed(1)
+    H, L, K = 64, 5, 16384
+
+    def mk():
+        return GraphEncoder(positional_embedding_size=32, max_degree=512, degree_embedding_size=16, output_dim=H,
+                            node_hidden_dim=H, num_layers=L, norm=True, gnn_model="gin", degree_input=True)
+
+    model, ema = mk(), mk()
+    ema.load_state_dict(model.state_dict())
+    model, ema = model.cuda(), ema.cuda()
+    contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).cuda()
+    eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=0)
+    sd0 = {k: v.detach().cpu().double().clone() for k, v in model.state_dict().items()}
+    state = dict(params={k: v.clone() for k, v in sd0.items()}, ema={k: v.clone() for k, v in sd0.items()},
+                 memory=contrast.memory.detach().cpu().double().clone(), index=0, adam_m={}, adam_v={}, adam_t=0)
+    eng.step(lr=0.005)
+    s = eng.read_stats()
+    buf = eng.cur_buf
+
+    def view(v):
+        n, m = int(buf.node_off[v, B]), int(buf.edge_off[v, B])
+        noff = buf.node_off[v].cpu().numpy().astype(np.int64)
+        seed = np.zeros(n, np.int64)
+        seed[noff[:B]] = 1
+        return dict(indptr=buf.indptr[v, :n + 1].cpu().numpy().astype(np.int64),
+                    indices=buf.indices[v, :m].cpu().numpy().astype(np.int64),
+                    pos=buf.pos[v, :n].cpu().double().numpy(), seed=seed,
+                    sub_deg=buf.sub_deg[v, :n].cpu().numpy(), node_off=noff)
+
+    r = ostep.train_step(state, view(0), view(1), num_layers=L, moco=True, T=0.07, lr=0.005,
+                         dropout_key=model.dropout_key, step_index=0)
+    assert np.isclose(s["loss"], r["loss"], rtol=1e-3), (s["loss"], r["loss"])
+    assert np.isclose(s["grad_norm"], r["grad_norm"], rtol=2e-3), (s["grad_norm"], r["grad_norm"])
+    fq, fk = eng.feat_q.cpu().numpy(), eng.feat_k.cpu().numpy()
+    assert np.allclose(fq, r["feat_q"].numpy(), rtol=1e-3, atol=1e-4), np.abs(fq - r["feat_q"].numpy()).max()
+    assert np.allclose(fk, r["feat_k"].numpy(), rtol=1e-3, atol=1e-4)
+    print("C2 step: loss %.6f (oracle %.6f), grad norm %.5f (oracle %.5f), nodes %d/%d" % (
+        s["loss"], r["loss"], s["grad_norm"], r["grad_norm"], s["nodes_q"], s["nodes_k"]))
+
+
+@pytest.mark.parametrize("B,K,d", [(256, 16384, 64), (1024, 65536, 256), (100, 1000, 128)])
+def test_fused_infonce_real_sizes(B, K, d):
+    """gccb_infonce_fused at the config-2 and config-4 head sizes against float64 torch: loss, mean positive
+    logit and dq (memory_moco.py:33-44 + criterions.py:12-17 + backward)."""
+    from gcc_b200 import _lib
+    lib = _lib.get()
+    g = torch.Generator(device="cuda").manual_seed(B + K)
+    q = torch.nn.functional.normalize(torch.randn(B, d, device="cuda", generator=g), dim=1)
+    k = torch.nn.functional.normalize(q + 0.3 * torch.randn(B, d, device="cuda", generator=g), dim=1)
+    stdv = 1.0 / (d / 3) ** 0.5
+    mem = (torch.rand(K, d, device="cuda", generator=g) * 2 * stdv - stdv)
+    mem[:K // 2] = torch.nn.functional.normalize(mem[:K // 2], dim=1)          # a half-filled queue: both regimes
+    stats = torch.zeros(4, device="cuda")
+    dq = torch.zeros(B, d, device="cuda")
+    ws = torch.empty(lib.gccb_infonce_workspace(B, d, K), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.gccb_infonce_fused(_lib.dptr(q), _lib.dptr(k), _lib.dptr(mem), B, d, K, 0.07, _lib.dptr(stats),
+                                      _lib.dptr(dq), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    q64 = q.double().requires_grad_(True)
+    out = torch.cat([(q64 * k.double()).sum(1, keepdim=True), q64 @ mem.double().t()], 1) / 0.07
+    loss = torch.nn.functional.cross_entropy(out, torch.zeros(B, dtype=torch.long, device="cuda"))
+    loss.backward()
+    assert np.isclose(float(stats[0]), float(loss), rtol=1e-5), (float(stats[0]), float(loss))
+    assert np.isclose(float(stats[1]), float(out[:, 0].mean()), rtol=1e-5)
+    want = q64.grad
+    scale = float(want.abs().max())
+    assert torch.allclose(dq.double(), want, rtol=1e-3, atol=1e-4 * scale), float((dq.double() - want).abs().max() / scale)
+
+
+@pytest.mark.parametrize("B,d", [(32, 32), (256, 64), (100, 256)])
+def test_e2e_head_matches_float64(B, d):
+    """gccb_e2e_nce (train.py:397-401 + criterions.py:27-33): loss, mean diagonal logit, dq and dk."""
+    from gcc_b200 import _lib
+    lib = _lib.get()
+    g = torch.Generator(device="cuda").manual_seed(B * d)
+    q = torch.nn.functional.normalize(torch.randn(B, d, device="cuda", generator=g), dim=1)
+    k = torch.nn.functional.normalize(q + 0.5 * torch.randn(B, d, device="cuda", generator=g), dim=1)
+    stats = torch.zeros(4, device="cuda")
+    dq, dk = torch.zeros(B, d, device="cuda"), torch.zeros(B, d, device="cuda")
+    ws = torch.empty(B * B * 4, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.gccb_e2e_nce(_lib.dptr(q), _lib.dptr(k), B, d, 0.07, _lib.dptr(stats), _lib.dptr(dq), _lib.dptr(dk),
+                                _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    q64, k64 = q.double().requires_grad_(True), k.double().requires_grad_(True)
+    out = k64 @ q64.t() / 0.07
+    loss = torch.nn.functional.cross_entropy(out, torch.arange(B, device="cuda"))
+    loss.backward()
+    assert np.isclose(float(stats[0]), float(loss), rtol=1e-5)
+    assert np.isclose(float(stats[1]), float(out.diagonal().mean()), rtol=1e-5)
+    for got, want in ((dq, q64.grad), (dk, k64.grad)):
+        scale = float(want.abs().max())
+        assert torch.allclose(got.double(), want, rtol=1e-3, atol=1e-5 * scale)
+
+
+def test_gin_hidden_256_forward_backward_vs_oracle():
+    """BASELINE config 4 width: GraphEncoder(hidden 256, 5 layers) forward + backward through the module API
+    against the torch-CPU float64 oracle with autograd (embeddings <= 1e-3, gradients <= 5e-3 of their scale).
+    bf16 tensor-core operands: the oracle rounds the GEMM operands the same way when the tensor-core path is on."""
+    from gcc_b200.datasets import synthetic
+    from gcc_b200.datasets.data_util import BatchedSubgraphs
+    from gcc_b200.models import GraphEncoder
+    from oracle import model as om
+    torch.manual_seed(5)
+    g = synthetic.chung_lu(4000, 30000, seed=6)
+    B, H, L = 24, 256, 5
+    ds = _dataset(g, B, 64, seed=3)
+    buf = ds.sample_batch(first_sample=0)
+    torch.cuda.synchronize()
+    buf.check_flags()
+    model = GraphEncoder(positional_embedding_size=32, max_degree=512, degree_embedding_size=16, output_dim=H,
+                         node_hidden_dim=H, num_layers=L, norm=True, gnn_model="gin", degree_input=True).cuda()
+    model.train()
+    model.gnn.drop.eval()                                   # dropout off: its mask parity is covered elsewhere
+    gq = BatchedSubgraphs(buf, 0)
+    sd0 = {k: v.detach().cpu().double().clone() for k, v in model.state_dict().items()}
+    feat = model(gq)
+    R = torch.randn(B, H, device="cuda")
+    (feat * R).sum().backward()
+    torch.cuda.synchronize()
+    n, m = int(buf.node_off[0, B]), int(buf.edge_off[0, B])
+    noff = buf.node_off[0].cpu().numpy().astype(np.int64)
+    seed = np.zeros(n, np.int64)
+    seed[noff[:B]] = 1
+    P = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float64 and not k.endswith(("running_mean", "running_var", ".eps")) else v)
+         for k, v in sd0.items()}
+    f, _, _ = om.gin_encoder_forward(P, buf.indptr[0, :n + 1].cpu().numpy().astype(np.int64),
+                                     buf.indices[0, :m].cpu().numpy().astype(np.int64), buf.pos[0, :n].cpu().double(),
+                                     seed, buf.sub_deg[0, :n].cpu().numpy(), noff, num_layers=L, bn_train=True)
+    assert np.allclose(feat.detach().cpu().numpy(), f.detach().numpy(), rtol=1e-3, atol=1e-4), \
+        np.abs(feat.detach().cpu().numpy() - f.detach().numpy()).max()
+    (f * R.cpu().double()).sum().backward()
+    checked = 0
+    for name, p in model.named_parameters():
+        if p.grad is None or name.startswith(("set2set", "lin_readout")):
+            continue
+        if "mlp.linears" in name and name.endswith("bias"):
+            continue                                    # exactly-zero true gradient (feeds a BatchNorm)
+        want = P[name].grad
+        want = np.zeros(tuple(p.shape)) if want is None else want.numpy()
+        got = p.grad.cpu().numpy()
+        scale = max(np.abs(want).max(), 1e-6)
+        assert np.allclose(got, want, rtol=5e-3, atol=5e-3 * scale), (name, np.abs(got - want).max(), scale)
+        checked += 1
+    assert checked >= 40
+
+
+def test_overflowed_batch_is_skipped_under_prefetch():
+    """with run-ahead on, a batch whose view overflows node_cap is published empty; the step must
+    leave weights, Adam state, queue and BatchNorm running statistics untouched, and read_stats() must raise
+    whichever ring buffer carried the flag."""
+    from gcc_b200 import _lib
+    from gcc_b200.contrastive.memory_moco import MemoryMoCo
+    from gcc_b200.datasets import synthetic
+    from gcc_b200.engine import PretrainEngine
+    from gcc_b200.models import GraphEncoder
+    torch.manual_seed(0)
+    g = synthetic.erdos_renyi(1000, 5000, seed=0)
+    ds = _dataset(g, 16, 64, node_cap=100, edge_cap=100000)     # far too small: every batch overflows
+
+    def mk():
+        return GraphEncoder(positional_embedding_size=32, max_degree=512, degree_embedding_size=16, output_dim=64,
+                            node_hidden_dim=64, num_layers=3, norm=True, gnn_model="gin", degree_input=True)
+
+    model, ema = mk(), mk()
+    ema.load_state_dict(model.state_dict())
+    model, ema = model.cuda(), ema.cuda()
+    contrast = MemoryMoCo(64, None, 64, 0.07, use_softmax=True).cuda()
+    eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=4)
+    snap = [t.detach().clone() for t in (model.flat_params, ema.flat_params, contrast.memory, model._running,
+                                          ema._running, eng.adam_m, eng.adam_v)]
+    for _ in range(7):                                           # steps land on several ring slots
+        eng.step(lr=0.005)
+    torch.cuda.synchronize()
+    now = (model.flat_params, ema.flat_params, contrast.memory, model._running, ema._running, eng.adam_m, eng.adam_v)
+    for a, b in zip(snap, now):
+        assert torch.equal(a, b)
+    assert int(eng.index_dev.item()) == 0
+    assert torch.isfinite(eng.stats).all()
+    with pytest.raises(_lib.GccbError):
+        eng.read_stats()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_replicas_stay_identical():
+    """5 data-parallel steps on 2 GPUs over NCCL: parameters, EMA parameters and queues hash identically on
+    both ranks, and the summed gradient equals the sum of the two single-GPU shards (tests/dist_replica_check.py)."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(ROOT, "tests", "dist_replica_check.py")], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "REPLICAS IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
