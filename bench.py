@@ -44,8 +44,6 @@ def parse():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--train-sms", type=int, default=0,
-                    help="SMs reserved for the training kernels (green-context partition); 0 = shared")
     ap.add_argument("--mode", default="moco", choices=["moco", "e2e"],
                     help="moco: the headline MoCo step; e2e: the reference's E2E recipe (train.py without --moco: both "
                          "views through the query encoder, in-batch negatives, no queue / momentum encoder)")
@@ -296,7 +294,7 @@ def run_ours(args, cfg):
     with contextlib.redirect_stdout(sys.stderr):           # the reference prints the queue shape; keep stdout = one JSON line
         contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
     eng = PretrainEngine(ds, model, ema, contrast, moco=args.mode == "moco", rank=rank, world_size=world,
-                         prefetch=args.prefetch, train_sms=args.train_sms or None)
+                         prefetch=args.prefetch)
     lib = _lib.get()
     total_steps = 75000                                     # train.py defaults: 100 epochs x 750
 

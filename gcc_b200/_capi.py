@@ -75,9 +75,6 @@ _PROTOS = {
     "gccb_tc_gemm_bf16": (C.c_int, [p, p, C.c_int32, C.c_int32, C.c_int32, p, p, C.c_float, p, p, C.c_int32, p,
                                     C.c_int32, p, p]),
     "gccb_cast_bf16": (C.c_int, [p, C.c_int32, C.c_int32, C.c_int32, p, C.c_int32, C.c_int32, C.c_int32, p, p]),
-    "gccb_partition_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
-    "gccb_partition_sm_count": (C.c_int32, [p, C.c_int32]),
-    "gccb_partition_stream": (C.c_int, [p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
 }
 
 SYMBOLS = tuple(_PROTOS)

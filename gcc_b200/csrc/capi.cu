@@ -28,7 +28,15 @@ int check_launch(const char* what) {
 }
 
 #ifndef GCCB_EMU
-cudaStream_t create_stream_like(cudaStream_t like, bool lowest_priority);   // partition.cu
+// a library side stream with the caller stream's scheduling priority (a default-priority weight-gradient
+// stream starves behind queued eigensolver CTAs), or the lowest priority on request
+static cudaStream_t create_stream_like(cudaStream_t like, bool lowest_priority) {
+  int prio = 0;
+  if (lowest_priority || cudaStreamGetPriority(like, &prio) != cudaSuccess) { cudaGetLastError(); prio = 0; }
+  cudaStream_t s = nullptr;
+  cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio);
+  return s;
+}
 
 StreamKit* stream_kit(cudaStream_t caller, int family, bool lowest_priority) {
   static StreamKit kits[16];
@@ -40,7 +48,7 @@ StreamKit* stream_kit(cudaStream_t caller, int family, bool lowest_priority) {
   StreamKit* k;
   if (nkits < 16) {
     k = &kits[nkits++];
-    for (int i = 0; i < 5; ++i) k->side[i] = create_stream_like(caller, lowest_priority);   // same green context as the caller
+    for (int i = 0; i < 5; ++i) k->side[i] = create_stream_like(caller, lowest_priority);
     for (int i = 0; i < 24; ++i) cudaEventCreateWithFlags(&k->ev[i], cudaEventDisableTiming);
   } else {
     k = &kits[15];                                        // more caller streams than kits: share the last one

@@ -26,7 +26,7 @@ from .parallel import StepExchange, first_sample_id
 class PretrainEngine:
     def __init__(self, dataset, model, model_ema, contrast, moco=True, learning_rate=0.005,
                  betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, clip_norm=1.0, alpha=0.999,
-                 nce_t=0.07, rank=0, world_size=1, process_group=None, prefetch=4, train_sms=None):
+                 nce_t=0.07, rank=0, world_size=1, process_group=None, prefetch=4):
         _lib.require_device()
         self.lib = _lib.get()
         self.ds, self.model, self.model_ema, self.contrast = dataset, model, model_ema, contrast
@@ -55,6 +55,8 @@ class PretrainEngine:
         self.hyper_host = torch.zeros(256, 4, dtype=torch.float32).pin_memory()
         # loss, prob, grad_norm(pre-clip), overflow marker of this rank's batch (multi-GPU skip protocol)
         self.stats = self.xch.stats_send if self.xch else torch.zeros(4, **f32)
+        self.stats_acc = torch.zeros(4, dtype=torch.float64, device=dev)   # per-step sums since the last read_stats()
+        self.steps_acc = 0
         self.norm_ws = torch.zeros(1, dtype=torch.float64, device=dev)
         self.any_skip = torch.zeros(1, dtype=torch.int32, device=dev)
         self.feat_q = torch.zeros(B, H, **f32)
@@ -63,15 +65,6 @@ class PretrainEngine:
         self.dk = torch.zeros(B, H, **f32)
         self.pooled = torch.zeros(max(L - 1, 1), B, H, **f32)
         self.pooled_k = torch.zeros(max(L - 1, 1), B, H, **f32)
-        # Optional SM partition (CUDA green contexts, gccb_partition_*): the training kernels get
-        # `train_sms` SMs of their own, the sampler / eigensolver run-ahead the rest.
-        self.partition = None
-        if train_sms and prefetch:
-            part = C.c_void_p()
-            _lib.check(self.lib.gccb_partition_create(dev.index or 0, int(train_sms), C.byref(part)),
-                       "gccb_partition_create")
-            self.partition = part
-            self.partition_sms = (self.lib.gccb_partition_sm_count(part, 0), self.lib.gccb_partition_sm_count(part, 1))
         self.aux_stream = self._new_stream(0, -1)      # key encoder, concurrent with the query encoder
         cap = dataset.node_cap
         acts_bytes = self.lib.gccb_gin_acts_bytes(C.byref(model.cfg), B, cap)
@@ -116,13 +109,7 @@ class PretrainEngine:
 
     # -------------------------------------------------------------------------------------------
     def _new_stream(self, group, priority):
-        """A stream of SM group `group` (0 training, 1 data) when partitioned, else a torch stream."""
-        if self.partition is None:
-            return torch.cuda.Stream(device=self.dev, priority=priority)
-        raw = C.c_void_p()
-        _lib.check(self.lib.gccb_partition_stream(self.partition, group, priority, C.byref(raw)),
-                   "gccb_partition_stream")
-        return torch.cuda.ExternalStream(raw.value, device=self.dev)
+        return torch.cuda.Stream(device=self.dev, priority=priority)
 
     def _hyper(self, lr):
         self.adam_t += 1
@@ -266,6 +253,10 @@ class PretrainEngine:
                                              self.payload if self.world > 1 else 0, skip_word, skip_mask, st),
                        "gccb_moco_enqueue")
             self.contrast.index = (self.contrast.index + B * self.world) % self.K
+        # the reference updates its meters from .item() reads every step (train.py:420-428); here the
+        # per-step scalars are summed on the device and read on demand
+        self.stats_acc.add_(self.stats)
+        self.steps_acc += 1
         if self.timing_main is not None:
             tm[1].record()
             self.timing_main.append(tm)
@@ -287,6 +278,32 @@ class PretrainEngine:
         for b_ in (self.bufs if self.prefetch else [buf]):     # every buffer of the run-ahead ring, not only
             b_.check_flags()                                   # the one the last step trained on
         s = self.stats.tolist()
+        acc, w = self.stats_acc.tolist(), max(self.steps_acc, 1)
+        self.stats_acc.zero_()
+        window = self.steps_acc
+        self.steps_acc = 0
         sizes = buf.node_off[:, self.B].tolist() + buf.edge_off[:, self.B].tolist()
         return dict(loss=s[0], prob=s[1], grad_norm=s[2], nodes_q=sizes[0], nodes_k=sizes[1],
-                    edges_q=sizes[2], edges_k=sizes[3])
+                    edges_q=sizes[2], edges_k=sizes[3], window_steps=window, window_loss=acc[0] / w,
+                    window_prob=acc[1] / w, window_grad_norm=acc[2] / w)
+
+    def optimizer_state_dict(self):
+        """The flat Adam buffers in the layout of torch.optim.Adam(model.parameters()).state_dict()
+        (train.py:667-672,752): per-parameter exp_avg / exp_avg_sq / step for the parameters that receive
+        gradients (the GIN path); the unused set2set / lin_readout tensors have no state, as in the reference
+        where they never get a gradient."""
+        names = [n for n, _ in self.model.named_parameters()]
+        state = {}
+        for i, n in enumerate(names):
+            if n in self.model._slices:
+                o, shape = self.model._slices[n]
+                cnt = 1
+                for d_ in shape:
+                    cnt *= d_
+                state[i] = {"step": torch.tensor(float(self.adam_t)),
+                            "exp_avg": self.adam_m[o:o + cnt].view(shape).clone(),
+                            "exp_avg_sq": self.adam_v[o:o + cnt].view(shape).clone()}
+        group = {"lr": self.lr0, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "params": list(range(len(names)))}
+        return {"state": state, "param_groups": [group]}

@@ -244,19 +244,6 @@ int gccb_tc_gemm_bf16(const void* A, const void* B, int32_t M_cap, int32_t N, in
 int gccb_cast_bf16(const float* src, int32_t rows, int32_t cols, int32_t lds, void* dst, int32_t rows_pad,
                    int32_t cols_pad, int32_t transpose, const int32_t* rows_dev, gccb_stream_t stream);
 
-/* ---- SM partitioning (new; no reference counterpart) ---------------------------------------------
- * Split the device's SMs into two CUDA green contexts: group 0 gets `first_sms` SMs (rounded up to
- * the hardware granularity), group 1 the rest.  Streams created from a group launch only on its
- * SMs; library-internal side streams (gccb_posenc size classes, gccb_gin_backward weight
- * gradients) are created inside the caller stream's group.  PretrainEngine puts the training
- * kernels on group 0 and the sampler / eigensolver run-ahead on group 1 so that the short training
- * kernels never queue behind long-lived eigensolver CTAs.  Setup-time calls (they allocate driver
- * objects that live until process exit); needs a CUDA 12.4+ driver. */
-typedef struct gccb_partition gccb_partition_t;
-int gccb_partition_create(int32_t device, int32_t first_sms, gccb_partition_t** out);
-int32_t gccb_partition_sm_count(const gccb_partition_t* p, int32_t which);
-int gccb_partition_stream(gccb_partition_t* p, int32_t which, int32_t priority, gccb_stream_t* out);
-
 #ifdef __cplusplus
 }
 #endif

@@ -32,8 +32,7 @@ ema.load_state_dict(model.state_dict())
 model, ema = model.to(dev), ema.to(dev)
 with contextlib.redirect_stdout(sys.stderr):
     contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
-eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=int(sys.argv[1]) if len(sys.argv) > 1 else 2,
-                     train_sms=int(sys.argv[2]) if len(sys.argv) > 2 else None)
+eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=int(sys.argv[1]) if len(sys.argv) > 1 else 2)
 for _ in range(5):
     eng.step(lr=0.005)
 torch.cuda.synchronize()

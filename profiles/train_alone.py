@@ -32,8 +32,7 @@ ema.load_state_dict(model.state_dict())
 model, ema = model.to(dev), ema.to(dev)
 with contextlib.redirect_stdout(sys.stderr):
     contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
-sms = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=2, train_sms=sms or None)
+eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=2)
 for _ in range(4):
     eng.step(lr=0.005)
 torch.cuda.synchronize()
@@ -42,9 +41,12 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 with torch.cuda.stream(eng.train_stream):
     for _ in range(3):
         eng._step(0.005, None, True)
+    from gcc_b200 import _lib
+    l0 = _lib.get().gccb_launch_count()
     e0.record()
     for _ in range(N):
         eng._step(0.005, None, True)
     e1.record()
+    launches = _lib.get().gccb_launch_count() - l0
 torch.cuda.synchronize()
-print("train part alone, train_sms=%s: %.3f ms/step" % (sms or "all", e0.elapsed_time(e1) / N))
+print("train part alone: %.3f ms/step, %d library launches/step" % (e0.elapsed_time(e1) / N, launches / N))

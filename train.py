@@ -10,10 +10,14 @@ What it keeps from the reference: flag names and defaults, run naming (train.py:
 triangular LR schedule with 10% warm-up (train.py:411-416, gcc/utils/misc.py:5-10), BatchNorm of the
 momentum encoder in train mode (train.py:357-365), the checkpoint dict
 {"opt","model","contrast","optimizer","epoch","model_ema"} with the reference's state_dict keys
-(train.py:748-786), print/TensorBoard scalars (train.py:438-472).  What changes: the data loader and
-the whole step run on the GPU through gcc_b200.engine.PretrainEngine (no DataLoader workers, no
-.item() per step: scalars are read every --print-freq steps).  Fine-tuning (--finetune) is out of
-scope.
+(train.py:748-786; "optimizer" is a torch.optim.Adam state_dict over model.parameters(), built from the
+flat Adam buffers), print/TensorBoard scalars (train.py:438-472), and the reference's step indexing:
+epochs are 1-based and global_step = epoch * n_batch + idx (train.py:411,733), so the LR schedule starts
+one epoch into its warm-up exactly like the reference's.  What changes: the data loader and the whole
+step run on the GPU through gcc_b200.engine.PretrainEngine (no DataLoader workers, no .item() per step:
+loss / prob / grad-norm are accumulated on the device EVERY step and read every --print-freq steps, so
+the meters average over all steps like the reference's).  Fine-tuning (--finetune) is out of scope
+(SURVEY.md section 2).
 """
 import argparse
 import os
@@ -115,6 +119,9 @@ def build_graph(args, device):
 def train_moco(epoch, engine, sw, opt, is_main):
     """One epoch (train.py:350-478): n_batch = dataset.total // batch_size steps."""
     n_batch = engine.ds.total // (opt.batch_size * engine.world)
+    if n_batch == 0:
+        raise ValueError("dataset.total = %d is smaller than one global batch (%d x %d): nothing to train on"
+                         % (engine.ds.total, opt.batch_size, engine.world))
     loss_meter, prob_meter, gs_meter, gnorm_meter = (AverageMeter() for _ in range(4))
     epoch_loss, batch_time = AverageMeter(), AverageMeter()
     end = time.time()
@@ -126,11 +133,12 @@ def train_moco(epoch, engine, sw, opt, is_main):
         if (idx + 1) % opt.print_freq == 0 or idx + 1 == n_batch:
             s = engine.read_stats()                      # the only host sync of the window
             bsz = opt.batch_size
-            loss_meter.update(s["loss"], bsz)
-            epoch_loss.update(s["loss"], bsz)
-            prob_meter.update(s["prob"], bsz)
+            w = max(s["window_steps"], 1)                # device-side sums over every step since the last read
+            loss_meter.update(s["window_loss"], bsz * w)
+            epoch_loss.update(s["window_loss"], bsz * w)
+            prob_meter.update(s["window_prob"], bsz * w)
             gs_meter.update((s["nodes_q"] + s["nodes_k"]) / 2.0 / bsz, 2 * bsz)
-            gnorm_meter.update(s["grad_norm"], 1)
+            gnorm_meter.update(s["window_grad_norm"], w)
             max_nodes, max_edges = max(max_nodes, s["nodes_q"]), max(max_edges, s["edges_q"])
             batch_time.update((time.time() - end) / opt.print_freq)
             end = time.time()
@@ -149,7 +157,7 @@ def train_moco(epoch, engine, sw, opt, is_main):
             for m in (loss_meter, prob_meter, gs_meter, gnorm_meter):
                 m.reset()
             max_nodes = max_edges = 0
-        if opt.max_steps and global_step + 1 >= opt.max_steps:
+        if opt.max_steps and engine.global_step >= opt.max_steps:
             break
     return epoch_loss.avg
 
@@ -205,12 +213,12 @@ def main(args):
             sw = None
     for epoch in range(start_epoch, args.epochs + 1):
         t0 = time.time()
-        loss = train_moco(epoch - 1, engine, sw, args, rank == 0)
+        loss = train_moco(epoch, engine, sw, args, rank == 0)        # 1-based, as the reference (train.py:733)
         if rank == 0:
             print("epoch {}, loss {:.4f}, total time {:.2f}".format(epoch, loss, time.time() - t0))
             if epoch % args.save_freq == 0:
                 state = {"opt": args, "model": model.state_dict(), "contrast": contrast.state_dict(),
-                         "optimizer": {"adam_m": engine.adam_m, "adam_v": engine.adam_v, "adam_t": engine.adam_t},
+                         "optimizer": engine.optimizer_state_dict(),
                          "epoch": epoch}
                 if args.moco:
                     state["model_ema"] = model_ema.state_dict()
