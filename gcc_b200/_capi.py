@@ -47,7 +47,7 @@ _PROTOS = {
     "gccb_last_error": (C.c_char_p, []),
     "gccb_launch_count": (C.c_ulonglong, []),
     "gccb_draw_seeds": (C.c_int, [p, C.c_int64, C.c_uint64, C.c_int64, C.c_int32, p, p, p]),
-    "gccb_sample_batch_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "gccb_sample_batch_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "gccb_sample_batch": (C.c_int, [C.POINTER(Graph), p, p, C.POINTER(Batch), p, C.c_size_t, p]),
     "gccb_posenc_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
     "gccb_posenc": (C.c_int, [C.POINTER(Batch), C.c_int32, C.c_int32, p, p, p, C.c_size_t, p]),

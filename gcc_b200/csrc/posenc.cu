@@ -36,14 +36,29 @@ namespace gccb {
 #define GCCB_EIG_MAXSWEEP 14
 #define GCCB_EIG_TOL 1.0e-6f
 #define GCCB_CF_B 48               // ChFSI block size (>= pos_dim 32 + guard vectors)
+// Chebyshev degree per outer iteration: as high as the fp32 block tolerates.  The filter on [-1, cut] gains
+// T_d(x1), x1 = (3 - cut) / (1 + cut), on the top eigenvalue relative to the damped interval; directions whose
+// relative gain drops below eps_fp32 vanish from the block, Gram-Schmidt then normalises noise into "Ritz vectors"
+// with arbitrary Ritz values, and those collide with wanted eigenvalues near the cut (measured: an n = 66 ego-net
+// diverges at a fixed degree 16).  So d = floor(acosh(G) / acosh(x1)) with G = 1e8, clamped to [4, GCCB_CF_DEG];
+// the first iteration (random block) is capped at GCCB_CF_DEG0.  Hub ego-nets (cut ~ 0.6-0.7, x1 ~ 1.4) run at
+// degree 16, small ones (cut ~ 0, x1 = 3) at 10.  Measured on C2 ego-nets (fp32 model of this kernel): 2.5 outer
+// iterations instead of 3.0 at the round-1 schedule (4, 8), hub ego-nets 2.6 instead of 3.9, worst residual 4e-5
+// instead of 3e-4 on n <= 160.
 #ifndef GCCB_CF_DEG0
-#define GCCB_CF_DEG0 8              // Chebyshev degree of the first outer iteration (random block: gain T_8(3) ~ 7e5
-#endif                             // keeps it numerically full rank for fp32 Gram-Schmidt; 12 does not)
+#define GCCB_CF_DEG0 8
+#endif
 #ifndef GCCB_CF_DEG
-#define GCCB_CF_DEG 16             // degree of the later iterations: the block is Ritz-rotated by then, so each column is
-#endif                             // one (scaled) direction plus noise and Gram-Schmidt in descending order stays stable;
-                                   // measured on C2 ego-nets (fp32 model): 2.0 outer iterations instead of 3.0 at (4, 8),
-                                   // hub ego-nets 2.7 instead of 3.9; (12, 24) breaks down
+#define GCCB_CF_DEG 16
+#endif
+#define GCCB_CF_LOGGAIN 19.1138f    // acosh(1e8)
+// When the smallest WANTED Ritz value sits at the bottom of the block (ego-nets whose top-32 reaches into the
+// null space: theta_k ~ theta_48 ~ 0), a cut at the lowest Ritz value leaves the wanted null vectors on the
+// boundary of the damped interval, where they are not separated from the negative spectrum; the cut then moves
+// GCCB_CF_MARGIN below theta_k.  Only for theta_k < GCCB_CF_MARGIN_BELOW: the degenerate cluster of hub ego-nets
+// (1/sqrt 2) is wider than any block and must not drag the cut down.
+#define GCCB_CF_MARGIN 0.05f
+#define GCCB_CF_MARGIN_BELOW 0.25f
 #ifndef GCCB_CF_SWEEPS0
 #define GCCB_CF_SWEEPS0 1          // Jacobi sweeps of the first Ritz solve (it only conditions the random block)
 #endif
@@ -591,8 +606,9 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
   for (; iter < GCCB_CF_MAXIT && !converged; ++iter) {
     // ---- Chebyshev filter on [-1, cut] (scaled three-term recurrence) -----------------------------
     {
-      const int deg = iter == 0 ? GCCB_CF_DEG0 : GCCB_CF_DEG;
       const float e = (cut + 1.0f) * 0.5f, cen = (cut - 1.0f) * 0.5f;
+      int deg = (int)floorf(GCCB_CF_LOGGAIN / acoshf((3.0f - cut) / (1.0f + cut)));
+      deg = max(4, min(iter == 0 ? GCCB_CF_DEG0 : GCCB_CF_DEG, deg));
       float sigma = e / (1.0f - cen);
       const float sigma1 = sigma;
       spmm_cheb(S, X, Y, ld, sigma1 / e, cen, 0.f);                           // Y1
@@ -764,9 +780,10 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
       });
     }
     if (tid == 0) {
-      float w = 0.f, lo = theta[0];
-      for (int c = 0; c < k; ++c) w = fmaxf(w, resid[c]);
+      float w = 0.f, lo = theta[0], tk = theta[0];
+      for (int c = 0; c < k; ++c) { w = fmaxf(w, resid[c]); tk = fminf(tk, theta[c]); }
       for (int i = 1; i < CB; ++i) lo = fminf(lo, theta[i]);
+      if (tk < GCCB_CF_MARGIN_BELOW) lo = fminf(lo, tk - GCCB_CF_MARGIN);
       s_bc[0] = sqrtf(w);
       s_bc[1] = lo;
     }
@@ -1072,8 +1089,9 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
   int iter = 0;
   for (; iter < GCCB_CF_MAXIT && !converged; ++iter) {
     {   // ---- Chebyshev filter ---------------------------------------------------------------------
-      const int deg = iter == 0 ? GCCB_CF_DEG0 : GCCB_CF_DEG;
       const float e = (cut + 1.0f) * 0.5f, cen = (cut - 1.0f) * 0.5f;
+      int deg = (int)floorf(GCCB_CF_LOGGAIN / acoshf((3.0f - cut) / (1.0f + cut)));
+      deg = max(4, min(iter == 0 ? GCCB_CF_DEG0 : GCCB_CF_DEG, deg));
       float sigma = e / (1.0f - cen);
       const float sigma1 = sigma;
       cl_spmm(C, X, Y, sigma1 / e, cen, 0.f);
@@ -1227,9 +1245,10 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       });
     }
     if (tid == 0) {
-      float w = 0.f, lo = theta[0];
-      for (int c = 0; c < k; ++c) w = fmaxf(w, resid[c]);
+      float w = 0.f, lo = theta[0], tk = theta[0];
+      for (int c = 0; c < k; ++c) { w = fmaxf(w, resid[c]); tk = fminf(tk, theta[c]); }
       for (int i = 1; i < CB; ++i) lo = fminf(lo, theta[i]);
+      if (tk < GCCB_CF_MARGIN_BELOW) lo = fminf(lo, tk - GCCB_CF_MARGIN);
       s_bc[0] = sqrtf(w);
       s_bc[1] = lo;
     }

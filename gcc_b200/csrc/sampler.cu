@@ -12,8 +12,11 @@
 // then all traces are walked in parallel (dependent-load depth = longest single
 // trace, not the whole budget).  The visited list is bitonic-sorted / uniqued in
 // shared memory; induction streams each visited vertex's neighbour list with
-// coalesced warp loads and binary-searches the shared-memory frontier.  Batching
-// is a two-pass count / scan / fill so the output layout is deterministic.
+// coalesced warp loads and binary-searches the shared-memory frontier.  Every neighbour
+// list is read ONCE: the local ids of the hits are parked in a scratch pool while the induced
+// degrees are counted, the per-view scan fixes the (deterministic) output layout, and the fill
+// kernel only copies pool -> batched CSR (rows with more than 128 induced neighbours -- the seed
+// row of a large ego-net -- are the exception: counted first, recorded on a second look).
 #include "common.cuh"
 
 namespace gccb {
@@ -64,6 +67,7 @@ __device__ __forceinline__ bool adj_find(const int32_t* __restrict__ indices, in
                                // vertices, ~1e5..1e6 neighbour probes) are the tail of these kernels
 #endif
 #define GCCB_SW (GCCB_ST / 32)
+#define GCCB_HIT_STAGE 128     // hits of one row parked in shared memory before their pool slot is known
 
 // Pass 1: walk + sort/unique + induced-degree count.  grid = 2B, block = GCCB_ST.
 // dyn smem: keys[P] ints, P = pow2 >= max_budget + HOPCAP.
@@ -73,9 +77,12 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
                        uint32_t restart_thresh, uint64_t key, const int64_t* __restrict__ seeds,
                        const int64_t* __restrict__ sample_ids, int B, int cap_n,
                        int32_t* __restrict__ subv_scratch, int32_t* __restrict__ subdeg_scratch,
+                       int32_t* __restrict__ rowstart_scratch, int32_t* __restrict__ pool, int pool_cap,
+                       int32_t* __restrict__ pool_counter,
                        int64_t* __restrict__ counters, int32_t* __restrict__ flags) {
   GCCB_DYN_SMEM(int, keys);
   __shared__ int scan_scratch[33];
+  __shared__ int stage[GCCB_SW][GCCB_HIT_STAGE];      // per-warp parking of one row's hits
   __shared__ int s_tstar, s_m;
   __shared__ unsigned long long s_sumdeg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -172,25 +179,79 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
   for (int i = tid; i < n; i += GCCB_ST) keys[i] = subv[i];
   __syncthreads();
 
-  // ---- phase D: induced degree of every ego-net vertex (warp per vertex) ---------------
+  // ---- phase D: induced neighbours of every ego-net vertex (warp per vertex), ONE look at each list ------
+  // Hits (local ids, in the order a scan of adj(v) meets them) are parked per warp, then moved to a slot of
+  // the scratch pool claimed with one atomic per row; the fill kernel copies pool -> batched CSR.
   int32_t* subdeg = subdeg_scratch + (size_t)slot * cap_n;
+  int32_t* rowstart = rowstart_scratch + (size_t)slot * cap_n;
+  int* wstage = stage[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
   int m_local = 0;
   unsigned long long sumdeg_local = 0ull;
+  int sr = 0;                                            // rank of the seed among the sorted non-seed keys
+  {
+    int lo = 1, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < seed) lo = mid + 1; else hi = mid; }
+    sr = lo - 1;
+  }
   for (int i = warp; i < n; i += GCCB_SW) {
     const int64_t v = keys[i];
     const int64_t beg = indptr[v], end = indptr[v + 1];
-    int cnt = 0;
-    if (end - beg > (int64_t)GCCB_REVERSE_FACTOR * n) {
-      for (int j = lane; j < n; j += 32) cnt += adj_find(indices, beg, end, keys[j]);
-    } else {
-      for (int64_t e = beg + lane; e < end; e += 32) {
-        int u = indices[e];
-        cnt += local_id(keys, n, seed, u) >= 0;
+    const bool reverse = end - beg > (int64_t)GCCB_REVERSE_FACTOR * n;
+    int pos = 0, cnt = 0;
+    // round 0 parks the hits; round 1 (only for rows with more than GCCB_HIT_STAGE hits) writes them to the pool
+    for (int round = 0; round < 2; ++round) {
+      int w = 0;
+      if (reverse) {
+        // hub row: probe adj(v) for every ego-net vertex in ascending parent id (= the order a scan of
+        // adj(v) would meet them): keys[1..n) is ascending, the seed (local id 0) is spliced in at rank sr
+        for (int t0 = 0; t0 < n; t0 += 32) {
+          const int t = t0 + lane;
+          int j = -1;
+          if (t < n) {
+            const int loc = t < sr ? t + 1 : (t == sr ? 0 : t);
+            if (adj_find(indices, beg, end, keys[loc])) j = loc;
+          }
+          const unsigned hit = __ballot_sync(0xffffffffu, j >= 0);
+          if (j >= 0) {
+            const int q = w + __popc(hit & lt_mask);
+            if (round == 1) pool[pos + q] = j;
+            else if (q < GCCB_HIT_STAGE) wstage[q] = j;
+          }
+          w += __popc(hit);
+        }
+      } else {
+        for (int64_t e0 = beg; e0 < end; e0 += 32) {
+          const int64_t e = e0 + lane;
+          int j = -1;
+          if (e < end) j = local_id(keys, n, seed, indices[e]);
+          const unsigned hit = __ballot_sync(0xffffffffu, j >= 0);
+          if (j >= 0) {
+            const int q = w + __popc(hit & lt_mask);
+            if (round == 1) pool[pos + q] = j;
+            else if (q < GCCB_HIT_STAGE) wstage[q] = j;
+          }
+          w += __popc(hit);
+        }
+      }
+      if (round == 1) break;
+      cnt = w;
+      if (lane == 0) {
+        pos = cnt > 0 ? atomicAdd(pool_counter, cnt) : 0;
+        if (pos + cnt > pool_cap) pos = -1;               // pool exhausted: the fill kernel looks again itself
+      }
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (pos < 0) break;
+      if (cnt <= GCCB_HIT_STAGE) {
+        __syncwarp();
+        for (int q = lane; q < cnt; q += 32) pool[pos + q] = wstage[q];
+        break;
       }
     }
-    cnt = warp_sum_i(cnt);
+    __syncwarp();                                          // wstage is reused by the next row
     if (lane == 0) {
       subdeg[i] = cnt;
+      rowstart[i] = pos;
       m_local += cnt;
       sumdeg_local += (unsigned long long)(end - beg);
     }
@@ -250,7 +311,8 @@ __global__ void __launch_bounds__(GCCB_ST)
 induce_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                    const int64_t* __restrict__ counters, int B, int cap_n, int node_cap,
                    int edge_cap, const int32_t* __restrict__ subv_scratch,
-                   const int32_t* __restrict__ subdeg_scratch,
+                   const int32_t* __restrict__ subdeg_scratch, const int32_t* __restrict__ rowstart_scratch,
+                   const int32_t* __restrict__ pool,
                    int32_t* __restrict__ node_off, const int32_t* __restrict__ edge_off,
                    int32_t* __restrict__ out_indptr, int32_t* __restrict__ out_indices,
                    int32_t* __restrict__ out_subdeg, int32_t* __restrict__ out_graph_id,
@@ -267,6 +329,7 @@ induce_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
   const int eoff = edge_off[view * (B + 1) + g];
   const int32_t* subv = subv_scratch + (size_t)slot * cap_n;
   const int32_t* subdeg = subdeg_scratch + (size_t)slot * cap_n;
+  const int32_t* rowstart = rowstart_scratch + (size_t)slot * cap_n;
   int32_t* v_indptr = out_indptr + (size_t)view * (node_cap + 1);
   int32_t* v_indices = out_indices + (size_t)view * edge_cap;
   const size_t nb = (size_t)view * node_cap;
@@ -290,9 +353,16 @@ induce_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
   if (g == B - 1 && tid == 0) v_indptr[noff + n] = eoff + run;   // closing entry = E_v
   __syncthreads();                                               // keys[] + v_indptr visible
   for (int i = warp; i < n; i += GCCB_SW) {
+    int wpos = v_indptr[noff + i];
+    const int rs = rowstart[i];
+    if (rs >= 0) {                                       // the walk kernel parked this row's hits: copy
+      const int d = subdeg[i];
+      for (int q = lane; q < d; q += 32) v_indices[wpos + q] = noff + pool[rs + q];
+      continue;
+    }
+    // (pool exhausted while this row was counted: look at its neighbour list again)
     const int64_t v = keys[i];
     const int64_t beg = indptr[v], end = indptr[v + 1];
-    int wpos = v_indptr[noff + i];
     if (end - beg > (int64_t)GCCB_REVERSE_FACTOR * n) {
       // candidates in ascending parent id = the order a scan of adj(v) would meet them:
       // keys[1..n) is ascending, the seed (local id 0) is spliced in at its rank sr
@@ -342,11 +412,12 @@ extern "C" int gccb_draw_seeds(const double* cdf, int64_t n_nodes, uint64_t key,
   return check_launch("draw_seeds_kernel");
 }
 
-// workspace layout: subv[2B][cap_n] | subdeg[2B][cap_n]
+// workspace layout: subv[2B][cap_n] | subdeg[2B][cap_n] | rowstart[2B][cap_n] | pool counter (16 ints) | pool[2*edge_cap]
 static int sampler_cap_n(int max_budget) { return (max_budget + (int)GCCB_HOPCAP + 1 + 3) & ~3; }
 
-extern "C" size_t gccb_sample_batch_workspace(int32_t batch, int32_t max_budget) {
-  return (size_t)2 * (size_t)(2 * batch) * (size_t)sampler_cap_n(max_budget) * sizeof(int32_t);
+extern "C" size_t gccb_sample_batch_workspace(int32_t batch, int32_t max_budget, int32_t edge_cap) {
+  return ((size_t)3 * (size_t)(2 * batch) * (size_t)sampler_cap_n(max_budget) + 16 + (size_t)2 * (size_t)edge_cap) *
+         sizeof(int32_t);
 }
 
 extern "C" int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds,
@@ -359,7 +430,7 @@ extern "C" int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds
   }
   const int B = batch->batch;
   const int cap_n = sampler_cap_n(graph->max_budget);
-  if (workspace_bytes < gccb_sample_batch_workspace(B, graph->max_budget)) {
+  if (workspace_bytes < gccb_sample_batch_workspace(B, graph->max_budget, batch->edge_cap)) {
     set_last_error("gccb_sample_batch: workspace too small");
     return GCCB_ERR_CAPACITY;
   }
@@ -372,6 +443,11 @@ extern "C" int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds
   }
   int32_t* subv = (int32_t*)workspace;
   int32_t* subdeg = subv + (size_t)2 * B * cap_n;
+  int32_t* rowstart = subdeg + (size_t)2 * B * cap_n;
+  int32_t* pool_counter = rowstart + (size_t)2 * B * cap_n;
+  int32_t* pool = pool_counter + 16;
+  const int pool_cap = 2 * batch->edge_cap;
+  cudaMemsetAsync(pool_counter, 0, sizeof(int32_t), (cudaStream_t)stream);
   auto k1 = rwr_walk_unique_kernel;
   auto k3 = induce_fill_kernel;
   if (smem > 48 * 1024) {
@@ -380,11 +456,11 @@ extern "C" int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds
   }
   GCCB_LAUNCH(k1, 2 * B, GCCB_ST, smem, stream, graph->indptr, graph->indices, graph->budget_table,
               graph->budget_table_len, graph->restart_thresh, graph->key, seeds, sample_ids, B,
-              cap_n, subv, subdeg, batch->counters, batch->flags);
+              cap_n, subv, subdeg, rowstart, pool, pool_cap, pool_counter, batch->counters, batch->flags);
   GCCB_LAUNCH(batch_offsets_kernel, 2, 256, 0, stream, batch->counters, B, batch->node_cap,
               batch->edge_cap, batch->node_off, batch->edge_off, batch->flags);
   GCCB_LAUNCH(k3, 2 * B, GCCB_ST, smem, stream, graph->indptr, graph->indices, batch->counters, B,
-              cap_n, batch->node_cap, batch->edge_cap, subv, subdeg, batch->node_off,
+              cap_n, batch->node_cap, batch->edge_cap, subv, subdeg, rowstart, pool, batch->node_off,
               batch->edge_off, batch->indptr, batch->indices, batch->sub_deg, batch->graph_id,
               batch->orig_id);
   return check_launch("gccb_sample_batch");

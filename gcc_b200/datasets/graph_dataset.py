@@ -112,7 +112,7 @@ class BatchBuffers:
         self.eigvals = torch.zeros(2 * B, pos_dim, dtype=torch.float32, device=device)
         self.seeds = torch.zeros(B, dtype=torch.int64, device=device)
         self.sample_ids = torch.zeros(B, dtype=torch.int64, device=device)
-        self.ws_sample = torch.zeros(max(lib.gccb_sample_batch_workspace(B, max_budget), 8),
+        self.ws_sample = torch.zeros(max(lib.gccb_sample_batch_workspace(B, max_budget, edge_cap), 8),
                                      dtype=torch.uint8, device=device)
         self.ws_posenc = torch.zeros(max(lib.gccb_posenc_workspace(B, node_cap), 8),
                                      dtype=torch.uint8, device=device)

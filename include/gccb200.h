@@ -102,7 +102,7 @@ int gccb_draw_seeds(const double* cdf, int64_t n_nodes, uint64_t key, int64_t fi
  * _rwr_trace_to_dgl_graph's unique/sort/subgraph (data_util.py:218-239) and
  * dgl.batch (data_util.py:29) for both views of `batch->batch` samples.
  * seeds/sample_ids: [B] (both views start from the same seed: step_dist=[1,0,0]).     */
-size_t gccb_sample_batch_workspace(int32_t batch, int32_t max_budget);
+size_t gccb_sample_batch_workspace(int32_t batch, int32_t max_budget, int32_t edge_cap);
 int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds,
                       const int64_t* sample_ids, const gccb_batch_t* batch, void* workspace,
                       size_t workspace_bytes, gccb_stream_t stream);
