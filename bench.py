@@ -320,6 +320,10 @@ def run_ours(args, cfg):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     eng.count_acc = torch.zeros(4, dtype=torch.float64, device=dev)   # algorithmic-byte counters (device side)
     eng.timing = []
+    for i in range(2):              # the diagnostics above use torch kernels / timed events the warm-up never
+        eng.step(lr=lr_at(eng.global_step))   # launched: CUDA loads them lazily (tens of ms) -- not inside the window
+    eng.count_acc.zero_()
+    eng.timing = []
     launches0 = lib.gccb_launch_count()
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()

@@ -32,7 +32,7 @@ class GinCfg(C.Structure):
     _fields_ = [("num_layers", C.c_int32), ("hidden", C.c_int32), ("pos_dim", C.c_int32),
                 ("deg_dim", C.c_int32), ("max_degree", C.c_int32), ("norm", C.c_int32),
                 ("bn_eps", C.c_float), ("bn_momentum", C.c_float), ("norm_eps", C.c_float),
-                ("dropout_p", C.c_float)]
+                ("dropout_p", C.c_float), ("tensor_cores", C.c_int32), ("_pad", C.c_int32)]
 
 
 class GinLayout(C.Structure):

@@ -10,6 +10,10 @@
 // Adjacency is assumed symmetric (the reference's input contract, gcc/utils/x2dgl.py:40-62),
 // so the transpose aggregation is the same gather as the forward.
 #include "gin_common.cuh"
+#include "tc_gemm.cuh"
+#ifndef GCCB_EMU
+#include <cuda_bf16.h>
+#endif
 
 namespace gccb {
 
@@ -17,7 +21,11 @@ namespace gccb {
 
 struct BwdLayout {            // byte offsets in the backward workspace
   size_t dh, g1[2], dz2[2], da, red, dS, dpool, part, total;   // g1/dz2 alternate between layers
+  // tensor-core path: bf16 operand of the input-gradient GEMMs, two transposed bf16 operands of the weight-
+  // gradient GEMMs ([W][cap_pad]), per-layer BatchNorm-1 coefficients (sc | sh) and the split-K partials
+  size_t dz16, tA, tB, coef1, splitk;
   int DW;                     // width of dh / da rows = max(H, 64)
+  int cap_pad, splits;
 };
 
 inline BwdLayout make_bwd_layout(const GinDims& d, int B, int node_cap) {
@@ -35,6 +43,22 @@ inline BwdLayout make_bwd_layout(const GinDims& d, int B, int node_cap) {
   b.dS = take((size_t)d.L * B * d.H * 4);
   b.dpool = take((size_t)d.L * B * b.DW * 4);
   b.part = take((size_t)GCCB_WG_CHUNKS * ((size_t)d.H * b.DW + d.H) * 4);
+  b.dz16 = b.tA = b.tB = b.coef1 = b.splitk = 0;
+  b.cap_pad = (node_cap + 63) & ~63;
+  b.splits = 0;
+#ifndef GCCB_EMU
+  if (d.tc) {
+    b.dz16 = take((size_t)node_cap * d.H * 2);
+    b.tA = take((size_t)d.H * b.cap_pad * 2);
+    b.tB = take((size_t)b.DW * b.cap_pad * 2);
+    b.coef1 = take((size_t)(d.L - 1) * 2 * d.H * 4);
+    const int tiles = (d.H / 128) * 1;                      // 128-row output tiles of a [H x <=256] weight gradient
+    b.splits = 148 / tiles;
+    if (b.splits > b.cap_pad / 64) b.splits = b.cap_pad / 64;
+    if (b.splits < 1) b.splits = 1;
+    b.splitk = take((size_t)b.splits * d.H * b.DW * 4);
+  }
+#endif
   b.total = off;
   return b;
 }
@@ -710,6 +734,247 @@ static int run_backward(const BwdArgs& a) {
   return check_launch("gccb_gin_backward");
 }
 
+
+#ifndef GCCB_EMU
+// ================================================================================================
+// Tensor-core backward (cfg.tensor_cores, hidden >= 128): the four GEMMs of a layer -- dx1 = dz2 W2,
+// da = dz1 W1, dW2 = dz2^T x1, dW1 = dz1^T a -- run on tcgen05 (csrc/tc_gemm.cu); the BatchNorm-backward
+// chains between them are the same arithmetic as the SIMT kernels above, as elementwise passes that also
+// emit the bf16 operand of the next GEMM.  The biases of the two Linear layers feed train-mode BatchNorms:
+// their true gradient is exactly zero (the SIMT path computes rounding noise ~1e-9 there); this path adds
+// nothing to them.
+
+// dz2 = BN_a backward of g3 (fp32 stash for the weight gradient + bf16 GEMM operand); block 0 also leaves the
+// BatchNorm-1 coefficients (sc | sh) of this layer for the transposed cast of x1 = relu(bn1(z1)).
+template <int H>
+__global__ void __launch_bounds__(256)
+gin_bwd_dz2_kernel(const int32_t* __restrict__ node_off_v, int B, const float* __restrict__ z2,
+                   const float* __restrict__ dh, const double* __restrict__ sums_1, const float* __restrict__ g1w,
+                   const float* __restrict__ be1, const double* __restrict__ sums_a, const float* __restrict__ ga,
+                   const float* __restrict__ bea, const double* __restrict__ sums_b, const float* __restrict__ gb,
+                   const float* __restrict__ beb, float bn_eps, const double* __restrict__ redB,
+                   const double* __restrict__ redA, float* __restrict__ dz2_out, __nv_bfloat16* __restrict__ dz16,
+                   float* __restrict__ coef1_out) {
+  __shared__ float coef[12 * H];
+  __shared__ float rmean[4 * H];
+  const int N = node_off_v[B];
+  const int tid = threadIdx.x;
+  bn_prepare(sums_1, N, H, g1w, be1, bn_eps, coef, coef + H, coef + 2 * H, coef + 3 * H, nullptr, false, false, 0.f);
+  bn_prepare(sums_a, N, H, ga, bea, bn_eps, coef + 4 * H, coef + 5 * H, coef + 6 * H, coef + 7 * H, nullptr, false, false, 0.f);
+  bn_prepare(sums_b, N, H, gb, beb, bn_eps, coef + 8 * H, coef + 9 * H, coef + 10 * H, coef + 11 * H, nullptr, false, false, 0.f);
+  const double invN = N > 0 ? 1.0 / (double)N : 0.0;
+  for (int c = tid; c < H; c += 256) {
+    rmean[c] = (float)(redB[c] * invN);
+    rmean[H + c] = (float)(redB[H + c] * invN);
+    rmean[2 * H + c] = (float)(redA[c] * invN);
+    rmean[3 * H + c] = (float)(redA[H + c] * invN);
+  }
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int c = tid; c < H; c += 256) { coef1_out[c] = coef[2 * H + c]; coef1_out[H + c] = coef[3 * H + c]; }
+  const BnC A = bnc(coef + 4 * H, H), Bc = bnc(coef + 8 * H, H);
+  const size_t total = (size_t)(N > 0 ? N : 0) * H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H);
+    float ya, yhat, g4;
+    const float zv = z2[i];
+    chain_g4(zv, dh[i], A, Bc, c, &ya, &yhat, &g4);
+    const float dy = Bc.sc[c] * (g4 - rmean[c] - yhat * rmean[H + c]);
+    const float g3 = ya > 0.f ? dy : 0.f;
+    const float z2hat = (zv - A.mean[c]) * A.invstd[c];
+    const float dz = A.sc[c] * (g3 - rmean[2 * H + c] - z2hat * rmean[3 * H + c]);
+    dz2_out[i] = dz;
+    dz16[i] = __float2bfloat16_rn(dz);
+  }
+}
+
+// g1 = [bn1(z1) > 0] dx1 in place; column sums of g1 and g1 * z1hat (BatchNorm-1 backward reductions)
+template <int H>
+__global__ void __launch_bounds__(256)
+gin_bwd_g1_kernel(const int32_t* __restrict__ node_off_v, int B, const float* __restrict__ z1,
+                  float* __restrict__ dx1_g1, const double* __restrict__ sums_1, const float* __restrict__ g1w,
+                  const float* __restrict__ be1, float bn_eps, double* __restrict__ red1_out) {
+  __shared__ float coef[4 * H];
+  __shared__ float red[2 * 8 * H];
+  const int N = node_off_v[B];
+  const int tid = threadIdx.x;
+  bn_prepare(sums_1, N, H, g1w, be1, bn_eps, coef, coef + H, coef + 2 * H, coef + 3 * H, nullptr, false, false, 0.f);
+  __syncthreads();
+  const BnC C1 = bnc(coef, H);
+  constexpr int RPB = 256 / H > 0 ? 256 / H : 1;
+  const int c = tid % H, rl = tid / H;
+  float s = 0.f, q = 0.f;
+  for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
+    const size_t i = (size_t)r * H + c;
+    const float zv = z1[i];
+    const float pre = fmaf(zv, C1.sc[c], C1.sh[c]);
+    const float g = pre > 0.f ? dx1_g1[i] : 0.f;
+    dx1_g1[i] = g;
+    s += g;
+    q = fmaf(g, (zv - C1.mean[c]) * C1.invstd[c], q);
+  }
+  red[(0 * RPB + rl) * H + c] = s;
+  red[(RPB + rl) * H + c] = q;
+  __syncthreads();
+  for (int idx = tid; idx < 2 * H; idx += 256) {
+    const int which = idx / H, cc = idx - which * H;
+    float t = 0.f;
+    for (int j = 0; j < RPB; ++j) t += red[(which * RPB + j) * H + cc];
+    atomicAdd(&red1_out[which * H + cc], (double)t);
+  }
+}
+
+// dz1 = BN_1 backward of g1 (in place, fp32) + bf16 GEMM operand
+template <int H>
+__global__ void __launch_bounds__(256)
+gin_bwd_dz1_kernel(const int32_t* __restrict__ node_off_v, int B, const float* __restrict__ z1,
+                   float* __restrict__ g1_dz1, const double* __restrict__ sums_1, const float* __restrict__ g1w,
+                   const float* __restrict__ be1, float bn_eps, const double* __restrict__ red1,
+                   __nv_bfloat16* __restrict__ dz16) {
+  __shared__ float coef[4 * H];
+  __shared__ float rmean[2 * H];
+  const int N = node_off_v[B];
+  const int tid = threadIdx.x;
+  bn_prepare(sums_1, N, H, g1w, be1, bn_eps, coef, coef + H, coef + 2 * H, coef + 3 * H, nullptr, false, false, 0.f);
+  const double invN = N > 0 ? 1.0 / (double)N : 0.0;
+  for (int c = tid; c < H; c += 256) {
+    rmean[c] = (float)(red1[c] * invN);
+    rmean[H + c] = (float)(red1[H + c] * invN);
+  }
+  __syncthreads();
+  const BnC C1 = bnc(coef, H);
+  const size_t total = (size_t)(N > 0 ? N : 0) * H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H);
+    const float zhat = (z1[i] - C1.mean[c]) * C1.invstd[c];
+    const float dz = C1.sc[c] * (g1_dz1[i] - rmean[c] - zhat * rmean[H + c]);
+    g1_dz1[i] = dz;
+    dz16[i] = __float2bfloat16_rn(dz);
+  }
+}
+
+template <int H>
+static int run_backward_tc(const BwdArgs& a) {
+  const GinDims& d = a.d;
+  const int B = a.batch->batch, cap = a.batch->node_cap;
+  const int32_t* node_off_v = a.batch->node_off + (size_t)a.view * (B + 1);
+  const int32_t* n_dev = node_off_v + B;
+  const int32_t* indptr = a.batch->indptr + (size_t)a.view * (cap + 1);
+  const int32_t* indices = a.batch->indices + (size_t)a.view * a.batch->edge_cap;
+  const int32_t* sub_deg = a.batch->sub_deg + (size_t)a.view * cap;
+  const int32_t* graph_id = a.batch->graph_id + (size_t)a.view * cap;
+  const double* stats = (const double*)(a.acts + a.al.stats);
+  float* dh = (float*)(a.ws + a.bl.dh);
+  float* da = (float*)(a.ws + a.bl.da);
+  double* red = (double*)(a.ws + a.bl.red);
+  float* dS = (float*)(a.ws + a.bl.dS);
+  float* dpool = (float*)(a.ws + a.bl.dpool);
+  __nv_bfloat16* dz16 = (__nv_bfloat16*)(a.ws + a.bl.dz16);
+  __nv_bfloat16* tA = (__nv_bfloat16*)(a.ws + a.bl.tA);
+  __nv_bfloat16* tB = (__nv_bfloat16*)(a.ws + a.bl.tB);
+  float* coef1 = (float*)(a.ws + a.bl.coef1);
+  float* splitk = (float*)(a.ws + a.bl.splitk);
+  const float* P = a.params;
+  float* G = a.grads;
+  const int DW = a.bl.DW, capP = a.bl.cap_pad;
+  const int tiles = (cap + GCCB_TILE_ROWS - 1) / GCCB_TILE_ROWS;
+  const int grid = tiles < 592 ? tiles : 592;
+  const uint32_t keep = (uint32_t)fmin((1.0 - (double)d.drop_p) * 4294967296.0, 4294967295.0);
+  StreamKit* kit = stream_kit((cudaStream_t)a.stream, 1);
+  cudaStream_t main_s = (cudaStream_t)a.stream;
+  cudaStream_t side = kit->side[0];
+  cudaEvent_t* ev_main = kit->ev;
+  cudaEvent_t* ev_side = kit->ev + 8;
+  cudaEvent_t ev_head = kit->ev[16], ev_join = kit->ev[17];
+  cudaMemsetAsync(red, 0, (size_t)(d.L - 1) * 3 * 2 * H * sizeof(double), main_s);
+  auto kpb = gin_pool_predict_bwd_kernel<H>;
+  GCCB_LAUNCH(kpb, B, 256, 0, a.stream, d, node_off_v, B, P, a.lay, (const float*)(a.acts + a.al.score),
+              a.dfeat, a.drop_key, a.drop_step, a.drop_base, keep, DW, dS, dpool);
+  cudaEventRecord(ev_head, main_s);
+  cudaStreamWaitEvent(side, ev_head, 0);
+  {
+    int maxout = H * (d.din > H ? d.din : H) + H;
+    dim3 gr((maxout + 255) / 256, d.L);
+    GCCB_LAUNCH(gin_pred_wgrad_kernel, gr, 256, 0, side, d, B, a.lay, (const float*)dS,
+                (const float*)(a.acts + a.al.pooled), a.al.PW, G);
+  }
+  for (int l = d.L - 2; l >= 0; --l) {
+    float* g1 = (float*)(a.ws + a.bl.g1[l & 1]);
+    float* dz2 = (float*)(a.ws + a.bl.dz2[l & 1]);
+    const int j = l + 1;
+    const float* z1 = (const float*)(a.acts + a.al.z1[l]);
+    const float* z2 = (const float*)(a.acts + a.al.z2[l]);
+    const float* a_l = (const float*)(a.acts + a.al.a[l]);
+    const double* s1 = stats + (size_t)(l * 3 + 0) * 2 * H;
+    const double* sa = stats + (size_t)(l * 3 + 1) * 2 * H;
+    const double* sb = stats + (size_t)(l * 3 + 2) * 2 * H;
+    double* r1 = red + (size_t)(l * 3 + 0) * 2 * H;
+    double* rA = red + (size_t)(l * 3 + 1) * 2 * H;
+    double* rB = red + (size_t)(l * 3 + 2) * 2 * H;
+    const int KW = gin_kw(d, l), inf = gin_in_features(d, l);
+    const __nv_bfloat16* w1b = (const __nv_bfloat16*)(a.acts + a.al.w16[l]);
+    const __nv_bfloat16* w1t = w1b + (size_t)H * KW + (size_t)H * H;
+    const __nv_bfloat16* w2t = w1t + (size_t)KW * H;
+    float* c1 = coef1 + (size_t)l * 2 * H;
+    auto kdh = gin_bwd_dh_kernel<H>;
+    GCCB_LAUNCH(kdh, grid, 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id,
+                (const float*)(dpool + (size_t)j * B * DW), DW, (const float*)da, j < d.L - 1 ? 1 : 0, dh);
+    auto kred = gin_bwd_reduce_kernel<H>;
+    GCCB_LAUNCH(kred, grid, 256, 0, a.stream, 0, node_off_v, B, z2, (const float*)dh, sa, P + a.lay.bna_w[l],
+                P + a.lay.bna_b[l], sb, P + a.lay.bnb_w[l], P + a.lay.bnb_b[l], d.bn_eps, (const double*)rB, rB);
+    GCCB_LAUNCH(kred, grid, 256, 0, a.stream, 1, node_off_v, B, z2, (const float*)dh, sa, P + a.lay.bna_w[l],
+                P + a.lay.bna_b[l], sb, P + a.lay.bnb_w[l], P + a.lay.bnb_b[l], d.bn_eps, (const double*)rB, rA);
+    if (l + 2 <= d.L - 2) cudaStreamWaitEvent(main_s, ev_side[l + 2], 0);   // g1 / dz2 [l&1] free again
+    // the side stream of the layer above still reads dz16's transposed copies, not dz16 itself: no wait needed
+    auto kz2 = gin_bwd_dz2_kernel<H>;
+    GCCB_LAUNCH(kz2, grid, 256, 0, a.stream, node_off_v, B, z2, (const float*)dh, s1, P + a.lay.bn1_w[l],
+                P + a.lay.bn1_b[l], sa, P + a.lay.bna_w[l], P + a.lay.bna_b[l], sb, P + a.lay.bnb_w[l],
+                P + a.lay.bnb_b[l], d.bn_eps, (const double*)rB, (const double*)rA, dz2, dz16, c1);
+    int rc = tc::gemm_bf16(dz16, w2t, cap, H, H, n_dev, nullptr, 1.0f, g1, nullptr, H, nullptr, 1, nullptr, main_s);
+    if (rc) return rc;
+    auto kg1 = gin_bwd_g1_kernel<H>;
+    GCCB_LAUNCH(kg1, grid, 256, 0, a.stream, node_off_v, B, z1, g1, s1, P + a.lay.bn1_w[l], P + a.lay.bn1_b[l],
+                d.bn_eps, r1);
+    auto kz1 = gin_bwd_dz1_kernel<H>;
+    GCCB_LAUNCH(kz1, grid, 256, 0, a.stream, node_off_v, B, z1, g1, s1, P + a.lay.bn1_w[l], P + a.lay.bn1_b[l],
+                d.bn_eps, (const double*)r1, dz16);
+    rc = tc::gemm_bf16(dz16, w1t, cap, KW, H, n_dev, nullptr, 1.0f, da, nullptr, KW, nullptr, 1, nullptr, main_s);
+    if (rc) return rc;
+    cudaEventRecord(ev_main[l], main_s);
+    cudaStreamWaitEvent(side, ev_main[l], 0);
+    // weight gradients on the side stream: transposed bf16 operands, split-K over the rows, fixed-order reduce
+    rc = tc::cast_bf16(dz2, cap, H, H, tA, capP, H, 1, n_dev, side);
+    if (!rc) rc = tc::cast_bf16(z1, cap, H, H, tB, capP, H, 1, n_dev, side, c1, c1 + H, 1);      // x1^T
+    if (!rc) rc = tc::gemm_bf16(tA, tB, H, H, capP, nullptr, nullptr, 1.0f, G + a.lay.w2[l], nullptr, H, nullptr,
+                                a.bl.splits, splitk, side, 1.0f, H);
+    if (!rc) rc = tc::cast_bf16(g1, cap, H, H, tA, capP, H, 1, n_dev, side);                       // dz1^T
+    if (!rc) rc = tc::cast_bf16(a_l, cap, KW, KW, tB, capP, KW, 1, n_dev, side);                   // a^T
+    if (!rc) rc = tc::gemm_bf16(tA, tB, H, KW, capP, nullptr, nullptr, 1.0f, G + a.lay.w1[l], nullptr, inf, nullptr,
+                                a.bl.splits, splitk, side, 1.0f, inf);
+    if (rc) return rc;
+    GCCB_LAUNCH(gin_bn_grads_kernel, (H + 127) / 128, 128, 0, side, H, (const double*)rB,
+                G + a.lay.bnb_w[l], G + a.lay.bnb_b[l]);
+    GCCB_LAUNCH(gin_bn_grads_kernel, (H + 127) / 128, 128, 0, side, H, (const double*)rA,
+                G + a.lay.bna_w[l], G + a.lay.bna_b[l]);
+    GCCB_LAUNCH(gin_bn_grads_kernel, (H + 127) / 128, 128, 0, side, H, (const double*)r1,
+                G + a.lay.bn1_w[l], G + a.lay.bn1_b[l]);
+    cudaEventRecord(ev_side[l], side);
+  }
+  auto kdh0 = gin_bwd_dh_kernel<GCCB_DINP>;
+  GCCB_LAUNCH(kdh0, grid, 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id, (const float*)dpool, DW,
+              (const float*)da, 1, dh);
+  {
+    size_t sm = (size_t)(d.maxdeg + 1) * d.D * sizeof(float);
+    auto k = gin_bwd_emb_kernel;
+    gccb::ensure_dyn_smem(k, sm);
+    GCCB_LAUNCH(k, 64, 256, sm, a.stream, d, node_off_v, B, sub_deg, (const float*)dh, G + a.lay.emb);
+  }
+  cudaEventRecord(ev_join, side);
+  cudaStreamWaitEvent(main_s, ev_join, 0);
+  return check_launch("gccb_gin_backward (tensor cores)");
+}
+#endif  // !GCCB_EMU
+
 }  // namespace gccb
 
 using namespace gccb;
@@ -743,6 +1008,9 @@ extern "C" int gccb_gin_backward(const gccb_gin_cfg_t* cfg, const gccb_batch_t* 
   a.grads = grads; a.ws = (char*)workspace; a.stream = stream;
   // the forward's dropout mask is re-derived from the same Philox counters
   a.drop_key = dropout_key; a.drop_step = dropout_step; a.drop_base = dropout_layer_base;
+#ifndef GCCB_EMU
+  if (a.d.tc) return a.d.H == 128 ? run_backward_tc<128>(a) : run_backward_tc<256>(a);
+#endif
   switch (a.d.H) {
     case 32: return run_backward<32>(a);
     case 64: return run_backward<64>(a);

@@ -12,6 +12,7 @@ namespace gccb {
 struct GinDims {
   int L, H, P, D, maxdeg, din;   // din = P + D + 1 (49)
   int norm;
+  int tc;                        // 1: Linear layers / their gradients on tcgen05 tensor cores (bf16 operands)
   float bn_eps, bn_mom, norm_eps, drop_p;
 };
 
@@ -27,9 +28,16 @@ struct ActsLayout {
   size_t pooled;                               // float [L][B][PW]
   size_t score;                                // float [B][H]  (pre-normalisation)
   size_t feat;                                 // float [B][H]
+  // tensor-core path only (d.tc): bf16 operands of the current layer's GEMMs and the bf16 weight copies
+  size_t a16;                                  // bf16 [node_cap][max(H, 64)]   a = h + sum_nbr h
+  size_t x16;                                  // bf16 [node_cap][H]            x1 = relu(bn1(z1))
+  size_t w16[GCCB_MAX_L];                      // bf16 per layer: W1 [H][KW] | W2 [H][H] | W1^T [KW][H] | W2^T [H][H]
   size_t total;
   int PW;
 };
+// padded input width of layer l's first Linear on the tensor-core path (K of the GEMM, multiple of 64)
+__host__ __device__ __forceinline__ int gin_kw(const GinDims& d, int l) { return l == 0 ? GCCB_DINP : d.H; }
+inline size_t gin_w16_elems(const GinDims& d, int l) { return (size_t)2 * d.H * gin_kw(d, l) + (size_t)2 * d.H * d.H; }
 
 inline ActsLayout make_acts_layout(const GinDims& d, int B, int node_cap) {
   ActsLayout a;
@@ -49,6 +57,13 @@ inline ActsLayout make_acts_layout(const GinDims& d, int B, int node_cap) {
   a.pooled = take((size_t)d.L * B * a.PW * 4);
   a.score = take((size_t)B * d.H * 4);
   a.feat = take((size_t)B * d.H * 4);
+  a.a16 = a.x16 = 0;
+  for (int l = 0; l < GCCB_MAX_L; ++l) a.w16[l] = 0;
+  if (d.tc) {
+    a.a16 = take((size_t)node_cap * (d.H > GCCB_DINP ? d.H : GCCB_DINP) * 2);
+    a.x16 = take((size_t)node_cap * d.H * 2);
+    for (int l = 0; l < d.L - 1; ++l) a.w16[l] = take(gin_w16_elems(d, l) * 2);
+  }
   a.total = off;
   return a;
 }
@@ -86,6 +101,11 @@ inline int dims_from_cfg(const gccb_gin_cfg_t* c, GinDims* d) {
   d->L = c->num_layers; d->H = c->hidden; d->P = c->pos_dim; d->D = c->deg_dim;
   d->maxdeg = c->max_degree; d->din = c->pos_dim + c->deg_dim + 1; d->norm = c->norm;
   d->bn_eps = c->bn_eps; d->bn_mom = c->bn_momentum; d->norm_eps = c->norm_eps; d->drop_p = c->dropout_p;
+#ifdef GCCB_EMU
+  d->tc = 0;                                              // the CPU emulator has no tensor cores
+#else
+  d->tc = (c->tensor_cores && c->hidden >= 128) ? 1 : 0;  // tcgen05 tiles are 128 x {128, 256}: hidden 32 / 64 stay SIMT fp32
+#endif
   if (d->L < 2 || d->L > GCCB_MAX_L || (d->H != 32 && d->H != 64 && d->H != 128 && d->H != 256) ||
       d->din > GCCB_DINP || d->P < 2 || d->P > 32 || d->D < 1 || d->maxdeg < 1) {
     set_last_error("gin: unsupported configuration (L=%d H=%d pos=%d deg=%d): need 2<=L<=8, "

@@ -16,6 +16,10 @@
 // (bit-level agreement with an fp32 reference matters more than tensor-pipe speed
 // at hidden=64, where the layer is bandwidth/launch bound -- see DESIGN.md).
 #include "gin_common.cuh"
+#include "tc_gemm.cuh"
+#ifndef GCCB_EMU
+#include <cuda_bf16.h>
+#endif
 
 namespace gccb {
 
@@ -458,6 +462,205 @@ static int run_forward(const FwdArgs& a) {
   return check_launch("gccb_gin_forward");
 }
 
+
+#ifndef GCCB_EMU
+// ================================================================================================
+// Tensor-core path (cfg.tensor_cores, hidden >= 128; BASELINE config 4): the two Linear layers of every
+// GIN MLP (gin.py:113-116) run as tcgen05 GEMMs (csrc/tc_gemm.cu) with bf16 operands staged by TMA and
+// fp32 accumulation in TMEM; bias add and the BatchNorm column statistics are the GEMM epilogue.  The
+// gather / segmented reduce and the BatchNorm + ReLU between the GEMMs are bandwidth-bound passes that
+// also emit the bf16 operand of the next GEMM.  Activations stay fp32 in the stash (the backward's
+// elementwise chain is unchanged).
+
+// bf16 copies of one layer's weights: W1 [H][KW] (zero padded k >= in_features), W2 [H][H], and their
+// transposes W1^T [KW][H], W2^T [H][H] (the B operands of the input-gradient GEMMs).  grid = (blocks, L-1)
+__global__ void __launch_bounds__(256)
+gin_cast_weights_kernel(GinDims d, gccb_gin_layout_t lay, const float* __restrict__ params, char* acts,
+                        ActsLayout al) {
+  const int l = blockIdx.y, H = d.H, KW = gin_kw(d, l), inf = gin_in_features(d, l);
+  const float* W1 = params + lay.w1[l];
+  const float* W2 = params + lay.w2[l];
+  __nv_bfloat16* w1b = (__nv_bfloat16*)(acts + al.w16[l]);
+  __nv_bfloat16* w2b = w1b + (size_t)H * KW;
+  __nv_bfloat16* w1t = w2b + (size_t)H * H;
+  __nv_bfloat16* w2t = w1t + (size_t)KW * H;
+  const int n1 = H * KW, n2 = H * H;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * n1 + 2 * n2; idx += gridDim.x * blockDim.x) {
+    if (idx < n1) {
+      const int o = idx / KW, k = idx - o * KW;
+      w1b[idx] = __float2bfloat16_rn(k < inf ? W1[(size_t)o * inf + k] : 0.f);
+    } else if (idx < n1 + n2) {
+      w2b[idx - n1] = __float2bfloat16_rn(W2[idx - n1]);
+    } else if (idx < 2 * n1 + n2) {
+      const int j = idx - n1 - n2, k = j / H, o = j - k * H;
+      w1t[j] = __float2bfloat16_rn(k < inf ? W1[(size_t)o * inf + k] : 0.f);
+    } else {
+      const int j = idx - 2 * n1 - n2, k = j / H, o = j - k * H;
+      w2t[j] = __float2bfloat16_rn(W2[(size_t)o * H + k]);
+    }
+  }
+}
+
+// a = (1 + eps) h + sum_nbr h  -> fp32 stash + bf16 GEMM operand.  One warp per row, 8 rows per CTA pass;
+// hub rows (more than GCCB_HUB_DEG neighbours) are split across the CTA's warps.
+template <int W>
+__global__ void __launch_bounds__(256)
+gin_agg_cast_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_t* __restrict__ indptr,
+                    const int32_t* __restrict__ indices, const float* __restrict__ h, float eps_gin,
+                    float* __restrict__ a_out, __nv_bfloat16* __restrict__ a16) {
+  __shared__ float scratch[8 * W];
+  __shared__ int hub_rows[8];
+  __shared__ int n_hub;
+  const int N = node_off_v[B];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int PER = (W + 31) / 32;
+  for (int base = blockIdx.x * 8; base < N; base += gridDim.x * 8) {
+    if (tid == 0) n_hub = 0;
+    __syncthreads();
+    const int r = base + warp;
+    if (r < N) {
+      const int beg = indptr[r], end = indptr[r + 1];
+      if (end - beg > GCCB_HUB_DEG) {
+        if (lane == 0) hub_rows[atomicAdd(&n_hub, 1)] = r;
+      } else {
+        float acc[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const int c = lane + 32 * j;
+          acc[j] = c < W ? (1.0f + eps_gin) * h[(size_t)r * W + c] : 0.f;
+        }
+        gather_range<W>(h, indices, beg, end, lane, acc);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const int c = lane + 32 * j;
+          if (c < W) {
+            a_out[(size_t)r * W + c] = acc[j];
+            a16[(size_t)r * W + c] = __float2bfloat16_rn(acc[j]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int hi = 0; hi < n_hub; ++hi) {
+      const int rh = hub_rows[hi];
+      const float sacc = gather_hub<W>(h, indices, indptr[rh], indptr[rh + 1], scratch);
+      if (tid < W) {
+        const float v = (1.0f + eps_gin) * h[(size_t)rh * W + tid] + sacc;
+        a_out[(size_t)rh * W + tid] = v;
+        a16[(size_t)rh * W + tid] = __float2bfloat16_rn(v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// x1 = relu(bn1(z1)) as the bf16 operand of the second GEMM (BatchNorm coefficients from the column sums the
+// first GEMM's epilogue accumulated; block 0 updates the running statistics).  4 columns per thread.
+template <int H>
+__global__ void __launch_bounds__(256)
+gin_bn_relu_cast_kernel(const int32_t* __restrict__ node_off_v, int B, const float* __restrict__ z1,
+                        const double* __restrict__ sums1, const float* __restrict__ g1, const float* __restrict__ be1,
+                        float bn_eps, float* __restrict__ running1, int use_running, int update_running,
+                        float momentum, __nv_bfloat16* __restrict__ x16) {
+  __shared__ float coef[4 * H];
+  const int N = node_off_v[B];
+  bn_prepare(sums1, N, H, g1, be1, bn_eps, coef, coef + H, coef + 2 * H, coef + 3 * H, running1, use_running != 0,
+             update_running != 0, momentum);
+  __syncthreads();
+  const float* sc = coef + 2 * H;
+  const float* sh = coef + 3 * H;
+  const size_t total4 = (size_t)(N > 0 ? N : 0) * (H / 4);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (H / 4)) * 4;
+    const float4 z = reinterpret_cast<const float4*>(z1)[i];
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(fmaf(z.x, sc[c], sh[c]), 0.f), fmaxf(fmaf(z.y, sc[c + 1], sh[c + 1]), 0.f));
+    const __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(fmaf(z.z, sc[c + 2], sh[c + 2]), 0.f), fmaxf(fmaf(z.w, sc[c + 3], sh[c + 3]), 0.f));
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&p0);
+    u.y = *reinterpret_cast<const uint32_t*>(&p1);
+    reinterpret_cast<uint2*>(x16)[i] = u;
+  }
+}
+
+template <int H>
+static int run_forward_tc(const FwdArgs& a) {
+  const GinDims& d = a.d;
+  const int B = a.batch->batch, cap = a.batch->node_cap;
+  const int32_t* node_off_v = a.batch->node_off + (size_t)a.view * (B + 1);
+  const int32_t* n_dev = node_off_v + B;
+  const int32_t* indptr = a.batch->indptr + (size_t)a.view * (cap + 1);
+  const int32_t* indices = a.batch->indices + (size_t)a.view * a.batch->edge_cap;
+  const int32_t* sub_deg = a.batch->sub_deg + (size_t)a.view * cap;
+  const int32_t* graph_id = a.batch->graph_id + (size_t)a.view * cap;
+  const float* pos_v = a.pos + (size_t)a.view * cap * d.P;
+  cudaStream_t st = (cudaStream_t)a.stream;
+  float* x0 = (float*)(a.acts + a.al.x0);
+  double* stats = (double*)(a.acts + a.al.stats);
+  __nv_bfloat16* a16 = (__nv_bfloat16*)(a.acts + a.al.a16);
+  __nv_bfloat16* x16 = (__nv_bfloat16*)(a.acts + a.al.x16);
+  const int tiles = (cap + GCCB_TILE_ROWS - 1) / GCCB_TILE_ROWS;
+  const int grid = tiles < 592 ? tiles : 592;
+  const int use_running = a.bn_train ? 0 : 1, upd = a.bn_train ? 1 : 0;
+  cudaMemsetAsync(stats, 0, a.al.pool_acc + (size_t)d.L * B * a.al.PW * sizeof(double) - a.al.stats, st);
+  GCCB_LAUNCH(gin_build_x0_kernel, grid, 256, 0, a.stream, d, node_off_v, B, pos_v, sub_deg, graph_id,
+              a.params + a.lay.emb, x0);
+  {
+    dim3 gw(64, d.L - 1);
+    GCCB_LAUNCH(gin_cast_weights_kernel, gw, 256, 0, a.stream, d, a.lay, a.params, a.acts, a.al);
+  }
+  const float* hin = x0;
+  const float* P = a.params;
+  const int agg_grid = (cap + 7) / 8 < 1184 ? (cap + 7) / 8 : 1184;
+  for (int l = 0; l < d.L - 1; ++l) {
+    float* a_l = (float*)(a.acts + a.al.a[l]);
+    float* z1 = (float*)(a.acts + a.al.z1[l]);
+    float* z2 = (float*)(a.acts + a.al.z2[l]);
+    float* hout = (float*)(a.acts + a.al.h[l]);
+    double* s1 = stats + (size_t)(l * 3 + 0) * 2 * H;
+    double* sa = stats + (size_t)(l * 3 + 1) * 2 * H;
+    double* sb = stats + (size_t)(l * 3 + 2) * 2 * H;
+    float* run1 = a.running ? a.running + (size_t)(l * 3 + 0) * 2 * H : nullptr;
+    float* runa = a.running ? a.running + (size_t)(l * 3 + 1) * 2 * H : nullptr;
+    float* runb = a.running ? a.running + (size_t)(l * 3 + 2) * 2 * H : nullptr;
+    const int KW = gin_kw(d, l);
+    const __nv_bfloat16* w1b = (const __nv_bfloat16*)(a.acts + a.al.w16[l]);
+    const __nv_bfloat16* w2b = w1b + (size_t)H * KW;
+    if (l == 0) {
+      auto k = gin_agg_cast_kernel<GCCB_DINP>;
+      GCCB_LAUNCH(k, agg_grid, 256, 0, a.stream, node_off_v, B, indptr, indices, hin, 0.0f, a_l, a16);
+    } else {
+      auto k = gin_agg_cast_kernel<H>;
+      GCCB_LAUNCH(k, agg_grid, 256, 0, a.stream, node_off_v, B, indptr, indices, hin, 0.0f, a_l, a16);
+    }
+    int rc = tc::gemm_bf16(a16, w1b, cap, H, KW, n_dev, P + a.lay.b1[l], 1.0f, z1, nullptr, H, s1, 1, nullptr, st);
+    if (rc) return rc;
+    auto kb = gin_bn_relu_cast_kernel<H>;
+    GCCB_LAUNCH(kb, grid, 256, 0, a.stream, node_off_v, B, (const float*)z1, (const double*)s1, P + a.lay.bn1_w[l],
+                P + a.lay.bn1_b[l], d.bn_eps, run1, use_running, upd, d.bn_mom, x16);
+    rc = tc::gemm_bf16(x16, w2b, cap, H, H, n_dev, P + a.lay.b2[l], 1.0f, z2, nullptr, H, sa, 1, nullptr, st);
+    if (rc) return rc;
+    auto kt = gin_bn_tail_kernel<H>;
+    GCCB_LAUNCH(kt, grid, 256, 0, a.stream, 0, node_off_v, B, z2, sa, P + a.lay.bna_w[l], P + a.lay.bna_b[l],
+                runa, sb, P + a.lay.bnb_w[l], P + a.lay.bnb_b[l], runb, d.bn_eps, use_running, upd,
+                d.bn_mom, sb, hout);
+    GCCB_LAUNCH(kt, grid, 256, 0, a.stream, 1, node_off_v, B, z2, sa, P + a.lay.bna_w[l], P + a.lay.bna_b[l],
+                runa, sb, P + a.lay.bnb_w[l], P + a.lay.bnb_b[l], runb, d.bn_eps, use_running, upd,
+                d.bn_mom, sb, hout);
+    hin = hout;
+  }
+  const uint32_t keep = (uint32_t)fmin((1.0 - (double)d.drop_p) * 4294967296.0, 4294967295.0);
+  double* pool_acc = (double*)(a.acts + a.al.pool_acc);
+  auto kpl = gin_pool_kernel<H>;
+  GCCB_LAUNCH(kpl, grid, 256, 0, a.stream, d.L, node_off_v, B, graph_id, (const float*)x0, a.d_hptrs, a.al.PW,
+              pool_acc);
+  auto kp = gin_pool_predict_kernel<H>;
+  GCCB_LAUNCH(kp, B, 256, 0, a.stream, d, node_off_v, B, (const double*)pool_acc, a.params, a.d_offs, a.d_offs + 8,
+              a.al.PW, a.drop_key, a.drop_step, a.drop_base, keep, (float*)(a.acts + a.al.pooled),
+              (float*)(a.acts + a.al.score), a.feat, a.pooled_user);
+  return check_launch("gccb_gin_forward (tensor cores)");
+}
+#endif  // !GCCB_EMU
+
 }  // namespace gccb
 
 using namespace gccb;
@@ -523,6 +726,9 @@ extern "C" int gccb_gin_forward(const gccb_gin_cfg_t* cfg, const gccb_batch_t* b
   GCCB_LAUNCH(gin_fill_tables_kernel, 1, 32, 0, stream, (char*)acts, a.al, a.lay, a.d.L, a.d_hptrs, a.d_offs,
               bn_train ? num_batches_tracked : (int64_t*)nullptr,
               (const int32_t*)(batch->node_off + (size_t)view * (batch->batch + 1) + batch->batch));
+#ifndef GCCB_EMU
+  if (a.d.tc) return a.d.H == 128 ? run_forward_tc<128>(a) : run_forward_tc<256>(a);
+#endif
   switch (a.d.H) {
     case 32: return run_forward<32>(a);
     case 64: return run_forward<64>(a);

@@ -20,7 +20,7 @@
 //   MMAs of tile t+1.
 // Shared-memory operand layout = the canonical K-major SWIZZLE_128B layout (8-row groups 1024 B apart),
 // which is exactly what a TMA box with CU_TENSOR_MAP_SWIZZLE_128B writes.
-#include "common.cuh"
+#include "tc_gemm.cuh"
 
 #ifndef GCCB_EMU
 #include <cuda.h>
@@ -304,22 +304,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-// out[r][c] = alpha * sum_s part[s][r][c] (+ bias[c]) ; optional bf16 copy.   grid-stride, float4
+// out[r][c] = alpha * sum_s part[s][r][c] (+ bias[c]) (+ beta * out[r][c]) for c < n_out; optional bf16 copy.
+// Partials have row pitch ldp, the output row pitch ldo.  Fixed summation order: deterministic.
 __global__ void __launch_bounds__(256)
-tc_splitk_reduce_kernel(const float* __restrict__ part, int splits, int M_cap, int N, int ldo,
-                        const int32_t* __restrict__ m_dev, float alpha, const float* __restrict__ bias,
+tc_splitk_reduce_kernel(const float* __restrict__ part, int splits, int M_cap, int n_out, int ldp, int ldo,
+                        const int32_t* __restrict__ m_dev, float alpha, float beta, const float* __restrict__ bias,
                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
   const int M = m_dev ? min(max(*m_dev, 0), M_cap) : M_cap;
-  const size_t total = (size_t)M * N;
-  const size_t stride = (size_t)M_cap * ldo;
+  const size_t total = (size_t)M * n_out;
+  const size_t stride = (size_t)M_cap * ldp;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int r = (int)(idx / N), c = (int)(idx - (size_t)r * N);
-    const size_t o = (size_t)r * ldo + c;
+    const int r = (int)(idx / n_out), c = (int)(idx - (size_t)r * n_out);
+    const size_t ip = (size_t)r * ldp + c, o = (size_t)r * ldo + c;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += part[(size_t)sp * stride + o];     // fixed order: deterministic
+    for (int sp = 0; sp < splits; ++sp) s += part[(size_t)sp * stride + ip];
     s *= alpha;
     if (bias) s += bias[c];
-    if (out_f32) out_f32[o] = s;
+    if (out_f32) {
+      if (beta != 0.f) s = fmaf(beta, out_f32[o], s);
+      out_f32[o] = s;
+    }
     if (out_bf16) out_bf16[o] = __float2bfloat16_rn(s);
   }
 }
@@ -356,7 +360,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int b
   return GCCB_OK;
 }
 
-static int sm_count() {
+int sm_count() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -386,10 +390,11 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& 
 // splits > 1: `scratch` must hold splits * M_cap * ldo floats; the partial sums are reduced in a fixed order.
 int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32_t* m_dev, const float* bias,
               float alpha, float* out_f32, void* out_bf16, int ldo, double* colstats, int splits, float* scratch,
-              cudaStream_t stream) {
-  if (!A || !B || M_cap <= 0 || N <= 0 || K <= 0 || (K % BK) || (N % 32) || ldo < N || (ldo % 8) || splits < 1 ||
+              cudaStream_t stream, float beta, int n_out) {
+  if (n_out < 0) n_out = N;
+  if (!A || !B || M_cap <= 0 || N <= 0 || K <= 0 || (K % BK) || (N % 32) || n_out > N || ldo < n_out || splits < 1 ||
       (!out_f32 && !out_bf16)) {
-    set_last_error("tc_gemm: bad argument (need K %% 64 == 0, N %% 32 == 0, ldo %% 8 == 0)");
+    set_last_error("tc_gemm: bad argument (need K %% 64 == 0, N %% 32 == 0, ldo >= n_out)");
     return GCCB_ERR_BADARG;
   }
   const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
@@ -398,8 +403,11 @@ int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32
     const int kb_total = K / BK, per = (kb_total + splits - 1) / splits;
     splits = (kb_total + per - 1) / per;
   }
-  if (splits > 1 && (!scratch || colstats)) {
-    set_last_error("tc_gemm: split-K needs a scratch buffer and cannot fuse column statistics");
+  // partial sums go through `scratch` and the reduce kernel when K is split, and also when the output is not
+  // a plain [M][N] store (accumulate into it, narrower than N, row pitch the epilogue's 16-byte stores cannot use)
+  const bool via_scratch = splits > 1 || beta != 0.f || n_out != N || (ldo % 8) != 0;
+  if (via_scratch && (!scratch || colstats)) {
+    set_last_error("tc_gemm: split-K / accumulate / narrow output need a scratch buffer and cannot fuse column statistics");
     return GCCB_ERR_BADARG;
   }
   CUtensorMap ma, mb;
@@ -408,8 +416,8 @@ int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32
   rc = make_map(&mb, B, N, K, BN);
   if (rc) return rc;
   GemmArgs g;
-  g.M_cap = M_cap; g.N = N; g.K = K; g.ldo = ldo; g.m_dev = m_dev; g.splits = splits;
-  if (splits > 1) {
+  g.M_cap = M_cap; g.N = N; g.K = K; g.ldo = via_scratch ? N : ldo; g.m_dev = m_dev; g.splits = splits;
+  if (via_scratch) {
     g.bias = nullptr; g.alpha = 1.0f; g.out_f32 = scratch; g.out_bf16 = nullptr; g.colstats = nullptr;
   } else {
     g.bias = bias; g.alpha = alpha; g.out_f32 = out_f32; g.out_bf16 = (__nv_bfloat16*)out_bf16; g.colstats = colstats;
@@ -420,12 +428,12 @@ int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32
     case 64: launch<64>(ma, mb, g, stream); break;
     default: launch<32>(ma, mb, g, stream); break;
   }
-  if (splits > 1) {
-    const size_t total = (size_t)M_cap * N;
+  if (via_scratch) {
+    const size_t total = (size_t)M_cap * n_out;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-    GCCB_LAUNCH(tc_splitk_reduce_kernel, blocks, 256, 0, stream, (const float*)scratch, splits, M_cap, N, ldo, m_dev,
-                alpha, bias, out_f32, (__nv_bfloat16*)out_bf16);
+    GCCB_LAUNCH(tc_splitk_reduce_kernel, blocks, 256, 0, stream, (const float*)scratch, splits, M_cap, n_out, N, ldo,
+                m_dev, alpha, beta, bias, out_f32, (__nv_bfloat16*)out_bf16);
   }
   return check_launch("tc_gemm");
 }
@@ -433,14 +441,22 @@ int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32
 // fp32 -> bf16 (optionally transposed): dst[c][r] or dst[r][c], zero padded to [rows_pad][cols_pad]
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int lds, __nv_bfloat16* __restrict__ dst,
-                 int rows_pad, int cols_pad, int transpose, const int32_t* __restrict__ rows_dev) {
+                 int rows_pad, int cols_pad, int transpose, const int32_t* __restrict__ rows_dev,
+                 const float* __restrict__ sc, const float* __restrict__ sh, int relu) {
   __shared__ float tile[32][33];
   const int R = rows_dev ? min(max(*rows_dev, 0), rows) : rows;
+  auto load = [&](int r, int c) {
+    if (r >= R || c >= cols) return 0.f;
+    float v = src[(size_t)r * lds + c];
+    if (sc) v = fmaf(v, sc[c], sh[c]);
+    if (relu) v = fmaxf(v, 0.f);
+    return v;
+  };
   if (!transpose) {
     const size_t total = (size_t)rows_pad * cols_pad;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
       const int r = (int)(idx / cols_pad), c = (int)(idx - (size_t)r * cols_pad);
-      dst[idx] = __float2bfloat16_rn(r < R && c < cols ? src[(size_t)r * lds + c] : 0.f);
+      dst[idx] = __float2bfloat16_rn(load(r, c));
     }
     return;
   }
@@ -452,7 +468,7 @@ cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int lds, __n
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
       const int r = r0 + i, c = c0 + tx;
-      tile[i][tx] = (r < R && c < cols) ? src[(size_t)r * lds + c] : 0.f;
+      tile[i][tx] = load(r, c);
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
@@ -463,13 +479,13 @@ cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int lds, __n
 }
 
 int cast_bf16(const float* src, int rows, int cols, int lds, void* dst, int rows_pad, int cols_pad, int transpose,
-              const int32_t* rows_dev, cudaStream_t stream) {
+              const int32_t* rows_dev, cudaStream_t stream, const float* sc, const float* sh, int relu) {
   const size_t total = (size_t)rows_pad * cols_pad;
   int blocks = (int)((total + 1023) / 1024);
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
   if (blocks < 1) blocks = 1;
   GCCB_LAUNCH(cast_bf16_kernel, blocks, 256, 0, stream, src, rows, cols, lds, (__nv_bfloat16*)dst, rows_pad, cols_pad,
-              transpose, rows_dev);
+              transpose, rows_dev, sc, sh, relu);
   return check_launch("cast_bf16");
 }
 

@@ -135,6 +135,10 @@ typedef struct {
   float bn_momentum;   /* 0.1  */
   float norm_eps;      /* 1e-5 */
   float dropout_p;     /* 0.5 (gin.py:202)                                          */
+  int32_t tensor_cores; /* 1: the Linear layers of the MLP (gin.py:107-116) and their input / weight
+                           gradients run on tcgen05 tensor cores with bf16 operands and fp32
+                           accumulation (hidden >= 128 only; BASELINE config 4); 0: fp32 SIMT  */
+  int32_t _pad;
 } gccb_gin_cfg_t;
 
 /* offsets (in floats) into the flat parameter buffer; arrays sized for L <= 8 */

@@ -64,9 +64,17 @@ def _bn(x, params, key, train, stats_out, momentum=0.1, eps=1e-5):
     return (x - rm) / torch.sqrt(rv + eps) * w + b
 
 
+def _round_operand(x, dt):
+    """Round a GEMM operand to `dt` (bf16: what the tensor-core path feeds tcgen05) in the forward only
+    (straight-through for autograd); accumulation stays in the oracle's precision."""
+    if dt is None:
+        return x
+    return x + (x.detach().to(dt).to(x.dtype) - x.detach())
+
+
 def gin_encoder_forward(params, indptr, indices, pos, seed_flag, sub_deg, node_off,
                         num_layers=5, max_degree=512, norm=True, bn_train=True,
-                        dropout_keep=None, dropout_p=0.5):
+                        dropout_keep=None, dropout_p=0.5, gemm_operand_dtype=None):
     """graph_encoder.py:132-200 (gin branch) on a batched graph.
 
     indptr/indices: batched CSR with global row ids; node_off: [B+1] offsets.
@@ -90,10 +98,11 @@ def gin_encoder_forward(params, indptr, indices, pos, seed_flag, sub_deg, node_o
         # DGL GINConv 'sum': rst = (1 + eps) * feat + sum_{u in N(v)} feat_u   [M]
         neigh = torch.zeros_like(h).index_add_(0, row, h[col])
         a = (1.0 + params[p + "eps"].to(dt)) * h + neigh
-        z1 = F.linear(a, params[p + "apply_func.mlp.linears.0.weight"],
+        gd = gemm_operand_dtype
+        z1 = F.linear(_round_operand(a, gd), _round_operand(params[p + "apply_func.mlp.linears.0.weight"], gd),
                       params[p + "apply_func.mlp.linears.0.bias"])      # gin.py:113-115
         x1 = F.relu(_bn(z1, params, p + "apply_func.mlp.batch_norms.0.", bn_train, stats))
-        z2 = F.linear(x1, params[p + "apply_func.mlp.linears.1.weight"],
+        z2 = F.linear(_round_operand(x1, gd), _round_operand(params[p + "apply_func.mlp.linears.1.weight"], gd),
                       params[p + "apply_func.mlp.linears.1.bias"])      # gin.py:116
         y = F.relu(_bn(z2, params, p + "apply_func.bn.", bn_train, stats))   # gin.py:55-57
         h = F.relu(_bn(y, params, "gnn.batch_norms.%d." % i, bn_train, stats))  # gin.py:219-220
