@@ -79,6 +79,7 @@ namespace gccb {
 #define GCCB_BIG_NT 512            // threads of the large-ego-net CTAs: 512 x 64 registers leave half of
 #endif                             // the SM's register file to concurrent kernels (these CTAs live for ms)
 #define GCCB_CF_MAXIT 8
+#define GCCB_GS_PANEL 4            // columns orthogonalised per Gram-Schmidt step (single-CTA kernels)
 #define GCCB_CF_TOL 4.0e-5f        // max residual ||L x - theta x|| over the wanted pairs
 #define GCCB_CF_STAG 2.0e-3f       // accepted when the residual stops halving below this: ego-nets whose
                                    // near-degenerate cluster is wider than the block stall at its spread
@@ -561,6 +562,9 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
   __shared__ int perm[CB];
   __shared__ float s_bc[2];
   __shared__ float sgn[32];
+  __shared__ float rd4[GCCB_GS_PANEL * CB];      // panel Gram-Schmidt: dots of the 4 panel columns with all columns
+  __shared__ float pl[16];                        // inverse of the panel's 4 x 4 Cholesky factor (lower triangle)
+  __shared__ int pflag;
   float* Ws = WT;
   float (*tile)[32][CB + 1] = reinterpret_cast<float (*)[32][CB + 1]>(WT);
   const int slot = worklist[(size_t)cls * 2 * B + item];
@@ -624,8 +628,15 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
       X = cur; Y = prev;                                 // filtered block in X, Y is scratch
     }
     GCCB_TICK(0);
-    // ---- CGS2: orthonormalise the columns of X in place (row-major: all dots of a column at once)
-    for (int j = 0; j < CB; ++j) {
+    // ---- Gram-Schmidt: orthonormalise the columns of X in place, FOUR columns per step ------------------
+    // One pass over the rows gives the dots of the 4 panel columns with all columns (panel included): R = Q^T Y
+    // and G = Y^T Y.  The Gram matrix of the projected panel follows without a second reduction,
+    // G' = G - R^T R (Pythagoras, the 4 x 4 generalisation of ||y - QQ^T y||^2 = y.y - sum r_i^2), its Cholesky
+    // factor orthonormalises the panel, and one update pass applies Y <- (Y - Q R) L^-T: the barriers and
+    // latency chains of one column now serve four.  Heavy cancellation (diag G' <= diag G / 2) asks for a
+    // second pass as before; a small Cholesky pivot (panel nearly dependent after the projection: the random
+    // block of the first iteration) sends the 4 columns through the one-column code below.
+    auto gs_scalar = [&](int j) {
       // classical Gram-Schmidt with selective re-orthogonalisation (Daniel-Gragg-Kaufman test): the
       // dots of column j with all columns (itself included) come from one pass over the rows;
       // ||y - Q Q^T y||^2 = y.y - sum r_i^2, so neither the test nor the norm needs another reduction
@@ -665,6 +676,121 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
         for (int r = tid; r < n; r += NT) X[(size_t)r * ld + j] *= inv;
         __syncthreads();
       }
+        };
+    for (int j0 = 0; j0 < CB; j0 += GCCB_GS_PANEL) {
+      bool done = false;
+      for (int pass = 0; pass < 2 && !done; ++pass) {
+        {   // dots of columns j0..j0+3 with every column
+          constexpr int nwu = NW < 8 ? NW : 8;
+          if (warp < nwu) {
+            float a0[GCCB_GS_PANEL], a1[GCCB_GS_PANEL];
+#pragma unroll
+            for (int q = 0; q < GCCB_GS_PANEL; ++q) a0[q] = a1[q] = 0.f;
+            for (int r = warp; r < n; r += nwu) {
+              const float* row = X + (size_t)r * ld;
+              const float x0 = row[lane], x1 = hi ? row[32 + lane] : 0.f;
+#pragma unroll
+              for (int q = 0; q < GCCB_GS_PANEL; ++q) {
+                const float y = row[j0 + q];
+                a0[q] = fmaf(x0, y, a0[q]);
+                a1[q] = fmaf(x1, y, a1[q]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < GCCB_GS_PANEL; ++q) {
+              part[(warp * GCCB_GS_PANEL + q) * CB + lane] = a0[q];
+              if (hi) part[(warp * GCCB_GS_PANEL + q) * CB + 32 + lane] = a1[q];
+            }
+          }
+          __syncthreads();
+          for (int t = tid; t < GCCB_GS_PANEL * CB; t += NT) {
+            const int q = t / CB, c = t - q * CB;
+            float sacc = 0.f;
+#pragma unroll
+            for (int w = 0; w < nwu; ++w) sacc += part[(w * GCCB_GS_PANEL + q) * CB + c];
+            rd4[t] = sacc;
+          }
+          __syncthreads();
+        }
+        if (warp == 0) {
+          // lane -> (a, b), a >= b, of the lower triangle of G'
+          const int a = lane < 1 ? 0 : lane < 3 ? 1 : lane < 6 ? 2 : 3;
+          const int b = lane - (a * (a + 1)) / 2;
+          float gp = 0.f;
+          if (lane < 10) {
+            float sacc = 0.f;
+            for (int i = 0; i < j0; ++i) sacc = fmaf(rd4[a * CB + i], rd4[b * CB + i], sacc);
+            gp = rd4[a * CB + j0 + b] - sacc;
+          }
+          float g[10];
+#pragma unroll
+          for (int q = 0; q < 10; ++q) g[q] = __shfl_sync(0xffffffffu, gp, q);
+          if (lane == 0) {
+            // g: 0 (0,0) | 1 (1,0) 2 (1,1) | 3 (2,0) 4 (2,1) 5 (2,2) | 6 (3,0) 7 (3,1) 8 (3,2) 9 (3,3)
+            const float yy0 = rd4[0 * CB + j0], yy1 = rd4[1 * CB + j0 + 1], yy2 = rd4[2 * CB + j0 + 2], yy3 = rd4[3 * CB + j0 + 3];
+            int flag = 0;
+            const bool tiny = !(g[0] > 1e-30f) || !(g[2] > 1e-30f) || !(g[5] > 1e-30f) || !(g[9] > 1e-30f);
+            const bool again = !(g[0] > 0.5f * yy0) || !(g[2] > 0.5f * yy1) || !(g[5] > 0.5f * yy2) || !(g[9] > 0.5f * yy3);
+            float li[10] = {1.f, 0.f, 1.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};   // identity: projection only
+#ifdef GCCB_GS_FORCE_SCALAR                              // A/B builds (profiles/build_variant.py)
+            if (true) flag = 2;
+#else
+            if (tiny) flag = 2;
+#endif
+            else if (again) flag = pass == 0 ? 1 : 2;
+            else {
+              const float l00 = sqrtf(g[0]);
+              const float l10 = g[1] / l00;
+              const float s11 = g[2] - l10 * l10;
+              const float l11 = sqrtf(fmaxf(s11, 0.f));
+              const float l20 = g[3] / l00;
+              const float l21 = (g[4] - l20 * l10) / fmaxf(l11, 1e-30f);
+              const float s22 = g[5] - l20 * l20 - l21 * l21;
+              const float l22 = sqrtf(fmaxf(s22, 0.f));
+              const float l30 = g[6] / l00;
+              const float l31 = (g[7] - l30 * l10) / fmaxf(l11, 1e-30f);
+              const float l32 = (g[8] - l30 * l20 - l31 * l21) / fmaxf(l22, 1e-30f);
+              const float s33 = g[9] - l30 * l30 - l31 * l31 - l32 * l32;
+              if (!(s11 > 1e-4f * g[2]) || !(s22 > 1e-4f * g[5]) || !(s33 > 1e-4f * g[9])) flag = 2;
+              else {
+                const float l33 = sqrtf(s33);
+                li[0] = 1.0f / l00; li[2] = 1.0f / l11; li[5] = 1.0f / l22; li[9] = 1.0f / l33;
+                li[1] = -l10 * li[0] * li[2];
+                li[4] = -l21 * li[2] * li[5];
+                li[3] = -(l20 * li[0] + l21 * li[1]) * li[5];
+                li[8] = -l32 * li[5] * li[9];
+                li[7] = -(l31 * li[2] + l32 * li[4]) * li[9];
+                li[6] = -(l30 * li[0] + l31 * li[1] + l32 * li[3]) * li[9];
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 10; ++q) pl[q] = li[q];
+            pflag = flag;
+          }
+        }
+        __syncthreads();
+        const int flag = pflag;
+        if (flag == 2) break;                              // one column at a time below
+        for (int r = tid; r < n; r += NT) {
+          float* row = X + (size_t)r * ld;
+          float v0 = row[j0], v1 = row[j0 + 1], v2 = row[j0 + 2], v3 = row[j0 + 3];
+          for (int i = 0; i < j0; ++i) {
+            const float q = row[i];
+            v0 = fmaf(-rd4[i], q, v0);
+            v1 = fmaf(-rd4[CB + i], q, v1);
+            v2 = fmaf(-rd4[2 * CB + i], q, v2);
+            v3 = fmaf(-rd4[3 * CB + i], q, v3);
+          }
+          row[j0] = pl[0] * v0;
+          row[j0 + 1] = fmaf(pl[1], v0, pl[2] * v1);
+          row[j0 + 2] = fmaf(pl[3], v0, fmaf(pl[4], v1, pl[5] * v2));
+          row[j0 + 3] = fmaf(pl[6], v0, fmaf(pl[7], v1, fmaf(pl[8], v2, pl[9] * v3)));
+        }
+        __syncthreads();
+        done = flag == 0;
+      }
+      if (!done)
+        for (int j = j0; j < j0 + GCCB_GS_PANEL; ++j) gs_scalar(j);
     }
     GCCB_TICK(1);
     // ---- Z = L Q (into Y), H = Q^T Z ----------------------------------------------------------------
