@@ -12,6 +12,11 @@
 // recurrence with V = K) and never writes logits; the unfused entry points exist so the
 // reference's module API (MemoryMoCo.forward returning `out`) stays drop-in.
 #include "common.cuh"
+#include "tc_gemm.cuh"
+#ifndef GCCB_EMU
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#endif
 
 namespace gccb {
 
@@ -389,6 +394,136 @@ e2e_grads_kernel(const float* __restrict__ q, const float* __restrict__ k, const
   }
 }
 
+#ifndef GCCB_EMU
+// ---- tensor-core InfoNCE (d >= 128: BASELINE config 4, K = 65536, B = 1024, d = 256) ------------------------
+// logits = (q . queue^T) / T and dq = P . queue are the two big products of memory_moco.py:33-44 and its
+// backward; both run on tcgen05 (csrc/tc_gemm.cu) with bf16 operands: the queue is cast once per step into a
+// [K][d] copy (B operand of the logits GEMM) and a transposed [d][K] copy (B operand of the dq GEMM, split-K
+// over the keys).  Between them one CTA per query row does the softmax in fp32 on the fp32 logits: loss,
+// probabilities (bf16 operand of the second GEMM) and the positive-pair terms.
+struct NceTcLayout { size_t q16, m16, mt16, logits, p16, ppos, dqn, splitk, total; int splits; };
+static NceTcLayout nce_tc_layout(int B, int d, int K) {
+  NceTcLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  L.q16 = take((size_t)B * d * 2);
+  L.m16 = take((size_t)K * d * 2);
+  L.mt16 = take((size_t)d * K * 2);
+  L.logits = take((size_t)B * K * 4);
+  L.p16 = take((size_t)B * K * 2);
+  L.ppos = take((size_t)B * 4);
+  L.dqn = take((size_t)B * d * 4);
+  const int tiles = ((B + 127) / 128) * 1;
+  L.splits = 148 / tiles < 1 ? 1 : 148 / tiles;
+  if (L.splits > K / 64) L.splits = K / 64;
+  L.splitk = take((size_t)L.splits * B * d * 4);
+  L.total = off;
+  return L;
+}
+static bool nce_use_tc(int B, int d, int K) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("GCCB200_TC"); env = (e && e[0] == '0') ? 0 : 1; }
+  return env && d >= 128 && d % 64 == 0 && K % 64 == 0 && B >= 128;
+}
+
+// one CTA per query row: positive logit (fp32 q.k), row max / sum over [lpos | logits], loss and statistics,
+// probabilities as the bf16 A operand of the dq GEMM, p_pos for the finalisation
+__global__ void __launch_bounds__(256)
+nce_tc_softmax_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ logits,
+                      int B, int d, int K, float invT, float* __restrict__ stats, __nv_bfloat16* __restrict__ p16,
+                      float* __restrict__ ppos) {
+  __shared__ float red_s[8];
+  __shared__ float bc[3];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const float* row = logits + (size_t)i * K;
+  float s = 0.f;
+  for (int c = tid; c < d; c += 256) s = fmaf(q[(size_t)i * d + c], k[(size_t)i * d + c], s);
+  s = warp_sum(s);
+  if ((tid & 31) == 0) red_s[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red_s[w]; bc[2] = t * invT; }
+  __syncthreads();
+  const float lpos = bc[2];
+  float mx = lpos;
+  for (int j = tid * 4; j < K; j += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + j);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  mx = warp_max(mx);
+  __syncthreads();
+  if ((tid & 31) == 0) red_s[tid >> 5] = mx;
+  __syncthreads();
+  if (tid == 0) { float m = red_s[0]; for (int w = 1; w < 8; ++w) m = fmaxf(m, red_s[w]); bc[0] = m; }
+  __syncthreads();
+  mx = bc[0];
+  float sum = 0.f;
+  for (int j = tid * 4; j < K; j += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + j);
+    sum += (expf(v.x - mx) + expf(v.y - mx)) + (expf(v.z - mx) + expf(v.w - mx));
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if ((tid & 31) == 0) red_s[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float t = expf(lpos - mx);
+    for (int w = 0; w < 8; ++w) t += red_s[w];
+    bc[1] = t;
+    atomicAdd(&stats[0], (logf(t) + mx - lpos) / (float)B);
+    atomicAdd(&stats[1], lpos / (float)B);
+    ppos[i] = expf(lpos - mx) / t;
+  }
+  __syncthreads();
+  const float inv = 1.0f / bc[1];
+  __nv_bfloat16* prow = p16 + (size_t)i * K;
+  for (int j = tid * 4; j < K; j += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + j);
+    const __nv_bfloat162 a = __floats2bfloat162_rn(expf(v.x - mx) * inv, expf(v.y - mx) * inv);
+    const __nv_bfloat162 b = __floats2bfloat162_rn(expf(v.z - mx) * inv, expf(v.w - mx) * inv);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(prow + j) = u;
+  }
+}
+// dq_i = ((p_pos - 1) k_i + sum_j p_ij queue_j) / (T B)
+__global__ void __launch_bounds__(256)
+nce_tc_finish_kernel(const float* __restrict__ k, const float* __restrict__ dqn, const float* __restrict__ ppos,
+                     int B, int d, float scale, float* __restrict__ dq) {
+  const int total = B * d;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int i = idx / d;
+    dq[idx] = fmaf(ppos[i] - 1.0f, k[idx], dqn[idx]) * scale;
+  }
+}
+
+static int infonce_tc(const float* q, const float* k, const float* memory, int B, int d, int K, float T, float* stats,
+                      float* dq, char* ws, cudaStream_t st) {
+  const NceTcLayout L = nce_tc_layout(B, d, K);
+  __nv_bfloat16* q16 = (__nv_bfloat16*)(ws + L.q16);
+  __nv_bfloat16* m16 = (__nv_bfloat16*)(ws + L.m16);
+  __nv_bfloat16* mt16 = (__nv_bfloat16*)(ws + L.mt16);
+  float* logits = (float*)(ws + L.logits);
+  __nv_bfloat16* p16 = (__nv_bfloat16*)(ws + L.p16);
+  float* ppos = (float*)(ws + L.ppos);
+  float* dqn = (float*)(ws + L.dqn);
+  float* splitk = (float*)(ws + L.splitk);
+  int rc = tc::cast_bf16(q, B, d, d, q16, B, d, 0, nullptr, st);
+  if (!rc) rc = tc::cast_bf16(memory, K, d, d, m16, K, d, 0, nullptr, st);
+  if (!rc) rc = tc::cast_bf16(memory, K, d, d, mt16, K, d, 1, nullptr, st);
+  if (!rc) rc = tc::gemm_bf16(q16, m16, B, K, d, nullptr, nullptr, 1.0f / T, logits, nullptr, K, nullptr, 1, nullptr, st);
+  if (rc) return rc;
+  GCCB_LAUNCH(nce_tc_softmax_kernel, B, 256, 0, st, q, k, (const float*)logits, B, d, K, 1.0f / T, stats, p16, ppos);
+  rc = tc::gemm_bf16(p16, mt16, B, d, K, nullptr, nullptr, 1.0f, dqn, nullptr, d, nullptr, L.splits, splitk, st);
+  if (rc) return rc;
+  int blocks = (B * d + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  GCCB_LAUNCH(nce_tc_finish_kernel, blocks, 256, 0, st, k, (const float*)dqn, (const float*)ppos, B, d,
+              1.0f / (T * (float)B), dq);
+  return check_launch("gccb_infonce_fused (tensor cores)");
+}
+#endif  // !GCCB_EMU
+
 static bool infonce_tiled(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 static int infonce_ck(int d) {
   if (infonce_tiled(d)) return d <= 128 ? 128 : 64;
@@ -440,7 +575,11 @@ extern "C" int gccb_nce_loss(const float* out, int32_t B, int32_t C, int32_t lab
 extern "C" size_t gccb_infonce_workspace(int32_t B, int32_t d, int32_t K) {
   int ck = infonce_ck(d);
   size_t nch = (size_t)(K + ck - 1) / ck;
-  return nch * (size_t)B * (d + 2) * sizeof(float);
+  size_t simt = nch * (size_t)B * (d + 2) * sizeof(float);
+#ifndef GCCB_EMU
+  if (nce_use_tc(B, d, K)) { size_t t = nce_tc_layout(B, d, K).total; return t > simt ? t : simt; }
+#endif
+  return simt;
 }
 
 extern "C" int gccb_infonce_fused(const float* q, const float* k, const float* memory, int32_t B,
@@ -455,6 +594,9 @@ extern "C" int gccb_infonce_fused(const float* q, const float* k, const float* m
   const int ck = infonce_ck(d);
   const int nch = (K + ck - 1) / ck;
   cudaMemsetAsync(stats, 0, 2 * sizeof(float), (cudaStream_t)stream);
+#ifndef GCCB_EMU
+  if (nce_use_tc(B, d, K)) return infonce_tc(q, k, memory, B, d, K, T, stats, dq, (char*)workspace, (cudaStream_t)stream);
+#endif
   if (infonce_tiled(d)) {
     const size_t smem = ((size_t)GCCB_NCE_RB2 * d + (size_t)ck * (d + 1) + (size_t)GCCB_NCE_RB2 * ck) * 4;
     dim3 grid(nch, (B + GCCB_NCE_RB2 - 1) / GCCB_NCE_RB2);

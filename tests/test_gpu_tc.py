@@ -36,7 +36,9 @@ def test_tc_gemm_matches_fp32_matmul(M, N, K):
     out, outb, cs = _gemm(A, Bm, m_valid=mv, bias=bias, alpha=0.5, want_bf16=True, stats=True)
     want = 0.5 * (A.float() @ Bm.float().t()) + bias
     scale = float(want.abs().max())
-    assert torch.allclose(out[:mv], want[:mv], atol=2e-3 * scale, rtol=0), float((out[:mv] - want[:mv]).abs().max())
+    err = float((out[:mv] - want[:mv]).abs().max()) / scale
+    print("tc_gemm M=%d N=%d K=%d: max |err| / max |out| = %.2e" % (M, N, K, err))
+    assert err < 2e-3, err
     assert torch.isnan(out[mv:]).all()                     # rows beyond the device-side row count stay untouched
     assert torch.allclose(outb[:mv].float(), want[:mv], atol=1e-2 * scale, rtol=1e-2)
     w64 = want[:mv].double()
