@@ -30,7 +30,8 @@ HOPCAP = 64
 
 
 def load_graphs(spec):
-    """CSRGraph | list[CSRGraph] | path to .npz(indptr, indices[, graph_sizes]) -> (union CSR, sizes)."""
+    """CSRGraph | list[CSRGraph] | path to .npz(indptr, indices[, graph_sizes]) | path to a DGL save_graphs
+    .bin -> (union CSR, sizes)."""
     if isinstance(spec, synthetic.CSRGraph):
         return spec, [spec.num_nodes]
     if isinstance(spec, (list, tuple)):
@@ -42,9 +43,16 @@ def load_graphs(spec):
                                    len(z["indptr"]) - 1, spec)
             sizes = z["graph_sizes"].tolist() if "graph_sizes" in z.files else [g.num_nodes]
             return g, sizes
-        raise NotImplementedError(
-            "DGL .bin graph files (dgl.data.utils.load_graphs, graph_dataset.py:26-28) are not "
-            "readable without DGL; convert to .npz(indptr, indices, graph_sizes)  [SURVEY 8f N3]")
+        if spec.endswith(".bin"):
+            # DGL 0.4.x save_graphs file (gcc/utils/x2dgl.py:129-131), read without DGL: graph_dataset.py:26-28
+            # (load_graphs) and :58-60 (load_labels "graph_sizes").  Layout restated from memory: datasets/dgl_bin.py
+            from . import dgl_bin
+            graphs, labels = dgl_bin.read_dgl_bin(spec)
+            sizes = labels["graph_sizes"].tolist() if "graph_sizes" in labels else [g.num_nodes for g in graphs]
+            if sizes != [g.num_nodes for g in graphs]:
+                raise ValueError("%s: label graph_sizes disagrees with the stored graphs" % spec)
+            return (graphs[0] if len(graphs) == 1 else synthetic.disjoint_union(graphs)), sizes
+        raise NotImplementedError("unknown graph file type %r (use DGL .bin or .npz)" % spec)
     raise TypeError("unsupported graph spec %r" % (spec,))
 
 
