@@ -215,7 +215,8 @@ __device__ __forceinline__ int jacobi_onesided(float* G, float* nrm, int n, int 
 // current outer residual).
 template <int NT>
 __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64]*/, int* pq /*[32]*/, int LD,
-                                              float tol, int max_sweeps) {
+                                              float tol, int max_sweeps, long long* n_work = nullptr,
+                                              long long* n_idle = nullptr) {
   constexpr int M = GCCB_CF_B, HALF = M / 2;
   const int tid = threadIdx.x;
   // rl[0..nr): pairs that rotate this round, rl[HALF-1], rl[HALF-2], ...: the others; rl[HALF] = nr.
@@ -267,7 +268,8 @@ __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64
       }
       __syncthreads();
       const int nr = rl[HALF];
-      if (nr == 0) continue;
+      if (nr == 0) { if (n_idle) ++*n_idle; continue; }
+      if (n_work) ++*n_work;
       rotated = 1;
       // A <- J^T A J on 2x2 blocks (rows of pair a, columns of pair b); only blocks with a rotating
       // pair on either side change: (a in R, b any) and (a not in R, b in R)
@@ -547,7 +549,7 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
                     int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res, long long* __restrict__ dbg_phase) {
   constexpr int CB = GCCB_CF_B, LD = CB + 1;
   GCCB_DYN_SMEM(float, dynsm);
-  long long ph[6] = {0, 0, 0, 0, 0, 0}, t_last = GCCB_CLK();
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = GCCB_CLK();
   __shared__ float Gs[CB * LD];                   // Ritz problem
   // union: Ritz vectors Ws[CB*LD] | staging tiles [2][32][CB+1] (only when the blocks are not in shared memory)
   __shared__ float WT[MODE == 1 ? CB * LD : 32 * (CB + 1) * 2];
@@ -864,7 +866,7 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
     }
     GCCB_TICK(2);
     // ---- 48 x 48 Ritz problem: two-sided Jacobi, eigenvectors in Ws (tiles are dead now) ----------
-    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0 : GCCB_EIG_MAXSWEEP);   // the first block is random: one sweep conditions it
+    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0 : GCCB_EIG_MAXSWEEP, &ph[6], &ph[7]);   // the first block is random: one sweep conditions it
     GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
@@ -925,7 +927,7 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
   if (!converged && tid == 0) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
   if (tid == 0) {
     dbg_iters[slot] = iter; dbg_res[slot] = prev_worst;
-    for (int i = 0; i < 6; ++i) dbg_phase[(size_t)slot * 8 + i] = ph[i];
+    for (int i = 0; i < 8; ++i) dbg_phase[(size_t)slot * 8 + i] = ph[i];
   }
   // columns 0..k-1 of X hold the k largest Ritz pairs in DESCENDING order; emit ascending
   // (data_util.py: eigsh(which='LA') returns ascending eigenvalues)
@@ -1144,7 +1146,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
                             float* __restrict__ dbg_res, long long* __restrict__ dbg_phase) {
   constexpr int CB = GCCB_CF_B, LD = CB + 1, NW = NT / 32;
   GCCB_DYN_SMEM(float, dynsm);
-  long long ph[6] = {0, 0, 0, 0, 0, 0}, t_last = GCCB_CLK();
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = GCCB_CLK();
   __shared__ float Gs[CB * LD];                   // Ritz problem
   __shared__ float Hp[CB * LD];                   // this CTA's partial of H (read by the others)
   __shared__ float WT[32 * (CB + 1) * 2];         // union: Ritz vectors Ws[CB*LD] | tiles [2][32][CB+1]
@@ -1331,7 +1333,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       __syncthreads();
     }
     GCCB_TICK(2);
-    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0 : GCCB_EIG_MAXSWEEP);   // redundant per CTA, bit-identical
+    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0 : GCCB_EIG_MAXSWEEP, &ph[6], &ph[7]);   // redundant per CTA, bit-identical
     GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
@@ -1389,7 +1391,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
   if (C.rank == 0 && tid == 0) {
     if (!converged) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
     dbg_iters[slot] = iter; dbg_res[slot] = prev_worst;
-    for (int i = 0; i < 6; ++i) dbg_phase[(size_t)slot * 8 + i] = ph[i];
+    for (int i = 0; i < 8; ++i) dbg_phase[(size_t)slot * 8 + i] = ph[i];
   }
   if (eigvals && C.rank == 0)
     for (int c = tid; c < pos_dim; c += NT) eigvals[(size_t)slot * pos_dim + c] = c < k ? theta[k - 1 - c] : 0.f;

@@ -73,5 +73,7 @@ for lo, hi in ((64, 96), (96, 160), (160, 480), (480, 100000)):
     m = (n > lo) & (n <= hi)
     if m.sum():
         tot = phase[m][:, :6].sum(0).astype(float)
-        print("n in (%d,%d]: cycles/ego-net %.0f k; split %s" % (lo, hi, tot.sum() / m.sum() / 1e3,
-              ", ".join("%s %.0f%%" % (nm, 100 * t / tot.sum()) for nm, t in zip(names, tot))))
+        print("n in (%d,%d]: cycles/ego-net %.0f k; split %s; Jacobi rounds/ego-net: %.0f working + %.0f idle" % (
+            lo, hi, tot.sum() / m.sum() / 1e3,
+            ", ".join("%s %.0f%%" % (nm, 100 * t / tot.sum()) for nm, t in zip(names, tot)),
+            phase[m][:, 6].mean(), phase[m][:, 7].mean()))

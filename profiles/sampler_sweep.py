@@ -17,6 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 scale = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 200_000_000
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 32768          # pairs per launch -> 2B ego-nets
+BUDGET_CAP = int(sys.argv[4]) if len(sys.argv) > 4 else 2000   # walk budgets above it are clipped (0 = the reference formula unclipped)
+HOPS = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [64, 128, 256, 512]
+REPS = int(sys.argv[6]) if len(sys.argv) > 6 else 3            # 1 under ncu
 dev = torch.device("cuda")
 g = synthetic.rmat_device(scale, pairs, seed=0, device=dev)
 torch.cuda.synchronize()
@@ -29,10 +32,9 @@ try:
 except Exception:
     peak, info["peak_source"] = 6650.0, "fallback 6650 GB/s"
 rows = []
-BUDGET_CAP = 2000
-for hops in (64, 128, 256, 512):
+for hops in HOPS:
     ds = LoadBalanceGraphDataset(rw_hops=hops, restart_prob=0.8, dgl_graphs_file=g, batch_size=B, seed=0,
-                                 device=dev, node_cap=B * 1024, edge_cap=B * 1024 * 48, budget_cap=BUDGET_CAP)
+                                 device=dev, node_cap=B * 1024, edge_cap=B * 1024 * 48, budget_cap=BUDGET_CAP or None)
     try:
         for i in range(2):
             ds.sample_batch(posenc=False)
@@ -44,7 +46,7 @@ for hops in (64, 128, 256, 512):
         del ds
         torch.cuda.empty_cache()
         continue
-    reps = 3
+    reps = REPS
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     acc = torch.zeros(4, dtype=torch.float64, device=dev)
     ev[0].record()
@@ -60,11 +62,13 @@ for hops in (64, 128, 256, 512):
     rows.append({"rw_hops": hops, "ms_per_launch_group": ms, "egonets_per_sec": 2 * B / (ms / 1e3),
                  "algorithmic_bytes": alg, "achieved_gbs": alg / (ms / 1e3) / 1e9, "frac_of_hbm_peak": alg / (ms / 1e3) / 1e9 / peak,
                  "avg_nodes": n_sum / (2 * B), "avg_induced_edges": m_sum / (2 * B), "avg_walk_steps": t_sum / (2 * B),
-                 "avg_scanned_neighbours": deg_sum / (2 * B), "max_budget": ds.graph.max_budget})
+                 "avg_scanned_neighbours": deg_sum / (2 * B), "max_budget": ds.graph.max_budget,
+                 "seeds_with_clipped_budget_frac": float((ds.graph.budget_table[deg[ds.buffers.seeds]] >= BUDGET_CAP).double().mean()) if BUDGET_CAP else 0.0})
     print(rows[-1], file=sys.stderr)
     del ds
     torch.cuda.empty_cache()
 info.update({"hbm_peak_gbs": peak, "sweep": rows,
-             "note": "walk budgets above %d are clipped (capacity knob of the sweep); inputs resident in HBM; timed with "
-                     "CUDA events over 3 launch groups (walk+unique, offsets, induce+fill)" % BUDGET_CAP})
+             "note": "walk budgets above %d are clipped (capacity knob of the sweep; 0 = unclipped); inputs resident in HBM; "
+                     "timed with CUDA events over %d launch groups (walk+unique, offsets, fill); physical DRAM bytes: the ncu "
+                     "capture next to this file" % (BUDGET_CAP, REPS)})
 print(json.dumps(info))
