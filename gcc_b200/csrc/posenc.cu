@@ -219,10 +219,15 @@ __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64
                                               long long* n_idle = nullptr) {
   constexpr int M = GCCB_CF_B, HALF = M / 2;
   const int tid = threadIdx.x;
-  // rl[0..nr): pairs that rotate this round, rl[HALF-1], rl[HALF-2], ...: the others; rl[HALF] = nr.
-  // Two copies alternate between rounds, so an idle round (nr == 0) costs ONE barrier: the next
-  // round's writer never touches the copy a slow reader may still be looking at.
-  __shared__ int rl2[2][HALF + 1];
+  // One 16-byte record per pair and round: (p | q << 16, c, s, -), written in COMPACTED order: slots
+  // [0, nr) hold the pairs that rotate this round, the others fill the array from the top.  A block / column
+  // update then costs one 128-bit shared-memory load per pair instead of five scalar ones (the rounds are
+  // bound by shared-memory instruction throughput: three CTAs share an SM).  Two copies alternate between
+  // rounds, so an idle round (nr == 0) costs ONE barrier: the next round's writer never touches the copy a
+  // slow reader may still be looking at.  (cs / pq of the caller are no longer used.)
+  __shared__ float4 rec2[2][HALF];
+  __shared__ int nrot2[2];
+  (void)cs; (void)pq;
   for (int idx = tid; idx < M * M; idx += NT) {
     const int j = idx / M, i = idx - j * M;
     V[j * LD + i] = i == j ? 1.0f : 0.f;
@@ -232,15 +237,15 @@ __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64
   for (; sweep < max_sweeps; ++sweep) {
     int rotated = 0;
     for (int r = 0; r < M - 1; ++r) {
-      int* rl = rl2[r & 1];
+      float4* rec = rec2[r & 1];
       if (tid < 32) {                                      // warp 0: one lane per pair
         bool rot = false;
+        int p = 0, q = 0;
+        float c = 1.0f, sn = 0.f;
         if (tid < HALF) {
-          int p, q;
           if (tid == 0) { p = M - 1; q = r; }
           else { p = (r + tid) % (M - 1); q = (r + M - 1 - tid) % (M - 1); }
           if (p > q) { int t = p; p = q; q = t; }
-          float c = 1.0f, s = 0.f;
           const float app = A[p * LD + p], aqq = A[q * LD + q], apq = A[q * LD + p];
           // (diagonal of G = H + 2I lies in [1, 3]: the arithmetic mean is as good a scale as the geometric one)
           if (fabsf(apq) > tol * 0.5f * (fabsf(app) + fabsf(aqq))) {
@@ -252,35 +257,34 @@ __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64
             const float den = fabsf(d) + __fsqrt_rn(fmaf(d, d, two_apq * two_apq));
             const float t = __fdividef(d >= 0.f ? two_apq : -two_apq, den);
             c = rsqrtf(fmaf(t, t, 1.0f));
-            s = c * t;
+            sn = c * t;
             rot = true;
           }
-          cs[2 * tid] = c; cs[2 * tid + 1] = s; pq[tid] = p | (q << 16);
         }
-        // compact the rotating pairs: most rounds of a nearly diagonal problem rotate only a few
         const unsigned mask = __ballot_sync(0xffffffffu, rot);
         if (tid < HALF) {
-          const unsigned below = mask & ((1u << tid) - 1u);
-          if (rot) rl[__popc(below)] = tid;
-          else rl[HALF - 1 - (tid - __popc(below))] = tid;
+          const int below = __popc(mask & ((1u << tid) - 1u));
+          const int slot = rot ? below : HALF - 1 - (tid - below);
+          rec[slot] = make_float4(__int_as_float(p | (q << 16)), c, sn, 0.f);
         }
-        if (tid == 0) rl[HALF] = __popc(mask);
+        if (tid == 0) nrot2[r & 1] = __popc(mask);
       }
       __syncthreads();
-      const int nr = rl[HALF];
+      const int nr = nrot2[r & 1];
       if (nr == 0) { if (n_idle) ++*n_idle; continue; }
       if (n_work) ++*n_work;
       rotated = 1;
-      // A <- J^T A J on 2x2 blocks (rows of pair a, columns of pair b); only blocks with a rotating
-      // pair on either side change: (a in R, b any) and (a not in R, b in R)
+      // A <- J^T A J on 2x2 blocks (rows of pair a, columns of pair b); only blocks with a rotating pair on
+      // either side change: (a in [0, nr), b any) and (a in [nr, HALF), b in [0, nr))
       const int n_first = nr * HALF, n_items = nr * (M - nr);
       for (int item = tid; item < n_items; item += NT) {
-        int pa, pb;
-        if (item < n_first) { const int ia = item / HALF; pa = rl[ia]; pb = item - ia * HALF; }
-        else { const int it2 = item - n_first; const int ia = it2 / nr; pa = rl[HALF - 1 - ia]; pb = rl[it2 - ia * nr]; }
-        const int ca = pq[pa], cb = pq[pb];
+        int sa, sb;
+        if (item < n_first) { sa = item / HALF; sb = item - sa * HALF; }
+        else { const int it2 = item - n_first; const int ia = it2 / nr; sa = nr + ia; sb = it2 - ia * nr; }
+        const float4 ra = rec[sa], rb = rec[sb];
+        const int ca = __float_as_int(ra.x), cb = __float_as_int(rb.x);
         const int p1 = ca & 0xffff, q1 = ca >> 16, p2 = cb & 0xffff, q2 = cb >> 16;
-        const float c1 = cs[2 * pa], s1 = cs[2 * pa + 1], c2 = cs[2 * pb], s2 = cs[2 * pb + 1];
+        const float c1 = ra.y, s1 = ra.z, c2 = rb.y, s2 = rb.z;
         float a = A[p2 * LD + p1], b = A[q2 * LD + p1], c_ = A[p2 * LD + q1], d = A[q2 * LD + q1];
         // columns: [x y] -> [c2 x - s2 y, s2 x + c2 y]
         float a2 = c2 * a - s2 * b, b2 = s2 * a + c2 * b, c3 = c2 * c_ - s2 * d, d2 = s2 * c_ + c2 * d;
@@ -293,13 +297,12 @@ __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64
       // V <- V J: only the columns of rotating pairs
       for (int item = tid; item < nr * M; item += NT) {
         const int ir = item / M, i = item - ir * M;
-        const int pr = rl[ir];
-        const int code = pq[pr];
+        const float4 rr = rec[ir];
+        const int code = __float_as_int(rr.x);
         const int p = code & 0xffff, q = code >> 16;
-        const float c = cs[2 * pr], s = cs[2 * pr + 1];
         const float x = V[p * LD + i], y = V[q * LD + i];
-        V[p * LD + i] = c * x - s * y;
-        V[q * LD + i] = s * x + c * y;
+        V[p * LD + i] = rr.y * x - rr.z * y;
+        V[q * LD + i] = rr.z * x + rr.y * y;
       }
       __syncthreads();
     }
