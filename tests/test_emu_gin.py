@@ -60,7 +60,7 @@ def _oracle_view(b, views, pos, v):
                 sub_deg=b.sub_deg[v, :N], node_off=b.node_off[v].astype(np.int64))
 
 
-@pytest.mark.parametrize("L,H,B_,hops", [(3, 32, 5, 12), (5, 64, 5, 12), (3, 64, 14, 28)])
+@pytest.mark.parametrize("L,H,B_,hops", [(3, 32, 5, 12), (5, 64, 5, 12), (3, 64, 14, 28), (3, 128, 5, 12), (5, 256, 6, 16), (5, 128, 24, 64)])
 def test_gin_forward_backward_vs_oracle(L, H, B_, hops):
     """(the third case spans several 64-row tiles: graphs straddle tile boundaries in the pooling,
     aggregation and weight-gradient kernels)"""
@@ -68,6 +68,7 @@ def test_gin_forward_backward_vs_oracle(L, H, B_, hops):
     rng = np.random.default_rng(L * 100 + H)
     b, views, pos = _batch(B_, hops)
     assert B_ < 10 or int(b.node_off[0, b.B]) > 128
+    print("N =", int(b.node_off[0, b.B]))
     cfg = glayout.make_cfg(num_layers=L, hidden=H)
     lay = glayout.c_layout(Lb, cfg)
     flat, sd, sl = _params(cfg, rng)
