@@ -240,6 +240,7 @@ gin_bwd_reduce_kernel(int mode, const int32_t* __restrict__ node_off_v, int B,
   float m_g4 = 0.f, m_g4y = 0.f;
   if (mode == 1) { m_g4 = (float)(redB_in[c] * invN); m_g4y = (float)(redB_in[H + c] * invN); }
   float s = 0.f, q = 0.f;
+#pragma unroll 4
   for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
     float ya, yhat, g4;
     chain_g4(z2[(size_t)r * H + c], dh[(size_t)r * H + c], A, Bc, c, &ya, &yhat, &g4);
@@ -774,6 +775,7 @@ gin_bwd_dz2_kernel(const int32_t* __restrict__ node_off_v, int B, const float* _
     for (int c = tid; c < H; c += 256) { coef1_out[c] = coef[2 * H + c]; coef1_out[H + c] = coef[3 * H + c]; }
   const BnC A = bnc(coef + 4 * H, H), Bc = bnc(coef + 8 * H, H);
   const size_t total = (size_t)(N > 0 ? N : 0) * H;
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % H);
     float ya, yhat, g4;
@@ -804,6 +806,7 @@ gin_bwd_g1_kernel(const int32_t* __restrict__ node_off_v, int B, const float* __
   constexpr int RPB = 256 / H > 0 ? 256 / H : 1;
   const int c = tid % H, rl = tid / H;
   float s = 0.f, q = 0.f;
+#pragma unroll 4
   for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
     const size_t i = (size_t)r * H + c;
     const float zv = z1[i];
@@ -844,6 +847,7 @@ gin_bwd_dz1_kernel(const int32_t* __restrict__ node_off_v, int B, const float* _
   __syncthreads();
   const BnC C1 = bnc(coef, H);
   const size_t total = (size_t)(N > 0 ? N : 0) * H;
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % H);
     const float zhat = (z1[i] - C1.mean[c]) * C1.invstd[c];

@@ -215,6 +215,7 @@ gin_bn_tail_kernel(int mode, const int32_t* __restrict__ node_off_v, int B,
   const float sca = coef_a[2 * H + c], sha = coef_a[3 * H + c];
   float s = 0.f, q = 0.f;
   if (mode == 0) {
+#pragma unroll 4                                          // independent loads: several rows in flight per thread
     for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
       float y = fmaxf(fmaf(z2[(size_t)r * H + c], sca, sha), 0.f);
       s += y;
@@ -231,6 +232,7 @@ gin_bn_tail_kernel(int mode, const int32_t* __restrict__ node_off_v, int B,
     }
   } else {
     const float scb = coef_b[2 * H + c], shb = coef_b[3 * H + c];
+#pragma unroll 4
     for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
       float y = fmaxf(fmaf(z2[(size_t)r * H + c], sca, sha), 0.f);
       h_out[(size_t)r * H + c] = fmaxf(fmaf(y, scb, shb), 0.f);

@@ -110,7 +110,7 @@ template <int BN>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGE_F = 128 * 33;                 // epilogue transpose buffer (floats)
-  static constexpr size_t TOTAL = 1024 + (size_t)STAGES * STAGE_BYTES + STAGE_F * 4 + 2 * 32 * 4 * 4 + 256;
+  static constexpr size_t TOTAL = 1024 + (size_t)STAGES * STAGE_BYTES + STAGE_F * 4 + 2 * 256 * 4 + 256;
 };
 
 template <int BN>
@@ -121,8 +121,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* tiles = base;                                       // [STAGES][A | B]
   float* stage_t = (float*)(base + (size_t)STAGES * S::STAGE_BYTES);   // [128][33]
-  float* colpart = stage_t + S::STAGE_F;                              // [2][4][32]
-  uint64_t* bars = (uint64_t*)(colpart + 2 * 4 * 32);
+  float* colpart = stage_t + S::STAGE_F;                              // [2 (chunk parity)][2][4][32]
+  uint64_t* bars = (uint64_t*)(colpart + 2 * 256);
   uint64_t* full = bars;                 // [STAGES]   TMA -> MMA
   uint64_t* empty = bars + STAGES;       // [STAGES]   MMA -> TMA
   uint64_t* tfull = bars + 2 * STAGES;   // [2]        MMA -> epilogue
@@ -236,58 +236,60 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const int col0 = nt * BN + c0;
-          float v[32];
+          // bias / scale, then stage the warp's 32 x 32 block in shared memory (row pitch 33: conflict-free both
+          // ways) so that global stores are row-contiguous: a TMEM lane holds one ROW, and storing from the
+          // registers directly would scatter every warp store over 32 rows
+          float* stw = stage_t + ew * 32 * 33;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[j]) * g.alpha;
             if (g.bias) x += g.bias[col0 + j];
-            v[j] = row_ok ? x : 0.f;
+            stw[lane * 33 + j] = row_ok ? x : 0.f;
           }
-          if (row_ok) {
-            if (outf) {
-              float4* dst = reinterpret_cast<float4*>(outf + (size_t)row * g.ldo + col0);
+          __syncwarp();
+          {
+            const int cg4 = (lane & 7) * 4, rsub = lane >> 3;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (g.out_bf16) {
-              uint4* dst = reinterpret_cast<uint4*>(g.out_bf16 + (size_t)row * g.ldo + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-                u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-                dst[j] = u;
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rsub;
+              const int grow = mt * BM + ew * 32 + rr;
+              if (grow < M) {
+                const float x0 = stw[rr * 33 + cg4], x1 = stw[rr * 33 + cg4 + 1], x2 = stw[rr * 33 + cg4 + 2],
+                            x3 = stw[rr * 33 + cg4 + 3];
+                if (outf) *reinterpret_cast<float4*>(outf + (size_t)grow * g.ldo + col0 + cg4) = make_float4(x0, x1, x2, x3);
+                if (g.out_bf16) {
+                  const __nv_bfloat162 p0 = __floats2bfloat162_rn(x0, x1), p1 = __floats2bfloat162_rn(x2, x3);
+                  uint2 u;
+                  u.x = *reinterpret_cast<const uint32_t*>(&p0);
+                  u.y = *reinterpret_cast<const uint32_t*>(&p1);
+                  *reinterpret_cast<uint2*>(g.out_bf16 + (size_t)grow * g.ldo + col0 + cg4) = u;
+                }
               }
             }
           }
           if (g.colstats) {
-            // column sums over the 128 rows of the tile: transpose through shared memory (row pitch 33:
-            // conflict-free both ways), 4 row groups x 32 columns, then one float64 atomic per column
-#pragma unroll
-            for (int j = 0; j < 32; ++j) stage_t[row_in_tile * 33 + j] = v[j];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int cc = et & 31, rq = et >> 5;
-            float s = 0.f, q = 0.f;
+            // column sums over the tile's 128 rows: lane = column over the warp's 32 staged rows, the 4 warps
+            // meet in colpart (double-buffered by chunk parity: one named barrier per chunk), then one float64
+            // atomic per column
+            float sacc = 0.f, qacc = 0.f;
 #pragma unroll 8
             for (int rr = 0; rr < 32; ++rr) {
-              const float x = stage_t[(rq * 32 + rr) * 33 + cc];
-              s += x;
-              q = fmaf(x, x, q);
+              const float x = stw[rr * 33 + lane];
+              sacc += x;
+              qacc = fmaf(x, x, qacc);
             }
-            colpart[(0 * 4 + rq) * 32 + cc] = s;
-            colpart[(1 * 4 + rq) * 32 + cc] = q;
+            float* cp = colpart + ((c0 >> 5) & 1) * 256;
+            cp[(0 * 4 + ew) * 32 + lane] = sacc;
+            cp[(1 * 4 + ew) * 32 + lane] = qacc;
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et < 64) {
-              const int which = et >> 5;
-              const float t = colpart[(which * 4 + 0) * 32 + cc] + colpart[(which * 4 + 1) * 32 + cc] +
-                              colpart[(which * 4 + 2) * 32 + cc] + colpart[(which * 4 + 3) * 32 + cc];
+              const int which = et >> 5, cc = et & 31;
+              const float t = cp[(which * 4 + 0) * 32 + cc] + cp[(which * 4 + 1) * 32 + cc] +
+                              cp[(which * 4 + 2) * 32 + cc] + cp[(which * 4 + 3) * 32 + cc];
               atomicAdd(&g.colstats[(size_t)which * g.N + col0 + cc], (double)t);
             }
           }
+          __syncwarp();                                    // the next chunk overwrites the staging block
         }
         tc_fence_before();
         __syncwarp();
@@ -438,54 +440,102 @@ int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32
   return check_launch("tc_gemm");
 }
 
-// fp32 -> bf16 (optionally transposed): dst[c][r] or dst[r][c], zero padded to [rows_pad][cols_pad]
+// fp32 -> bf16 (optionally transposed), optional per-column affine + ReLU first; zero padded to
+// [rows_pad][cols_pad] (dst [cols_pad][rows_pad] when transposed); rows >= *rows_dev are zeros.
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int lds, __nv_bfloat16* __restrict__ dst,
-                 int rows_pad, int cols_pad, int transpose, const int32_t* __restrict__ rows_dev,
+                 int rows_pad, int cols_pad, const int32_t* __restrict__ rows_dev,
                  const float* __restrict__ sc, const float* __restrict__ sh, int relu) {
-  __shared__ float tile[32][33];
   const int R = rows_dev ? min(max(*rows_dev, 0), rows) : rows;
-  auto load = [&](int r, int c) {
-    if (r >= R || c >= cols) return 0.f;
-    float v = src[(size_t)r * lds + c];
-    if (sc) v = fmaf(v, sc[c], sh[c]);
-    if (relu) v = fmaxf(v, 0.f);
-    return v;
-  };
-  if (!transpose) {
-    const size_t total = (size_t)rows_pad * cols_pad;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-      const int r = (int)(idx / cols_pad), c = (int)(idx - (size_t)r * cols_pad);
-      dst[idx] = __float2bfloat16_rn(load(r, c));
+  const size_t total = (size_t)rows_pad * cols_pad;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / cols_pad), c = (int)(idx - (size_t)r * cols_pad);
+    float v = 0.f;
+    if (r < R && c < cols) {
+      v = src[(size_t)r * lds + c];
+      if (sc) v = fmaf(v, sc[c], sh[c]);
+      if (relu) v = fmaxf(v, 0.f);
+    }
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// transposing variant: one 64 x 64 tile per CTA through shared memory: 128-bit coalesced reads along the source
+// rows, 32-bit (2 x bf16) coalesced writes along the destination rows; grid = all tiles (the weight-gradient
+// operands of a config-4 batch are 100k+ rows: the pass has to run near HBM speed)
+__global__ void __launch_bounds__(256)
+cast_bf16_t_kernel(const float* __restrict__ src, int rows, int cols, int lds, __nv_bfloat16* __restrict__ dst,
+                   int rows_pad, int cols_pad, const int32_t* __restrict__ rows_dev,
+                   const float* __restrict__ sc, const float* __restrict__ sh, int relu) {
+  __shared__ float tile[64][65];
+  const int R = rows_dev ? min(max(*rows_dev, 0), rows) : rows;
+  const int tcn = (cols_pad + 63) / 64;
+  const int r0 = (blockIdx.x / tcn) * 64, c0 = (blockIdx.x % tcn) * 64;
+  const int tid = threadIdx.x;
+  const bool vec_ok = (lds % 4) == 0 && ((uintptr_t)src % 16) == 0;
+  if (r0 >= R) {                                           // nothing valid in this row band: zeros
+    for (int i = tid; i < 64 * 32; i += 256) {
+      const int c = c0 + i / 32, r = r0 + (i % 32) * 2;
+      if (c < cols_pad && r < rows_pad) *reinterpret_cast<uint32_t*>(dst + (size_t)c * rows_pad + r) = 0u;
     }
     return;
   }
-  // dst is [cols_pad][rows_pad]: 32 x 32 tiles through shared memory (coalesced both ways)
-  const int tr = (rows_pad + 31) / 32, tcn = (cols_pad + 31) / 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-  for (int t = blockIdx.x; t < tr * tcn; t += gridDim.x) {
-    const int r0 = (t / tcn) * 32, c0 = (t % tcn) * 32;
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-      const int r = r0 + i, c = c0 + tx;
-      tile[i][tx] = load(r, c);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = tid + k * 256;                           // 1024 float4 slots: row = i / 16, 4 columns at (i % 16) * 4
+    const int rr = i >> 4, cc = (i & 15) * 4;
+    const int r = r0 + rr, c = c0 + cc;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < R) {
+      if (vec_ok && c + 3 < cols) {
+        const float4 t = *reinterpret_cast<const float4*>(src + (size_t)r * lds + c);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (c + q < cols) v[q] = src[(size_t)r * lds + c + q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (c + q < cols) {
+          if (sc) v[q] = fmaf(v[q], sc[c + q], sh[c + q]);
+          if (relu) v[q] = fmaxf(v[q], 0.f);
+        } else v[q] = 0.f;
+      }
     }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-      const int c = c0 + i, r = r0 + tx;
-      if (c < cols_pad && r < rows_pad) dst[(size_t)c * rows_pad + r] = __float2bfloat16_rn(tile[tx][i]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tile[rr][cc + q] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid + k * 256;                           // 2048 pairs: column = i / 32, rows 2 * (i % 32), +1
+    const int cc = i >> 5, rr = (i & 31) * 2;
+    const int c = c0 + cc, r = r0 + rr;
+    if (c < cols_pad && r < rows_pad) {                    // rows_pad is even (multiple of 64)
+      const __nv_bfloat162 pr = __floats2bfloat162_rn(tile[rr][cc], tile[rr + 1][cc]);
+      *reinterpret_cast<uint32_t*>(dst + (size_t)c * rows_pad + r) = *reinterpret_cast<const uint32_t*>(&pr);
     }
   }
 }
 
 int cast_bf16(const float* src, int rows, int cols, int lds, void* dst, int rows_pad, int cols_pad, int transpose,
               const int32_t* rows_dev, cudaStream_t stream, const float* sc, const float* sh, int relu) {
+  if (transpose && (rows_pad % 2) == 0) {
+    const int tiles = ((rows_pad + 63) / 64) * ((cols_pad + 63) / 64);
+    GCCB_LAUNCH(cast_bf16_t_kernel, tiles, 256, 0, stream, src, rows, cols, lds, (__nv_bfloat16*)dst, rows_pad,
+                cols_pad, rows_dev, sc, sh, relu);
+    return check_launch("cast_bf16 (transposed)");
+  }
+  if (transpose) {
+    set_last_error("cast_bf16: the transposed cast needs an even rows_pad");
+    return GCCB_ERR_BADARG;
+  }
   const size_t total = (size_t)rows_pad * cols_pad;
   int blocks = (int)((total + 1023) / 1024);
-  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
   if (blocks < 1) blocks = 1;
   GCCB_LAUNCH(cast_bf16_kernel, blocks, 256, 0, stream, src, rows, cols, lds, (__nv_bfloat16*)dst, rows_pad, cols_pad,
-              transpose, rows_dev, sc, sh, relu);
+              rows_dev, sc, sh, relu);
   return check_launch("cast_bf16");
 }
 
