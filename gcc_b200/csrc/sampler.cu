@@ -72,7 +72,7 @@ __device__ __forceinline__ bool adj_find(const int32_t* __restrict__ indices, in
 // Pass 1: walk + sort/unique + induced-degree count.  grid = 2B, block = GCCB_ST.
 // dyn smem: keys[P] ints, P = pow2 >= max_budget + HOPCAP.
 __global__ void __launch_bounds__(GCCB_ST)
-rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t n_nodes,
                        const int32_t* __restrict__ budget_table, int budget_table_len,
                        uint32_t restart_thresh, uint64_t key, const int64_t* __restrict__ seeds,
                        const int64_t* __restrict__ sample_ids, int B, int cap_n,
@@ -88,7 +88,8 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = blockIdx.x;            // view-major: slot = view * B + g
   const int view = slot / B, g = slot - view * B;
-  const int64_t seed64 = seeds[g];
+  int64_t seed64 = seeds[g];
+  seed64 = seed64 < 0 ? 0 : (seed64 >= n_nodes ? n_nodes - 1 : seed64);   // caller-supplied seeds: never read out of bounds
   const int seed = (int)seed64;
   const uint64_t sample = (uint64_t)sample_ids[g];
   int64_t sdeg = indptr[seed64 + 1] - indptr[seed64];
@@ -454,7 +455,7 @@ extern "C" int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds
     gccb::ensure_dyn_smem(k1, smem);
     gccb::ensure_dyn_smem(k3, smem);
   }
-  GCCB_LAUNCH(k1, 2 * B, GCCB_ST, smem, stream, graph->indptr, graph->indices, graph->budget_table,
+  GCCB_LAUNCH(k1, 2 * B, GCCB_ST, smem, stream, graph->indptr, graph->indices, graph->n_nodes, graph->budget_table,
               graph->budget_table_len, graph->restart_thresh, graph->key, seeds, sample_ids, B,
               cap_n, subv, subdeg, rowstart, pool, pool_cap, pool_counter, batch->counters, batch->flags);
   GCCB_LAUNCH(batch_offsets_kernel, 2, 256, 0, stream, batch->counters, B, batch->node_cap,

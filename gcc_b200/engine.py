@@ -106,6 +106,7 @@ class PretrainEngine:
             # go ahead of the queued sampler / eigensolver CTAs whenever an SM slot frees up
             self.train_stream = self._new_stream(0, -1)
         self.cur_buf = dataset.buffers
+        self._seed_ev = None
 
     # -------------------------------------------------------------------------------------------
     def _new_stream(self, group, priority):
@@ -132,7 +133,13 @@ class PretrainEngine:
         else:
             ds_.wait_stream(main)
         if seeds is not None:
-            ds_.wait_stream(main)                      # the caller's H2D copy of the seeds is ordered on `main`
+            # only the caller's H2D copy of the seeds has to be ordered before the sampler -- NOT the training
+            # stream's backlog (waiting on `main` here would hold the next batch's data path behind the
+            # previous step's training part and give the run-ahead away)
+            if self._seed_ev is not None:
+                ds_.wait_event(self._seed_ev)
+            else:
+                ds_.wait_stream(main)
             seeds.record_stream(ds_)
         with torch.cuda.stream(ds_):
             t = None
@@ -157,8 +164,11 @@ class PretrainEngine:
             return self._step(lr, seeds, _presampled)
         caller = torch.cuda.current_stream(self.dev)
         self.train_stream.wait_stream(caller)
+        self._seed_ev = None
         if seeds is not None:
             seeds.record_stream(self.train_stream)
+            self._seed_ev = torch.cuda.Event()
+            self._seed_ev.record(caller)               # after the caller's copy into `seeds`
         with torch.cuda.stream(self.train_stream):
             self._step(lr, seeds, False)
         caller.wait_stream(self.train_stream)
@@ -167,7 +177,8 @@ class PretrainEngine:
         """One optimisation step.  `seeds`: optional int64 CUDA tensor [B] (else drawn on device
         from the Philox stream); with prefetch on they seed the batch being PREPARED by this call
         (consumed `prefetch` steps later), like a DataLoader running ahead -- the first call
-        prepares prefetch+1 batches.  Returns nothing; read_stats() syncs."""
+        prepares prefetch+1 batches, of which only the first uses `seeds` (the rest are drawn on the
+        device).  Out-of-range seeds are clamped by the sampler.  Returns nothing; read_stats() syncs."""
         lib, st = self.lib, _lib.stream_ptr()
         ds, model, ema = self.ds, self.model, self.model_ema
         B, H, L = self.B, self.H, self.L
@@ -177,6 +188,8 @@ class PretrainEngine:
         elif self.prefetch:
             while self.prepared < self.global_step + self.depth:
                 self._prepare(seeds)
+                seeds = None        # warm-up: only the first batch of a multi-batch fill takes the caller's seeds,
+                                    # the others are drawn on the device (no duplicated batches)
             slot = self.global_step % self.depth
             buf = self.bufs[slot]
             torch.cuda.current_stream(self.dev).wait_event(self.ready[slot])

@@ -142,8 +142,6 @@ class GraphEncoder(nn.Module):
         self._nbt = torch.zeros(3 * (L - 1), dtype=torch.long)
         self._param_list = []
         self._bind_views(register=True)
-        self._grad_bufs = [None, None]
-        self._grad_flip = 0
         self.dropout_key = 0x9E3779B97F4A7C15 ^ (torch.initial_seed() & 0xFFFFFFFFFFFF)
         self._drop_step = 0
         self._scratch = {}
@@ -205,7 +203,6 @@ class GraphEncoder(nn.Module):
             nbt[i] = mod._buffers[leaf]
         self._flat, self._running, self._nbt = flat, running, nbt
         self._bind_views(register=False)
-        self._grad_bufs = [None, None]
         self._scratch = {}
         return self
 
@@ -277,13 +274,9 @@ class GraphEncoder(nn.Module):
         dev = self._flat.device
         own = grads_flat is None
         if own:
-            # alternate two buffers so that a p.grad that autograd "stole" from the previous backward
-            # never aliases the buffer being written now
-            self._grad_flip ^= 1
-            if self._grad_bufs[self._grad_flip] is None:
-                self._grad_bufs[self._grad_flip] = torch.empty(self._n_live, dtype=torch.float32, device=dev)
-            grads_flat = self._grad_bufs[self._grad_flip]
-            grads_flat.zero_()
+            # a fresh buffer per backward: autograd may keep the returned views as p.grad (or accumulate into
+            # them), so a buffer must never be recycled by a later backward
+            grads_flat = torch.zeros(self._n_live, dtype=torch.float32, device=dev)
         if ws is None:
             nbytes = lib.gccb_gin_backward_workspace(C.byref(self.cfg), buf.B, buf.node_cap)
             key = ("bwd", nbytes)
