@@ -154,40 +154,43 @@ gin_bwd_dh_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_t* 
                   const float* __restrict__ dpool_j, int DW, const float* __restrict__ da, int has_da,
                   float* __restrict__ dh) {
   __shared__ float scratch[8 * W];
-  __shared__ int hub_rows[8];
+  __shared__ int hub_rows[GCCB_TILE_ROWS];
   __shared__ int n_hub;
   const int N = node_off_v[B];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int PER = (W + 31) / 32;
-  for (int base = blockIdx.x * 8; base < N; base += gridDim.x * 8) {      // uniform over the CTA
+  // 64-row tiles, warps independent inside a tile; hub rows (split across the CTA) after the tile: two
+  // barriers per 64 rows
+  for (int row0 = blockIdx.x * GCCB_TILE_ROWS; row0 < N; row0 += gridDim.x * GCCB_TILE_ROWS) {
     if (tid == 0) n_hub = 0;
     __syncthreads();
-    const int r = base + warp;
-    if (r < N) {
+    for (int rr = warp; rr < GCCB_TILE_ROWS; rr += 8) {
+      const int r = row0 + rr;
+      if (r >= N) break;
       const int beg = indptr[r], end = indptr[r + 1];
       if (has_da && end - beg > GCCB_HUB_DEG) {
         if (lane == 0) hub_rows[atomicAdd(&n_hub, 1)] = r;   // deferred: split across the CTA below
-      } else {
-        const int g = graph_id[r];
-        float acc[PER];
+        continue;
+      }
+      const int g = graph_id[r];
+      float acc[PER];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        int c = lane + 32 * j;
+        acc[j] = c < W ? dpool_j[(size_t)g * DW + c] : 0.f;
+      }
+      if (has_da) {
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
           int c = lane + 32 * j;
-          acc[j] = c < W ? dpool_j[(size_t)g * DW + c] : 0.f;
+          if (c < W) acc[j] += da[(size_t)r * W + c];
         }
-        if (has_da) {
+        gather_range<W>(da, indices, beg, end, lane, acc);
+      }
 #pragma unroll
-          for (int j = 0; j < PER; ++j) {
-            int c = lane + 32 * j;
-            if (c < W) acc[j] += da[(size_t)r * W + c];
-          }
-          gather_range<W>(da, indices, beg, end, lane, acc);
-        }
-#pragma unroll
-        for (int j = 0; j < PER; ++j) {
-          int c = lane + 32 * j;
-          if (c < W) dh[(size_t)r * W + c] = acc[j];
-        }
+      for (int j = 0; j < PER; ++j) {
+        int c = lane + 32 * j;
+        if (c < W) dh[(size_t)r * W + c] = acc[j];
       }
     }
     __syncthreads();

@@ -511,34 +511,37 @@ gin_agg_cast_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_t
                     const int32_t* __restrict__ indices, const float* __restrict__ h, float eps_gin,
                     float* __restrict__ a_out, __nv_bfloat16* __restrict__ a16) {
   __shared__ float scratch[8 * W];
-  __shared__ int hub_rows[8];
+  __shared__ int hub_rows[GCCB_TILE_ROWS];
   __shared__ int n_hub;
   const int N = node_off_v[B];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int PER = (W + 31) / 32;
-  for (int base = blockIdx.x * 8; base < N; base += gridDim.x * 8) {
+  // 64-row tiles: the warps run through their rows without meeting; only the (rare) hub rows of a tile are
+  // deferred to a cooperative pass, i.e. two barriers per 64 rows
+  for (int row0 = blockIdx.x * GCCB_TILE_ROWS; row0 < N; row0 += gridDim.x * GCCB_TILE_ROWS) {
     if (tid == 0) n_hub = 0;
     __syncthreads();
-    const int r = base + warp;
-    if (r < N) {
+    for (int rr = warp; rr < GCCB_TILE_ROWS; rr += 8) {
+      const int r = row0 + rr;
+      if (r >= N) break;
       const int beg = indptr[r], end = indptr[r + 1];
       if (end - beg > GCCB_HUB_DEG) {
         if (lane == 0) hub_rows[atomicAdd(&n_hub, 1)] = r;
-      } else {
-        float acc[PER];
+        continue;
+      }
+      float acc[PER];
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-          const int c = lane + 32 * j;
-          acc[j] = c < W ? (1.0f + eps_gin) * h[(size_t)r * W + c] : 0.f;
-        }
-        gather_range<W>(h, indices, beg, end, lane, acc);
+      for (int j = 0; j < PER; ++j) {
+        const int c = lane + 32 * j;
+        acc[j] = c < W ? (1.0f + eps_gin) * h[(size_t)r * W + c] : 0.f;
+      }
+      gather_range<W>(h, indices, beg, end, lane, acc);
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-          const int c = lane + 32 * j;
-          if (c < W) {
-            a_out[(size_t)r * W + c] = acc[j];
-            a16[(size_t)r * W + c] = __float2bfloat16_rn(acc[j]);
-          }
+      for (int j = 0; j < PER; ++j) {
+        const int c = lane + 32 * j;
+        if (c < W) {
+          a_out[(size_t)r * W + c] = acc[j];
+          a16[(size_t)r * W + c] = __float2bfloat16_rn(acc[j]);
         }
       }
     }
@@ -612,7 +615,7 @@ static int run_forward_tc(const FwdArgs& a) {
   }
   const float* hin = x0;
   const float* P = a.params;
-  const int agg_grid = (cap + 7) / 8 < 1184 ? (cap + 7) / 8 : 1184;
+  const int agg_grid = tiles < 1184 ? tiles : 1184;
   for (int l = 0; l < d.L - 1; ++l) {
     float* a_l = (float*)(a.acts + a.al.a[l]);
     float* z1 = (float*)(a.acts + a.al.z1[l]);
