@@ -106,28 +106,36 @@ struct GemmArgs {
   int splits;
 };
 
-template <int BN>
+// BRES: the whole B operand (N == BN rows, K <= 256) stays resident in shared memory for the life of the CTA --
+// the GIN MLP case (a 256 x 256 weight matrix = 128 KB of bf16): only the A tiles stream through the ring, so a
+// 128-row tile costs 64 KB of L2 -> shared-memory traffic instead of 192 KB.
+template <int BN, bool BRES>
 struct Smem {
-  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = BRES ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int BRES_KB = 4;                        // k-blocks of the resident operand (K <= 256)
+  static constexpr size_t BRES_BYTES = BRES ? (size_t)BRES_KB * B_BYTES : 0;
   static constexpr int STAGE_F = 128 * 33;                 // epilogue transpose buffer (floats)
-  static constexpr size_t TOTAL = 1024 + (size_t)STAGES * STAGE_BYTES + STAGE_F * 4 + 2 * 256 * 4 + 256;
+  static constexpr size_t TOTAL = 1024 + BRES_BYTES + (size_t)STAGES * STAGE_BYTES + STAGE_F * 4 + 2 * 256 * 4 + 256;
 };
 
-template <int BN>
+template <int BN, bool BRES>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  using S = Smem<BN>;
+  using S = Smem<BN, BRES>;
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* tiles = base;                                       // [STAGES][A | B]
-  float* stage_t = (float*)(base + (size_t)STAGES * S::STAGE_BYTES);   // [128][33]
+  unsigned char* bres = base;                                        // [BRES_KB][B] (BRES only)
+  unsigned char* tiles = base + S::BRES_BYTES;                       // [STAGES][A | B]  (BRES: [STAGES][A])
+  float* stage_t = (float*)(tiles + (size_t)STAGES * S::STAGE_BYTES);   // [128][33]
   float* colpart = stage_t + S::STAGE_F;                              // [2 (chunk parity)][2][4][32]
   uint64_t* bars = (uint64_t*)(colpart + 2 * 256);
   uint64_t* full = bars;                 // [STAGES]   TMA -> MMA
   uint64_t* empty = bars + STAGES;       // [STAGES]   MMA -> TMA
   uint64_t* tfull = bars + 2 * STAGES;   // [2]        MMA -> epilogue
   uint64_t* tempty = bars + 2 * STAGES + 2;   // [2]   epilogue -> MMA
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  uint64_t* bfull = bars + 2 * STAGES + 4;    // [1]   resident B operand landed
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.m_dev ? min(max(*g.m_dev, 0), g.M_cap) : g.M_cap;
@@ -143,6 +151,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_THREADS / 32); }
+    mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {                       // TMEM allocation: one full warp; the same warp frees it
@@ -164,6 +173,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         int stage = 0;
         uint32_t phase = 0;
+        if (BRES && blockIdx.x < num_tiles) {              // the whole B operand, once
+          mbar_expect_tx(bfull, (uint32_t)(nkb * S::B_BYTES));
+          for (int kb = 0; kb < nkb; ++kb) tma_load_2d(bres + (size_t)kb * S::B_BYTES, &map_b, kb * BK, 0, bfull);
+        }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
           for (int kb = kb0; kb < kb1; ++kb) {
@@ -171,7 +184,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             unsigned char* sa = tiles + (size_t)stage * S::STAGE_BYTES;
             mbar_expect_tx(&full[stage], S::STAGE_BYTES);
             tma_load_2d(sa, &map_a, kb * BK, mt * BM, &full[stage]);
-            tma_load_2d(sa + S::A_BYTES, &map_b, kb * BK, nt * BN, &full[stage]);
+            if (!BRES) tma_load_2d(sa + S::A_BYTES, &map_b, kb * BK, nt * BN, &full[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -184,6 +197,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        if (BRES && blockIdx.x < num_tiles) mbar_wait(bfull, 0);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
           tc_fence_after();
@@ -192,7 +206,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(tiles + (size_t)stage * S::STAGE_BYTES);
-            const uint32_t sb = sa + S::A_BYTES;
+            const uint32_t sb = BRES ? smem_u32(bres + (size_t)kb * S::B_BYTES) : sa + S::A_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advancing 16 elements (32 B) along K inside the 128-byte swizzle atom = +32 B on the start address
@@ -373,10 +387,10 @@ int sm_count() {
   return n;
 }
 
-template <int BN>
+template <int BN, bool BRES = false>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
-  auto k = tc_gemm_kernel<BN>;
-  const size_t smem = Smem<BN>::TOTAL;
+  auto k = tc_gemm_kernel<BN, BRES>;
+  const size_t smem = Smem<BN, BRES>::TOTAL;
   gccb::ensure_dyn_smem(k, smem);
   const int m_tiles = (g.M_cap + BM - 1) / BM, tiles = m_tiles * (g.N / BN);
   int gx = sm_count() / g.splits;
@@ -424,9 +438,11 @@ int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32
   } else {
     g.bias = bias; g.alpha = alpha; g.out_f32 = out_f32; g.out_bf16 = (__nv_bfloat16*)out_bf16; g.colstats = colstats;
   }
+  // the B operand stays in shared memory when it is one tile wide, at most 256 deep and reused by several row tiles
+  const bool bres = !via_scratch && N == BN && K <= 256 && (BN == 256 || BN == 128) && (M_cap + BM - 1) / BM > sm_count();
   switch (BN) {
-    case 256: launch<256>(ma, mb, g, stream); break;
-    case 128: launch<128>(ma, mb, g, stream); break;
+    case 256: if (bres) launch<256, true>(ma, mb, g, stream); else launch<256>(ma, mb, g, stream); break;
+    case 128: if (bres) launch<128, true>(ma, mb, g, stream); else launch<128>(ma, mb, g, stream); break;
     case 64: launch<64>(ma, mb, g, stream); break;
     default: launch<32>(ma, mb, g, stream); break;
   }
