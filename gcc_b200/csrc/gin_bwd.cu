@@ -220,6 +220,7 @@ __device__ __forceinline__ void chain_g4(float z2v, float dhv, const BnC& A, con
 }
 
 // Column reductions for BN_b (mode 0: sum g4, sum g4*yhat) and BN_a (mode 1: sum g3, sum g3*z2hat)
+// thread -> 4 consecutive columns of every RP-th row, two rows (4 x 16-byte loads) in flight per thread
 template <int H>
 __global__ void __launch_bounds__(256)
 gin_bwd_reduce_kernel(int mode, const int32_t* __restrict__ node_off_v, int B,
@@ -230,41 +231,65 @@ gin_bwd_reduce_kernel(int mode, const int32_t* __restrict__ node_off_v, int B,
                       const double* __restrict__ redB_in, double* __restrict__ red_out) {
   __shared__ float coef_a[4 * H];
   __shared__ float coef_b[4 * H];
-  __shared__ float red[2 * 8 * H];
+  __shared__ float red[2 * 1024];
   const int N = node_off_v[B];
   const int tid = threadIdx.x;
   bn_prepare(sums_a, N, H, ga, bea, bn_eps, coef_a, coef_a + H, coef_a + 2 * H, coef_a + 3 * H, nullptr, false, false, 0.f);
   bn_prepare(sums_b, N, H, gb, beb, bn_eps, coef_b, coef_b + H, coef_b + 2 * H, coef_b + 3 * H, nullptr, false, false, 0.f);
   __syncthreads();
   const BnC A = bnc(coef_a, H), Bc = bnc(coef_b, H);
-  constexpr int RPB = 256 / H > 0 ? 256 / H : 1;
-  const int c = tid % H, rl = tid / H;
+  constexpr int TPR = H / 4, RP = 256 / TPR;
+  const int c4 = (tid % TPR) * 4, rsub = tid / TPR;
   const float invN = N > 0 ? 1.0f / (float)N : 0.f;
-  float m_g4 = 0.f, m_g4y = 0.f;
-  if (mode == 1) { m_g4 = (float)(redB_in[c] * invN); m_g4y = (float)(redB_in[H + c] * invN); }
-  float s = 0.f, q = 0.f;
-#pragma unroll 4
-  for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
-    float ya, yhat, g4;
-    chain_g4(z2[(size_t)r * H + c], dh[(size_t)r * H + c], A, Bc, c, &ya, &yhat, &g4);
-    if (mode == 0) {
-      s += g4;
-      q = fmaf(g4, yhat, q);
-    } else {
-      float dy = Bc.sc[c] * (g4 - m_g4 - yhat * m_g4y);
-      float g3 = ya > 0.f ? dy : 0.f;
-      float z2hat = (z2[(size_t)r * H + c] - A.mean[c]) * A.invstd[c];
-      s += g3;
-      q = fmaf(g3, z2hat, q);
+  float m_g4[4] = {0.f, 0.f, 0.f, 0.f}, m_g4y[4] = {0.f, 0.f, 0.f, 0.f};
+  if (mode == 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m_g4[k] = (float)(redB_in[c4 + k] * invN); m_g4y[k] = (float)(redB_in[H + c4 + k] * invN); }
+  }
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  const int stride = gridDim.x * RP;
+  for (int r = blockIdx.x * RP + rsub; r < N; r += 2 * stride) {
+    float4 zv[2], dv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rr = r + u * stride;
+      const bool ok = rr < N;
+      zv[u] = ok ? *reinterpret_cast<const float4*>(z2 + (size_t)rr * H + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[u] = ok ? *reinterpret_cast<const float4*>(dh + (size_t)rr * H + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (r + u * stride < N) {
+        const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w}, dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c4 + k;
+          float ya, yhat, g4;
+          chain_g4(zz[k], dd[k], A, Bc, c, &ya, &yhat, &g4);
+          if (mode == 0) {
+            s[k] += g4;
+            q[k] = fmaf(g4, yhat, q[k]);
+          } else {
+            const float dy = Bc.sc[c] * (g4 - m_g4[k] - yhat * m_g4y[k]);
+            const float g3 = ya > 0.f ? dy : 0.f;
+            const float z2hat = (zz[k] - A.mean[c]) * A.invstd[c];
+            s[k] += g3;
+            q[k] = fmaf(g3, z2hat, q[k]);
+          }
+        }
+      }
     }
   }
-  red[(0 * RPB + rl) * H + c] = s;
-  red[(RPB + rl) * H + c] = q;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    red[(0 * RP + rsub) * H + c4 + k] = s[k];
+    red[(RP + rsub) * H + c4 + k] = q[k];
+  }
   __syncthreads();
   for (int idx = tid; idx < 2 * H; idx += 256) {
     int which = idx / H, cc = idx - which * H;
     float t = 0.f;
-    for (int j = 0; j < RPB; ++j) t += red[(which * RPB + j) * H + cc];
+    for (int j = 0; j < RP; ++j) t += red[(which * RP + j) * H + cc];
     atomicAdd(&red_out[which * H + cc], (double)t);
   }
 }
@@ -777,19 +802,43 @@ gin_bwd_dz2_kernel(const int32_t* __restrict__ node_off_v, int B, const float* _
   if (blockIdx.x == 0)
     for (int c = tid; c < H; c += 256) { coef1_out[c] = coef[2 * H + c]; coef1_out[H + c] = coef[3 * H + c]; }
   const BnC A = bnc(coef + 4 * H, H), Bc = bnc(coef + 8 * H, H);
-  const size_t total = (size_t)(N > 0 ? N : 0) * H;
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % H);
-    float ya, yhat, g4;
-    const float zv = z2[i];
-    chain_g4(zv, dh[i], A, Bc, c, &ya, &yhat, &g4);
-    const float dy = Bc.sc[c] * (g4 - rmean[c] - yhat * rmean[H + c]);
-    const float g3 = ya > 0.f ? dy : 0.f;
-    const float z2hat = (zv - A.mean[c]) * A.invstd[c];
-    const float dz = A.sc[c] * (g3 - rmean[2 * H + c] - z2hat * rmean[3 * H + c]);
-    dz2_out[i] = dz;
-    dz16[i] = __float2bfloat16_rn(dz);
+  // 4 consecutive columns per thread (16-byte accesses), two element groups in flight
+  const size_t total4 = (size_t)(N > 0 ? N : 0) * (H / 4);
+  const size_t gstride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + tid; i0 < total4; i0 += 2 * gstride) {
+    float4 zv[2], dv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t i = i0 + u * gstride;
+      const bool ok = i < total4;
+      zv[u] = ok ? reinterpret_cast<const float4*>(z2)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[u] = ok ? reinterpret_cast<const float4*>(dh)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t i = i0 + u * gstride;
+      if (i < total4) {
+        const int c0 = (int)(i % (H / 4)) * 4;
+        const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w}, dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + k;
+          float ya, yhat, g4;
+          chain_g4(zz[k], dd[k], A, Bc, c, &ya, &yhat, &g4);
+          const float dy = Bc.sc[c] * (g4 - rmean[c] - yhat * rmean[H + c]);
+          const float g3 = ya > 0.f ? dy : 0.f;
+          const float z2hat = (zz[k] - A.mean[c]) * A.invstd[c];
+          o[k] = A.sc[c] * (g3 - rmean[2 * H + c] - z2hat * rmean[3 * H + c]);
+        }
+        reinterpret_cast<float4*>(dz2_out)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 w;
+        w.x = *reinterpret_cast<const uint32_t*>(&p0);
+        w.y = *reinterpret_cast<const uint32_t*>(&p1);
+        reinterpret_cast<uint2*>(dz16)[i] = w;
+      }
+    }
   }
 }
 
@@ -800,32 +849,53 @@ gin_bwd_g1_kernel(const int32_t* __restrict__ node_off_v, int B, const float* __
                   float* __restrict__ dx1_g1, const double* __restrict__ sums_1, const float* __restrict__ g1w,
                   const float* __restrict__ be1, float bn_eps, double* __restrict__ red1_out) {
   __shared__ float coef[4 * H];
-  __shared__ float red[2 * 8 * H];
+  __shared__ float red[2 * 1024];
   const int N = node_off_v[B];
   const int tid = threadIdx.x;
   bn_prepare(sums_1, N, H, g1w, be1, bn_eps, coef, coef + H, coef + 2 * H, coef + 3 * H, nullptr, false, false, 0.f);
   __syncthreads();
   const BnC C1 = bnc(coef, H);
-  constexpr int RPB = 256 / H > 0 ? 256 / H : 1;
-  const int c = tid % H, rl = tid / H;
-  float s = 0.f, q = 0.f;
-#pragma unroll 4
-  for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
-    const size_t i = (size_t)r * H + c;
-    const float zv = z1[i];
-    const float pre = fmaf(zv, C1.sc[c], C1.sh[c]);
-    const float g = pre > 0.f ? dx1_g1[i] : 0.f;
-    dx1_g1[i] = g;
-    s += g;
-    q = fmaf(g, (zv - C1.mean[c]) * C1.invstd[c], q);
+  constexpr int TPR = H / 4, RP = 256 / TPR;
+  const int c4 = (tid % TPR) * 4, rsub = tid / TPR;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  const int stride = gridDim.x * RP;
+  for (int r = blockIdx.x * RP + rsub; r < N; r += 2 * stride) {
+    float4 zv[2], dv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rr = r + u * stride;
+      const bool ok = rr < N;
+      zv[u] = ok ? *reinterpret_cast<const float4*>(z1 + (size_t)rr * H + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[u] = ok ? *reinterpret_cast<const float4*>(dx1_g1 + (size_t)rr * H + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rr = r + u * stride;
+      if (rr < N) {
+        const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w}, dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c4 + k;
+          const float pre = fmaf(zz[k], C1.sc[c], C1.sh[c]);
+          o[k] = pre > 0.f ? dd[k] : 0.f;
+          s[k] += o[k];
+          q[k] = fmaf(o[k], (zz[k] - C1.mean[c]) * C1.invstd[c], q[k]);
+        }
+        *reinterpret_cast<float4*>(dx1_g1 + (size_t)rr * H + c4) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
   }
-  red[(0 * RPB + rl) * H + c] = s;
-  red[(RPB + rl) * H + c] = q;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    red[(0 * RP + rsub) * H + c4 + k] = s[k];
+    red[(RP + rsub) * H + c4 + k] = q[k];
+  }
   __syncthreads();
   for (int idx = tid; idx < 2 * H; idx += 256) {
     const int which = idx / H, cc = idx - which * H;
     float t = 0.f;
-    for (int j = 0; j < RPB; ++j) t += red[(which * RPB + j) * H + cc];
+    for (int j = 0; j < RP; ++j) t += red[(which * RP + j) * H + cc];
     atomicAdd(&red1_out[which * H + cc], (double)t);
   }
 }
@@ -849,14 +919,38 @@ gin_bwd_dz1_kernel(const int32_t* __restrict__ node_off_v, int B, const float* _
   }
   __syncthreads();
   const BnC C1 = bnc(coef, H);
-  const size_t total = (size_t)(N > 0 ? N : 0) * H;
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % H);
-    const float zhat = (z1[i] - C1.mean[c]) * C1.invstd[c];
-    const float dz = C1.sc[c] * (g1_dz1[i] - rmean[c] - zhat * rmean[H + c]);
-    g1_dz1[i] = dz;
-    dz16[i] = __float2bfloat16_rn(dz);
+  const size_t total4 = (size_t)(N > 0 ? N : 0) * (H / 4);
+  const size_t gstride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + tid; i0 < total4; i0 += 2 * gstride) {
+    float4 zv[2], gv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t i = i0 + u * gstride;
+      const bool ok = i < total4;
+      zv[u] = ok ? reinterpret_cast<const float4*>(z1)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      gv[u] = ok ? reinterpret_cast<const float4*>(g1_dz1)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t i = i0 + u * gstride;
+      if (i < total4) {
+        const int c0 = (int)(i % (H / 4)) * 4;
+        const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w}, gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + k;
+          const float zhat = (zz[k] - C1.mean[c]) * C1.invstd[c];
+          o[k] = C1.sc[c] * (gg[k] - rmean[c] - zhat * rmean[H + c]);
+        }
+        reinterpret_cast<float4*>(g1_dz1)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 w;
+        w.x = *reinterpret_cast<const uint32_t*>(&p0);
+        w.y = *reinterpret_cast<const uint32_t*>(&p1);
+        reinterpret_cast<uint2*>(dz16)[i] = w;
+      }
+    }
   }
 }
 

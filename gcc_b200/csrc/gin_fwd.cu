@@ -199,7 +199,7 @@ gin_bn_tail_kernel(int mode, const int32_t* __restrict__ node_off_v, int B,
                    float momentum, double* __restrict__ sums_b_out, float* __restrict__ h_out) {
   __shared__ float coef_a[4 * H];
   __shared__ float coef_b[4 * H];
-  __shared__ float red[2 * 8 * H];
+  __shared__ float red[2 * 1024];
   const int N = node_off_v[B];
   const int tid = threadIdx.x;
   // BN_a running stats are updated by mode 0 only, BN_b's by mode 1 only (once each)
@@ -209,33 +209,73 @@ gin_bn_tail_kernel(int mode, const int32_t* __restrict__ node_off_v, int B,
     bn_prepare(sums_b_in, N, H, gb, beb, bn_eps, coef_b, coef_b + H, coef_b + 2 * H, coef_b + 3 * H,
                running_b, use_running != 0, update_running != 0, momentum);
   __syncthreads();
-  // thread -> fixed column c = tid % H, row lane = tid / H ; rows strided
-  constexpr int RPB = 256 / H > 0 ? 256 / H : 1;       // rows handled per pass (H <= 256)
-  const int c = tid % H, rl = tid / H;
-  const float sca = coef_a[2 * H + c], sha = coef_a[3 * H + c];
-  float s = 0.f, q = 0.f;
+  // thread -> 4 consecutive columns (one 16-byte access) of every RP-th row; four rows in flight per thread
+  // (this pass is bandwidth bound: N x H floats in, N x H out)
+  constexpr int TPR = H / 4, RP = 256 / TPR;
+  const int c4 = (tid % TPR) * 4, rsub = tid / TPR;
+  float sca[4], sha[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sca[k] = coef_a[2 * H + c4 + k]; sha[k] = coef_a[3 * H + c4 + k]; }
+  const int stride = gridDim.x * RP;
   if (mode == 0) {
-#pragma unroll 4                                          // independent loads: several rows in flight per thread
-    for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
-      float y = fmaxf(fmaf(z2[(size_t)r * H + c], sca, sha), 0.f);
-      s += y;
-      q = fmaf(y, y, q);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = blockIdx.x * RP + rsub; r < N; r += 4 * stride) {
+      float4 z[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + u * stride;
+        z[u] = rr < N ? *reinterpret_cast<const float4*>(z2 + (size_t)rr * H + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * stride < N) {
+          const float zz[4] = {z[u].x, z[u].y, z[u].z, z[u].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float y = fmaxf(fmaf(zz[k], sca[k], sha[k]), 0.f);
+            s[k] += y;
+            q[k] = fmaf(y, y, q[k]);
+          }
+        }
+      }
     }
-    red[(0 * RPB + rl) * H + c] = s;
-    red[(RPB + rl) * H + c] = q;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      red[(0 * RP + rsub) * H + c4 + k] = s[k];
+      red[(RP + rsub) * H + c4 + k] = q[k];
+    }
     __syncthreads();
     for (int idx = tid; idx < 2 * H; idx += 256) {
       int which = idx / H, cc = idx - which * H;
       float t = 0.f;
-      for (int j = 0; j < RPB; ++j) t += red[(which * RPB + j) * H + cc];
+      for (int j = 0; j < RP; ++j) t += red[(which * RP + j) * H + cc];
       atomicAdd(&sums_b_out[which * H + cc], (double)t);
     }
   } else {
-    const float scb = coef_b[2 * H + c], shb = coef_b[3 * H + c];
-#pragma unroll 4
-    for (int r = blockIdx.x * RPB + rl; r < N; r += gridDim.x * RPB) {
-      float y = fmaxf(fmaf(z2[(size_t)r * H + c], sca, sha), 0.f);
-      h_out[(size_t)r * H + c] = fmaxf(fmaf(y, scb, shb), 0.f);
+    float scb[4], shb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { scb[k] = coef_b[2 * H + c4 + k]; shb[k] = coef_b[3 * H + c4 + k]; }
+    for (int r = blockIdx.x * RP + rsub; r < N; r += 4 * stride) {
+      float4 z[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + u * stride;
+        z[u] = rr < N ? *reinterpret_cast<const float4*>(z2 + (size_t)rr * H + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + u * stride;
+        if (rr < N) {
+          const float zz[4] = {z[u].x, z[u].y, z[u].z, z[u].w};
+          float o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float y = fmaxf(fmaf(zz[k], sca[k], sha[k]), 0.f);
+            o[k] = fmaxf(fmaf(y, scb[k], shb[k]), 0.f);
+          }
+          *reinterpret_cast<float4*>(h_out + (size_t)rr * H + c4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
     }
   }
 }

