@@ -16,7 +16,7 @@ from gcc_b200.datasets.graph_dataset import LoadBalanceGraphDataset  # noqa: E40
 from gcc_b200.engine import PretrainEngine  # noqa: E402
 from gcc_b200.models import GraphEncoder  # noqa: E402
 
-cfg = bench.CONFIGS["c2"]
+cfg = bench.CONFIGS[sys.argv[3] if len(sys.argv) > 3 else "c2"]
 dev = torch.device("cuda")
 g = bench.make_graph_device(cfg, dev)
 B, L, H, K = cfg["batch"], cfg["layers"], cfg["hidden"], cfg["K"]
@@ -33,7 +33,7 @@ ema.load_state_dict(model.state_dict())
 model, ema = model.to(dev), ema.to(dev)
 with contextlib.redirect_stdout(sys.stderr):
     contrast = MemoryMoCo(H, None, K, 0.07, use_softmax=True).to(dev)
-eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=int(sys.argv[1]) if len(sys.argv) > 1 else 2)
+eng = PretrainEngine(ds, model, ema, contrast, moco=True, prefetch=int(sys.argv[1]) if len(sys.argv) > 1 else 4)
 for _ in range(12):
     eng.step(lr=0.005)
 torch.cuda.synchronize()

@@ -376,7 +376,8 @@ def test_engine_step_matches_oracle_and_learns():
             continue                                    # exactly-zero true gradient (feeds a BatchNorm)
         got = gflat[off:off + int(np.prod(shape))].reshape(shape)
         want = r["grads"][k].numpy() if k in r["grads"] else np.zeros(shape)
-        scale = max(np.abs(want).max(), 1e-6)
+        # (floor: apply_func.bn.weight has a true gradient of ~1e-6 at initialisation -- fp32 summation noise)
+        scale = max(np.abs(want).max(), 1e-4)
         assert np.allclose(got, want, rtol=5e-3, atol=2e-3 * scale), (k, np.abs(got - want).max(), scale)
     # weights after the first Adam step: update = lr * g/(|g|+eps) is sign-like, so entries whose
     # gradient is ~eps-sized are ill-conditioned in the reference too; require agreement elsewhere
