@@ -352,7 +352,14 @@ def run_ours(args, cfg):
     samp_ev, eng.timing = eng.timing, None
     cnt_acc, eng.count_acc = eng.count_acc, None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    rank_skew = None
     if world > 1:
+        # per-rank window and step-time percentiles: the collective makes every step cost the slowest rank's time
+        mine = torch.tensor([ms, med, ps[min(len(ps) - 1, int(0.95 * len(ps)))]], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_skew = {"window_ms": [round(float(x[0]), 3) for x in allr], "p50_ms": [round(float(x[1]), 3) for x in allr],
+                     "p95_ms": [round(float(x[2]), 3) for x in allr]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = 2.0 * B * world * args.steps / (ms_max / 1e3)
@@ -440,7 +447,7 @@ def run_ours(args, cfg):
                     "d2h_bytes_per_step": 16, "steps": n_e2e,
                     "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step (trains batch t, prepares a later batch from these seeds) -> stats D2H every step, host waits for the previous step's copy"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
-            "step_time": step_dist, "mode": args.mode,
+            "step_time": step_dist, "mode": args.mode, "rank_skew": rank_skew,
             "clocks": clk, "roofline": roofline, "eigensolver": eig, "phases_ms": phases,
             "loss": stats["loss"], "grad_norm": stats["grad_norm"]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
