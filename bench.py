@@ -403,24 +403,27 @@ def run_ours(args, cfg):
                                   .clip(max=len(cdf_host) - 1).astype(np.int64)).pin_memory()
     loss_ring = torch.zeros(4, 4, dtype=torch.float32).pin_memory()
     done = [torch.cuda.Event() for _ in range(4)]
-    seeds_ring = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(4)]
+    NSEED = 2 * (args.prefetch + 2)             # a slot is rewritten long after the sampler that reads it has run
+    seeds_ring = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(NSEED)]
     for i in range(2):
-        seeds_ring[i & 3].copy_(host_seeds[i], non_blocking=True)
-        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i & 3])
+        seeds_ring[i % NSEED].copy_(host_seeds[i], non_blocking=True)
+        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i % NSEED])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_losses = []
+    LAG = 2                                    # < ring depth 4
     for i in range(n_e2e):
-        seeds_ring[i & 3].copy_(host_seeds[2 + i], non_blocking=True)   # seeds of the batch prepared this step
-        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i & 3])
+        seeds_ring[(i + 2) % NSEED].copy_(host_seeds[2 + i], non_blocking=True)   # seeds of the batch prepared this step
+        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[(i + 2) % NSEED])
         loss_ring[i & 3].copy_(eng.stats, non_blocking=True)            # D2H of this step's loss / prob / grad norm
         done[i & 3].record()
-        if i >= 1:          # the reference's .item() per step (train.py:420-422), read one step late so that the
-            done[(i - 1) & 3].synchronize()                             # host enqueues step i while step i-1 runs
-            e2e_losses.append(float(loss_ring[(i - 1) & 3][0]))
-    done[(n_e2e - 1) & 3].synchronize()
-    e2e_losses.append(float(loss_ring[(n_e2e - 1) & 3][0]))
+        if i >= LAG:        # the reference's .item() per step (train.py:420-422), read LAG steps late so that the
+            done[(i - LAG) & 3].synchronize()                           # host enqueues ahead while those steps run
+            e2e_losses.append(float(loss_ring[(i - LAG) & 3][0]))
+    for i in range(max(n_e2e - LAG, 0), n_e2e):
+        done[i & 3].synchronize()
+        e2e_losses.append(float(loss_ring[i & 3][0]))
     eng.wait_data_streams()
     e1.record()
     barrier()
@@ -445,7 +448,7 @@ def run_ours(args, cfg):
             "pairs_per_sec": value / 2.0,
             "e2e": {"value": e2e_value, "unit": "subgraphs/sec", "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": 16, "steps": n_e2e,
-                    "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step (trains batch t, prepares a later batch from these seeds) -> stats D2H every step, host waits for the previous step's copy"},
+                    "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step (trains batch t, prepares a later batch from these seeds) -> stats D2H every step, the host reads each step's copy two steps later"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "step_time": step_dist, "mode": args.mode, "rank_skew": rank_skew,
             "clocks": clk, "roofline": roofline, "eigensolver": eig, "phases_ms": phases,

@@ -235,7 +235,16 @@ __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64
   __syncthreads();
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
-    int rotated = 0;
+    // One look at the whole triangle decides whether another sweep is needed (the same test the rounds
+    // apply): a converged matrix costs one barrier instead of M - 1 idle rounds.
+    if (max_sweeps > 1) {
+      int any = 0;
+      for (int idx = tid; idx < M * M; idx += NT) {
+        const int q = idx / M, p = idx - q * M;
+        if (p < q && fabsf(A[q * LD + p]) > tol * 0.5f * (fabsf(A[p * LD + p]) + fabsf(A[q * LD + q]))) any = 1;
+      }
+      if (!__syncthreads_or(any)) break;
+    }
     for (int r = 0; r < M - 1; ++r) {
       float4* rec = rec2[r & 1];
       if (tid < 32) {                                      // warp 0: one lane per pair
@@ -273,26 +282,44 @@ __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64
       const int nr = nrot2[r & 1];
       if (nr == 0) { if (n_idle) ++*n_idle; continue; }
       if (n_work) ++*n_work;
-      rotated = 1;
-      // A <- J^T A J on 2x2 blocks (rows of pair a, columns of pair b); only blocks with a rotating pair on
-      // either side change: (a in [0, nr), b any) and (a in [nr, HALF), b in [0, nr))
-      const int n_first = nr * HALF, n_items = nr * (M - nr);
+      // A <- J^T A J on 2x2 blocks (rows of pair a, columns of pair b).  A is symmetric and only its canonical
+      // triangle T(x, y) = A[max(x, y) * LD + min(x, y)] is kept up to date (the rotation test above and the
+      // caller read nothing else), so each UNORDERED pair of slots {a, b} is one work item instead of two;
+      // only blocks with a rotating slot change: a in [0, nr), b in [a, HALF).  Row a has HALF - a blocks:
+      // rows f and nr - 1 - f are folded into one line of constant width W = 2 HALF - nr + 1, which makes the
+      // item -> (a, b) map a single division (an odd nr leaves its middle row half used).
+      const int W = 2 * HALF - nr + 1, n_items = ((nr + 1) >> 1) * W;
       for (int item = tid; item < n_items; item += NT) {
+        const int f = item / W, j = item - f * W;
         int sa, sb;
-        if (item < n_first) { sa = item / HALF; sb = item - sa * HALF; }
-        else { const int it2 = item - n_first; const int ia = it2 / nr; sa = nr + ia; sb = it2 - ia * nr; }
-        const float4 ra = rec[sa], rb = rec[sb];
-        const int ca = __float_as_int(ra.x), cb = __float_as_int(rb.x);
-        const int p1 = ca & 0xffff, q1 = ca >> 16, p2 = cb & 0xffff, q2 = cb >> 16;
-        const float c1 = ra.y, s1 = ra.z, c2 = rb.y, s2 = rb.z;
-        float a = A[p2 * LD + p1], b = A[q2 * LD + p1], c_ = A[p2 * LD + q1], d = A[q2 * LD + q1];
-        // columns: [x y] -> [c2 x - s2 y, s2 x + c2 y]
+        if (j < HALF - f) { sa = f; sb = f + j; }
+        else { sa = nr - 1 - f; sb = sa + (j - (HALF - f)); if (sa == f) continue; }
+        const float4 ra = rec[sa];
+        const int ca = __float_as_int(ra.x);
+        const int p1 = ca & 0xffff, q1 = ca >> 16;
+        const float c1 = ra.y, s1 = ra.z;
+        if (sa == sb) {                                    // the pair's own 2 x 2 block: app, aqq change, apq -> 0
+          const float app = A[p1 * LD + p1], aqq = A[q1 * LD + q1], apq = A[q1 * LD + p1];
+          const float cc = c1 * c1, ss = s1 * s1, x2 = 2.0f * c1 * s1 * apq;
+          A[p1 * LD + p1] = cc * app - x2 + ss * aqq;
+          A[q1 * LD + q1] = ss * app + x2 + cc * aqq;
+          A[q1 * LD + p1] = 0.f;
+          continue;
+        }
+        const float4 rb = rec[sb];
+        const int cb = __float_as_int(rb.x);
+        const int p2 = cb & 0xffff, q2 = cb >> 16;
+        const float c2 = rb.y, s2 = rb.z;
+        const int i_a = max(p1, p2) * LD + min(p1, p2), i_b = max(p1, q2) * LD + min(p1, q2);
+        const int i_c = max(q1, p2) * LD + min(q1, p2), i_d = max(q1, q2) * LD + min(q1, q2);
+        float a = A[i_a], b = A[i_b], c_ = A[i_c], d = A[i_d];
+        // index 2 (pair b): [x y] -> [c2 x - s2 y, s2 x + c2 y]
         float a2 = c2 * a - s2 * b, b2 = s2 * a + c2 * b, c3 = c2 * c_ - s2 * d, d2 = s2 * c_ + c2 * d;
-        // rows: [x; y] -> [c1 x - s1 y; s1 x + c1 y]
-        A[p2 * LD + p1] = c1 * a2 - s1 * c3;
-        A[q2 * LD + p1] = c1 * b2 - s1 * d2;
-        A[p2 * LD + q1] = s1 * a2 + c1 * c3;
-        A[q2 * LD + q1] = s1 * b2 + c1 * d2;
+        // index 1 (pair a): [x; y] -> [c1 x - s1 y; s1 x + c1 y]
+        A[i_a] = c1 * a2 - s1 * c3;
+        A[i_b] = c1 * b2 - s1 * d2;
+        A[i_c] = s1 * a2 + c1 * c3;
+        A[i_d] = s1 * b2 + c1 * d2;
       }
       // V <- V J: only the columns of rotating pairs
       for (int item = tid; item < nr * M; item += NT) {
@@ -306,7 +333,6 @@ __device__ __forceinline__ int jacobi_ritz48(float* A, float* V, float* cs /*[64
       }
       __syncthreads();
     }
-    if (!rotated) break;
   }
   return sweep;
 }
