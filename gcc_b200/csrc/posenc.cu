@@ -59,8 +59,17 @@ namespace gccb {
 // (1/sqrt 2) is wider than any block and must not drag the cut down.
 #define GCCB_CF_MARGIN 0.05f
 #define GCCB_CF_MARGIN_BELOW 0.25f
+// Jacobi sweeps of the FIRST Ritz solve (random block after one low-degree filter: it never converges there).
+// Single-CTA kernels (n <= 384): none -- the Gram-Schmidt basis goes on as it is, ordered by its Rayleigh
+// quotients diag(H); measured on C2 ego-nets: 2.50 outer iterations instead of 2.76 for n <= 96 (the half-rotated
+// block of a one-sweep solve gave the second filter worse cut / degree estimates than the plain diagonal), 11 %
+// fewer cycles per ego-net, same residuals.  Cluster kernels (n > 384, hub ego-nets): one sweep -- without it the
+// largest ego-nets need 6-7 outer iterations instead of 3-4 and become the long pole of the batch.
 #ifndef GCCB_CF_SWEEPS0
-#define GCCB_CF_SWEEPS0 1          // Jacobi sweeps of the first Ritz solve (it only conditions the random block)
+#define GCCB_CF_SWEEPS0 0
+#endif
+#ifndef GCCB_CF_SWEEPS0_CLUSTER
+#define GCCB_CF_SWEEPS0_CLUSTER 1
 #endif
 #define GCCB_CF_NSM_A 96            // shared-memory block classes: n <= 96 (3 CTAs/SM) and
 #define GCCB_CF_NSM 160            //   n <= 160 (2 CTAs/SM),
@@ -69,6 +78,9 @@ namespace gccb {
 #define GCCB_CF_NSM_D1 1536        //   n <= 1536: cluster of 8 CTAs (DSMEM), 192-row slabs (75 KB per CTA);
 #define GCCB_CF_NSM_D 3584         //   n <= 3584: cluster of 8 CTAs, 448-row slabs; larger: L2 workspace
 #define GCCB_EIG_NCLASS 7
+#ifndef GCCB_CF_SMEM_PAD_A
+#define GCCB_CF_SMEM_PAD_A 0       // A/B builds: extra shared memory per n <= 96 CTA (lowers its CTAs per SM)
+#endif
 #ifndef GCCB_CAP_MID1
 #define GCCB_CAP_MID1 (148 * 3)     // persistent grid of the n <= 96 class (3 CTAs per SM)
 #endif
@@ -634,6 +646,24 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
     X[(size_t)(i / CB) * ld + (i % CB)] = (float)(int32_t)w.x * (1.0f / 2147483648.0f);
   }
   __syncthreads();
+#ifndef GCCB_CF_NO_DEFLATE
+  // The top eigenvector of D^-1/2 A D^-1/2 is known in closed form: v0 = sqrt(deg) (eigenvalue 1; ||v0||^2 =
+  // sum of degrees).  It becomes column 0 and is projected out of the random columns: the first filter
+  // amplifies the v0 component ~35x more than anything below 0.5, so without this every filtered column is
+  // nearly parallel to v0 and the first Gram-Schmidt pass runs on cancellation (second passes, one-column
+  // fallbacks).  Only the START block changes -- any start block is valid.
+  {
+    float* rdot0 = rd4;
+    column_sums(n, part, rdot0, rr2, 0, [&](int r, int c) { return X[(size_t)r * ld + c] / dinv[r]; });
+    const float inv_vv = 1.0f / (float)max(S.indptr[noff + n] - S.indptr[noff], 1);
+    for (int i = tid; i < n * CB; i += NT) {
+      const int r = i / CB, c = i - r * CB;
+      const float v = 1.0f / dinv[r];
+      X[(size_t)r * ld + c] = c == 0 ? v : fmaf(-rdot0[c] * inv_vv, v, X[(size_t)r * ld + c]);
+    }
+    __syncthreads();
+  }
+#endif
   float cut = 0.0f;                                     // the filter suppresses [-1, cut]
   float prev_worst = 3.0e38f;
   bool converged = false;
@@ -895,7 +925,9 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
     }
     GCCB_TICK(2);
     // ---- 48 x 48 Ritz problem: two-sided Jacobi, eigenvectors in Ws (tiles are dead now) ----------
-    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0 : GCCB_EIG_MAXSWEEP, &ph[6], &ph[7]);   // the first block is random: one sweep conditions it
+    const bool ritz_skipped = iter == 0 && GCCB_CF_SWEEPS0 == 0;       // W = I: only the ordering below applies
+    if (!ritz_skipped)
+      jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0 : GCCB_EIG_MAXSWEEP, &ph[6], &ph[7]);
     GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
@@ -913,11 +945,16 @@ __device__ __forceinline__ void posenc_chfsi_item(const int item, const int32_t*
       const float* w1 = Ws + perm[hi ? 32 + lane : 0] * LD;
       const float* row = X + (size_t)r * ld;
       float a0 = 0.f, a1 = 0.f;
+      if (ritz_skipped) {                                // a column permutation
+        a0 = row[perm[lane]];
+        a1 = row[perm[hi ? 32 + lane : 0]];
+      } else {
 #pragma unroll 8
-      for (int i = 0; i < CB; ++i) {
-        const float q = row[i];                          // broadcast
-        a0 = fmaf(q, w0[i], a0);
-        a1 = fmaf(q, w1[i], a1);
+        for (int i = 0; i < CB; ++i) {
+          const float q = row[i];                          // broadcast
+          a0 = fmaf(q, w0[i], a0);
+          a1 = fmaf(q, w1[i], a1);
+        }
       }
       __syncwarp();                                      // all lanes have read row r before it is overwritten
       X[(size_t)r * ld + lane] = a0;
@@ -1362,7 +1399,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
       __syncthreads();
     }
     GCCB_TICK(2);
-    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0 : GCCB_EIG_MAXSWEEP, &ph[6], &ph[7]);   // redundant per CTA, bit-identical
+    jacobi_ritz48<NT>(Gs, Ws, cs, pq, LD, iter == 0 ? 1e-3f : 1e-6f, iter == 0 ? GCCB_CF_SWEEPS0_CLUSTER : GCCB_EIG_MAXSWEEP, &ph[6], &ph[7]);   // redundant per CTA, bit-identical
     GCCB_TICK(3);
     for (int j = tid; j < CB; j += NT) {
       const float mj = Gs[j * LD + j];
@@ -1514,7 +1551,7 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   auto kbig = posenc_chfsi_kernel<1, GCCB_BIG_NT>;
   auto kmid = posenc_chfsi_kernel<1, 256>;
   auto ksmall = posenc_jacobi_kernel;
-  const size_t s_a = (size_t)2 * GCCB_CF_NSM_A * (GCCB_CF_B + 1) * sizeof(float);
+  const size_t s_a = (size_t)2 * GCCB_CF_NSM_A * (GCCB_CF_B + 1) * sizeof(float) + GCCB_CF_SMEM_PAD_A;
   const size_t s_b = (size_t)2 * GCCB_CF_NSM * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_c = (size_t)2 * GCCB_CF_NSM_C * (GCCB_CF_B + 1) * sizeof(float);
   const size_t s_d = (size_t)2 * ((GCCB_CF_NSM_D + CLUSTER - 1) / CLUSTER) * (GCCB_CF_B + 1) * sizeof(float);

@@ -30,7 +30,16 @@ namespace gccb {
 namespace tc {
 
 constexpr int BM = 128, BK = 64, STAGES = 4, UMMA_K = 16;
-constexpr int EPI_THREADS = 128, THREADS = 64 + EPI_THREADS;
+constexpr int BIAS_SMEM = 512;                             // floats of bias staged in shared memory
+// Epilogue warps: a warp may only touch the TMEM lane group (warp % 4), so the 128 accumulator rows always need
+// 4 warps; wide tiles are split by COLUMNS over PARTS such sets (BN = 256: 16 warps of 64 columns each).  One
+// epilogue warp per scheduler issues an instruction every ~5 cycles (ncu: 18 % issue-slot use, the tile loop was
+// bound by this warp's dependent chain, not by TMA or the tensor pipe); four per scheduler hide each other.
+template <int BN> struct Epi {
+  static constexpr int PARTS = BN >= 256 ? 4 : BN >= 128 ? 2 : 1;
+  static constexpr int WARPS = 4 * PARTS, THREADS_EPI = 32 * WARPS, THREADS = 64 + THREADS_EPI;
+  static constexpr int COLS = BN / PARTS;                  // columns per warp (a multiple of 32)
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -120,7 +129,7 @@ struct Smem {
 };
 
 template <int BN, bool BRES>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(Epi<BN>::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   using S = Smem<BN, BRES>;
@@ -128,7 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   unsigned char* bres = base;                                        // [BRES_KB][B] (BRES only)
   unsigned char* tiles = base + S::BRES_BYTES;                       // [STAGES][A | B]  (BRES: [STAGES][A])
   float* stage_t = (float*)(tiles + (size_t)STAGES * S::STAGE_BYTES);   // [128][33]
-  float* colpart = stage_t + S::STAGE_F;                              // [2 (chunk parity)][2][4][32]
+  float* colpart = stage_t + S::STAGE_F;                              // [512]: bias staging
   uint64_t* bars = (uint64_t*)(colpart + 2 * 256);
   uint64_t* full = bars;                 // [STAGES]   TMA -> MMA
   uint64_t* empty = bars + STAGES;       // [STAGES]   MMA -> TMA
@@ -150,7 +159,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_THREADS / 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], Epi<BN>::WARPS); }
     mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -160,6 +169,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // bias (zeros when absent) in shared memory when it fits: the epilogue then needs no global loads
+  float* bias_s = colpart;                                            // [BIAS_SMEM]
+  const bool bias_in_smem = g.N <= BIAS_SMEM;
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < g.N; i += blockDim.x) bias_s[i] = g.bias ? g.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -221,25 +235,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     } else {
-      // ===== epilogue warps 2..5: TMEM lanes 32 * (warp % 4) .. +31 ====================================
+      // ===== epilogue warps 2..: TMEM lanes 32 * (warp % 4) .. +31, columns [part * COLS, (part + 1) * COLS) ====
       const int ew = warp & 3;                              // TMEM lane group this warp may access
-      const int et = threadIdx.x - 64;                      // 0..127
+      const int part = (warp - 2) >> 2;
+      constexpr int COLS = Epi<BN>::COLS;
+      const int et = threadIdx.x - 64;                      // 0 .. THREADS_EPI - 1
       const int row_in_tile = ew * 32 + lane;
       int acc = 0;
       uint32_t acc_phase = 0;
       float* outf = g.out_f32 ? g.out_f32 + (size_t)split * g.M_cap * g.ldo : nullptr;
       if (g.colstats) {                                     // per-warp column accumulators (n_tiles == 1 with statistics)
-        for (int i = lane; i < 2 * BN; i += 32) stage_t[ew * (2 * BN) + i] = 0.f;
+        for (int i = lane; i < COLS; i += 32) {               // own columns only: the warps of a lane group share a row
+          stage_t[ew * (2 * BN) + part * COLS + i] = 0.f;
+          stage_t[ew * (2 * BN) + BN + part * COLS + i] = 0.f;
+        }
         __syncwarp();
       }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
         const int row = mt * BM + row_in_tile;
         const bool row_ok = row < M;
+        const bool full_tile = (mt + 1) * BM <= M;
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = part * COLS; c0 < (part + 1) * COLS; c0 += 32) {
           uint32_t r[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c0);
           asm volatile(
@@ -255,11 +275,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const int col0 = nt * BN + c0;
           float v[32];
+          if (bias_in_smem) {                               // bias (or zeros) staged in shared memory: 8 x LDS.128
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]) * g.alpha;
-            if (g.bias) x += g.bias[col0 + j];
-            v[j] = row_ok ? x : 0.f;
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = b4[j];
+              v[4 * j] = fmaf(__uint_as_float(r[4 * j]), g.alpha, b.x);
+              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), g.alpha, b.y);
+              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), g.alpha, b.z);
+              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), g.alpha, b.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), g.alpha, g.bias ? g.bias[col0 + j] : 0.f);
+          }
+          if (!full_tile) {                                 // only the last row tile has rows to mask
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
           }
           // a TMEM lane holds one ROW: each lane stores its 32 columns as 16-byte pieces (measured faster than
           // staging the block in shared memory for row-contiguous warp stores)
@@ -313,8 +345,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (g.colstats) {                                     // one float64 atomic per column and CTA
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < 2 * BN; i += EPI_THREADS) {
+        asm volatile("bar.sync 1, %0;" ::"n"(Epi<BN>::THREADS_EPI) : "memory");
+        for (int i = et; i < 2 * BN; i += Epi<BN>::THREADS_EPI) {
           const float t = stage_t[i] + stage_t[2 * BN + i] + stage_t[4 * BN + i] + stage_t[6 * BN + i];
           const int which = i / BN, c = i - which * BN;
           if (blockIdx.x < num_tiles) atomicAdd(&g.colstats[(size_t)which * g.N + c], (double)t);
@@ -408,7 +440,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& 
   if (gx > tiles) gx = tiles;
   dim3 grid(gx, g.splits);
   ++gccb::g_launch_count;
-  k<<<grid, THREADS, smem, stream>>>(ma, mb, g);
+  k<<<grid, Epi<BN>::THREADS, smem, stream>>>(ma, mb, g);
   return GCCB_OK;
 }
 
