@@ -25,7 +25,14 @@ class _Holder(nn.Module):
 
 class _BatchNormHolder(_Holder):
     """Class name contains 'BatchNorm' on purpose: train.py:360-365 (set_bn_train) switches
-    modules to train mode by class name."""
+    modules to train mode by class name, and the finetune branch resets the statistics the same way
+    (clear_bn, train.py:648-653)."""
+
+    def reset_running_stats(self):
+        # in place: the buffers are views of the encoder's flat running-statistics arrays
+        self._buffers["running_mean"].zero_()
+        self._buffers["running_var"].fill_(1.0)
+        self._buffers["num_batches_tracked"].zero_()
 
 
 def _child(mod, name, cls=_Holder):

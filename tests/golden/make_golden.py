@@ -6,7 +6,7 @@ DGL is absent here, so `dgl_stub.py` supplies the few DGL objects the hot path
 touches (documented [M] semantics); every other line that runs is the
 reference's own: gcc.contrastive.{memory_moco,criterions}, gcc.utils.misc,
 gcc.models.{graph_encoder,gin}, gcc.datasets.{graph_dataset,data_util} and
-train.py's train_moco / moment_update / clip_grad_norm.
+train.py's train_moco / moment_update / clip_grad_norm / train_finetune / test_finetune.
 
 Run:  python tests/golden/make_golden.py          (needs /root/reference)
 The fixtures are committed; the GPU box never needs /root/reference.
@@ -330,11 +330,107 @@ def golden_train(tag, num_layer, hidden, B, K, moco, num_steps=3):
     save("train_%s_golden.npz" % tag, **out)
 
 
+def golden_finetune(num_layer=3, hidden=32, B=8, num_classes=3):
+    """train.py:train_finetune / test_finetune (reference code) on fixed labeled batches: two ego-net batches
+    (NodeClassificationDatasetLabeled items: seed = row 0), one whole-graph batch built by the reference's
+    _rwr_trace_to_dgl_graph(entire_graph=True) (GraphClassificationDatasetLabeled items: the seed flag sits on
+    the max-degree node, positional features from the reference's own eigsh call), then one validation batch."""
+    import train as ref_train
+    from oracle import posenc as opos
+    torch.manual_seed(23)
+    np.random.seed(23)
+    g = synthetic.erdos_renyi(300, 1200, seed=4)
+    rt = orwr.restart_threshold(0.8)
+
+    def ego_batch(first_sid, budget=24):
+        graphs = []
+        for i in range(B):
+            sid = first_sid + i
+            seed = (sid * 37 + 11) % g.num_nodes
+            r = orwr.rwr_subgraph(g.indptr, g.indices, KEY, sid, 0, seed, budget, rt)
+            sg = dgl_stub.StubGraph.from_csr(r["indptr"], r["indices"])
+            sg.ndata["pos_undirected"] = torch.from_numpy(opos.posenc_exact(r["indptr"], r["indices"], r["n"], 32))
+            sd = torch.zeros(r["n"], dtype=torch.long)
+            sd[0] = 1
+            sg.ndata["seed"] = sd
+            graphs.append(sg)
+        return dgl_stub.batch(graphs)
+
+    def whole_batch(seed0):
+        graphs = []
+        for i in range(B):
+            wg = synthetic.erdos_renyi(12 + 3 * i, 30 + 9 * i, seed=seed0 + i)
+            parent = dgl_stub.StubGraph.from_csr(wg.indptr, wg.indices)
+            node_idx = int(parent.in_degrees().argmax())             # graph_dataset.py:361 (out == in: symmetric)
+            trace = [torch.tensor([node_idx])]
+            sg = ref_du._rwr_trace_to_dgl_graph(g=parent, seed=node_idx, trace=trace,
+                                                positional_embedding_size=32, entire_graph=True)
+            graphs.append(sg)
+        return dgl_stub.batch(graphs)
+
+    batches = [ego_batch(0), ego_batch(100), whole_batch(50)]
+    valid = ego_batch(200)
+    ys = [torch.from_numpy(np.random.randint(0, num_classes, size=B)).long() for _ in range(4)]
+
+    model = ref_ge.GraphEncoder(positional_embedding_size=32, max_node_freq=16, max_edge_freq=16, max_degree=512,
+                                freq_embedding_size=16, degree_embedding_size=16, output_dim=hidden,
+                                node_hidden_dim=hidden, edge_hidden_dim=hidden, num_layers=num_layer,
+                                num_step_set2set=6, num_layer_set2set=3, norm=True, gnn_model="gin",
+                                degree_input=True)
+    drop = _MaskDrop(KEY, hidden)
+    model.gnn.drop = drop
+    output_layer = torch.nn.Linear(hidden, num_classes)
+    criterion = torch.nn.CrossEntropyLoss()
+    optimizer = torch.optim.Adam(model.parameters(), lr=0.005, betas=(0.9, 0.999), weight_decay=1e-5)
+    out_opt = torch.optim.Adam(output_layer.parameters(), lr=0.005, betas=(0.9, 0.999), weight_decay=1e-5)
+    opt = types.SimpleNamespace(gpu="cpu", hidden_size=hidden, learning_rate=0.005, epochs=6, print_freq=1000,
+                                tb_freq=1000)
+    sw = types.SimpleNamespace(add_scalar=lambda *a, **k: None)
+    out = {"num_steps": np.array(len(batches)), "B": np.array(B), "hidden": np.array(hidden),
+           "num_layer": np.array(num_layer), "num_classes": np.array(num_classes),
+           "key": np.array(KEY, dtype=np.uint64), "epochs": np.array(opt.epochs)}
+    for k_, v in model.state_dict().items():
+        out["init/" + k_] = v.numpy().copy()
+    out["init_out/weight"] = output_layer.weight.detach().numpy().copy()
+    out["init_out/bias"] = output_layer.bias.detach().numpy().copy()
+
+    def dump(prefix, bg, y):
+        sp, si = bg.batched_csr()
+        out[prefix + "_indptr"], out[prefix + "_indices"] = sp, si
+        out[prefix + "_num_nodes"] = np.array(bg.batch_num_nodes)
+        out[prefix + "_pos"] = bg.ndata["pos_undirected"].numpy()
+        out[prefix + "_seed"] = bg.ndata["seed"].numpy()
+        out[prefix + "_y"] = y.numpy()
+
+    losses, f1s = [], []
+    for st, (bg, y) in enumerate(zip(batches, ys)):
+        dump("s%d" % st, bg, y)
+        drop.step, drop.layer = st, 0
+        # n_batch = len(loader) = 1, idx = 0: global_step = epoch * n_batch + idx = st  (train.py:231)
+        loss, f1 = ref_train.train_finetune(st, [(bg, y)], model, output_layer, criterion, optimizer, out_opt, sw, opt)
+        losses.append(loss)
+        f1s.append(f1)
+        for k_, v in model.state_dict().items():
+            out["s%d_model/%s" % (st, k_)] = v.numpy().copy()
+        out["s%d_out/weight" % st] = output_layer.weight.detach().numpy().copy()
+        out["s%d_out/bias" % st] = output_layer.bias.detach().numpy().copy()
+        for n_, p in model.named_parameters():
+            if p.grad is not None:
+                out["s%d_grad/%s" % (st, n_)] = p.grad.numpy().copy()
+    dump("valid", valid, ys[3])
+    vloss, vf1 = ref_train.test_finetune(len(batches), [(valid, ys[3])], model, output_layer, criterion, sw, opt)
+    with torch.no_grad():
+        out["valid_logits"] = output_layer(model(valid)).numpy().copy()
+    out["losses"], out["f1"] = np.array(losses), np.array(f1s)
+    out["valid_loss"], out["valid_f1"] = np.array(vloss), np.array(vf1)
+    save("train_finetune_golden.npz", **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     a = ap.parse_args()
-    todo = a.only.split(",") if a.only else ["moco", "misc", "posenc", "dataset", "train"]
+    todo = a.only.split(",") if a.only else ["moco", "misc", "posenc", "dataset", "train", "finetune"]
     if "moco" in todo:
         golden_moco()
     if "misc" in todo:
@@ -346,6 +442,8 @@ def main():
     if "train" in todo:
         golden_train("moco", num_layer=5, hidden=64, B=8, K=32, moco=True)
         golden_train("e2e", num_layer=2, hidden=32, B=8, K=32, moco=False)
+    if "finetune" in todo:
+        golden_finetune()
 
 
 if __name__ == "__main__":

@@ -16,8 +16,15 @@ epochs are 1-based and global_step = epoch * n_batch + idx (train.py:411,733), s
 one epoch into its warm-up exactly like the reference's.  What changes: the data loader and the whole
 step run on the GPU through gcc_b200.engine.PretrainEngine (no DataLoader workers, no .item() per step:
 loss / prob / grad-norm are accumulated on the device EVERY step and read every --print-freq steps, so
-the meters average over all steps like the reference's).  Fine-tuning (--finetune) is out of scope
-(SURVEY.md section 2).
+the meters average over all steps like the reference's).
+
+Fine-tuning (--finetune, train.py:175-337,516-545,631-660,788-792 of the reference): train_finetune /
+test_finetune keep the reference's signatures and arithmetic -- GraphEncoder forward/backward through the
+same device kernels (autograd Function), torch's Linear head, CrossEntropyLoss, clip_grad_value_(1), two
+torch Adam optimisers, micro-F1 per batch -- over the labeled datasets of gcc_b200/datasets/labeled.py,
+split by the reference's StratifiedKFold(10, shuffle, seed)[fold_idx].
+
+    python train.py --finetune --dataset usa_airport --resume saved/.../current.pth --epochs 30 --fold-idx 0
 """
 import argparse
 import os
@@ -89,17 +96,22 @@ def parse_option(argv=None):
     parser.add_argument("--gpu", default=None, type=int, nargs="+", help="GPU id to use.")
     parser.add_argument("--seed", type=int, default=0, help="random seed.")
     parser.add_argument("--max-steps", type=int, default=0, help="stop after this many steps (0 = full run)")
+    # finetune setting / cross validation (train.py:109-120)
+    parser.add_argument("--finetune", action="store_true")
+    parser.add_argument("--fold-idx", type=int, default=0, help="fold of the 10-fold stratified split")
+    parser.add_argument("--cv", action="store_true", help="run all 10 folds and print mean / std of the micro-F1")
     # fmt: on
     return parser.parse_args(argv)
 
 
 def option_update(opt):
     """Run naming of the reference (train.py:133-166)."""
-    prefix = "Pretrain_{}".format(opt.exp) if opt.exp else "Pretrain"
-    opt.model_name = "{}_{}_{}_{}_layer_{}_lr_{}_decay_{}_bsz_{}_hid_{}_samples_{}_nce_t_{}_nce_k_{}_rw_hops_{}_restart_prob_{}_aug_1st_ft_False_deg_{}_pos_{}_momentum_{}".format(
+    ft = bool(getattr(opt, "finetune", False))
+    prefix = ("FT_{}" if ft else "Pretrain_{}").format(opt.exp) if opt.exp else ("FT" if ft else "Pretrain")
+    opt.model_name = "{}_{}_{}_{}_layer_{}_lr_{}_decay_{}_bsz_{}_hid_{}_samples_{}_nce_t_{}_nce_k_{}_rw_hops_{}_restart_prob_{}_aug_1st_ft_{}_deg_{}_pos_{}_momentum_{}".format(
         prefix, "moco" if opt.moco else "e2e", os.path.basename(str(opt.dataset)), opt.model, opt.num_layer,
         opt.learning_rate, opt.weight_decay, opt.batch_size, opt.hidden_size, opt.num_samples, opt.nce_t,
-        opt.nce_k, opt.rw_hops, opt.restart_prob, opt.degree_embedding_size, opt.positional_embedding_size,
+        opt.nce_k, opt.rw_hops, opt.restart_prob, ft, opt.degree_embedding_size, opt.positional_embedding_size,
         opt.alpha)
     opt.model_folder = os.path.join(opt.model_path, opt.model_name)
     os.makedirs(opt.model_folder, exist_ok=True)
@@ -162,7 +174,194 @@ def train_moco(epoch, engine, sw, opt, is_main):
     return epoch_loss.avg
 
 
+class LabeledLoader:
+    """What DataLoader(Subset(dataset, idx), batch_size, collate_fn=labeled_batcher(), shuffle=...) is to the
+    reference (train.py:543-545,576-592): an iterable of (graph_q, y) with a length in batches."""
+
+    def __init__(self, dataset, indices, batch_size, shuffle, seed=0):
+        self.dataset, self.indices, self.batch_size, self.shuffle = dataset, np.asarray(indices), batch_size, shuffle
+        self.rng = np.random.RandomState(seed)
+
+    def __len__(self):
+        return self.dataset.num_batches(len(self.indices), self.batch_size)
+
+    def __iter__(self):
+        return self.dataset.batches(self.indices, self.batch_size, self.shuffle, self.rng)
+
+
+def train_finetune(epoch, train_loader, model, output_layer, criterion, optimizer, output_layer_optimizer, sw, opt):
+    """One finetune epoch (train.py:175-297): same order of operations as the reference."""
+    from sklearn.metrics import f1_score
+    n_batch = len(train_loader)
+    model.train()
+    output_layer.train()
+    batch_time, loss_meter, f1_meter = AverageMeter(), AverageMeter(), AverageMeter()
+    epoch_loss_meter, epoch_f1_meter, graph_size = AverageMeter(), AverageMeter(), AverageMeter()
+    max_num_nodes = max_num_edges = 0
+    end = time.time()
+    for idx, (graph_q, y) in enumerate(train_loader):
+        bsz = graph_q.batch_size
+        feat_q = model(graph_q)
+        assert feat_q.shape == (bsz, opt.hidden_size)
+        out = output_layer(feat_q)
+        loss = criterion(out, y)
+        optimizer.zero_grad()
+        output_layer_optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_value_(model.parameters(), 1)
+        torch.nn.utils.clip_grad_value_(output_layer.parameters(), 1)
+        global_step = epoch * n_batch + idx
+        lr_this_step = opt.learning_rate * warmup_linear(global_step / (opt.epochs * n_batch), 0.1)
+        for group in list(optimizer.param_groups) + list(output_layer_optimizer.param_groups):
+            group["lr"] = lr_this_step
+        optimizer.step()
+        output_layer_optimizer.step()
+        preds = out.argmax(dim=1)
+        f1 = f1_score(y.cpu().numpy(), preds.cpu().numpy(), average="micro")
+        f1_meter.update(f1, bsz)
+        epoch_f1_meter.update(f1, bsz)
+        loss_meter.update(loss.item(), bsz)
+        epoch_loss_meter.update(loss.item(), bsz)
+        graph_size.update(graph_q.number_of_nodes() / bsz, bsz)
+        max_num_nodes = max(max_num_nodes, graph_q.number_of_nodes())
+        max_num_edges = max(max_num_edges, graph_q.number_of_edges())
+        batch_time.update(time.time() - end)
+        end = time.time()
+        if (idx + 1) % opt.print_freq == 0:
+            print("Train: [{0}][{1}/{2}]\tBT {bt.val:.3f} ({bt.avg:.3f})\tloss {loss.val:.3f} ({loss.avg:.3f})\t"
+                  "f1 {f1.val:.3f} ({f1.avg:.3f})\tGS {gs.val:.3f} ({gs.avg:.3f})".format(
+                      epoch, idx + 1, n_batch, bt=batch_time, loss=loss_meter, f1=f1_meter, gs=graph_size))
+        if sw is not None and (idx + 1) % opt.tb_freq == 0:
+            sw.add_scalar("ft_loss", loss_meter.avg, global_step)
+            sw.add_scalar("ft_f1", f1_meter.avg, global_step)
+            sw.add_scalar("graph_size", graph_size.avg, global_step)
+            sw.add_scalar("lr", lr_this_step, global_step)
+            sw.add_scalar("graph_size/max", max_num_nodes, global_step)
+            sw.add_scalar("graph_size/max_edges", max_num_edges, global_step)
+            loss_meter.reset()
+            f1_meter.reset()
+            graph_size.reset()
+            max_num_nodes = max_num_edges = 0
+    return epoch_loss_meter.avg, epoch_f1_meter.avg
+
+
+def test_finetune(epoch, valid_loader, model, output_layer, criterion, sw, opt):
+    """Validation pass (train.py:300-337): eval-mode encoder (running BatchNorm statistics, no dropout)."""
+    from sklearn.metrics import f1_score
+    n_batch = len(valid_loader)
+    model.eval()
+    output_layer.eval()
+    epoch_loss_meter, epoch_f1_meter = AverageMeter(), AverageMeter()
+    for idx, (graph_q, y) in enumerate(valid_loader):
+        bsz = graph_q.batch_size
+        with torch.no_grad():
+            feat_q = model(graph_q)
+            assert feat_q.shape == (bsz, opt.hidden_size)
+            out = output_layer(feat_q)
+        loss = criterion(out, y)
+        preds = out.argmax(dim=1)
+        f1 = f1_score(y.cpu().numpy(), preds.cpu().numpy(), average="micro")
+        epoch_loss_meter.update(loss.item(), bsz)
+        epoch_f1_meter.update(f1, bsz)
+    global_step = (epoch + 1) * n_batch
+    if sw is not None:
+        sw.add_scalar("ft_loss/valid", epoch_loss_meter.avg, global_step)
+        sw.add_scalar("ft_f1/valid", epoch_f1_meter.avg, global_step)
+    print(f"Epoch {epoch}, loss {epoch_loss_meter.avg:.3f}, f1 {epoch_f1_meter.avg:.3f}")
+    return epoch_loss_meter.avg, epoch_f1_meter.avg
+
+
+def _make_encoder(args):
+    return GraphEncoder(positional_embedding_size=args.positional_embedding_size, max_node_freq=args.max_node_freq,
+                        max_edge_freq=args.max_edge_freq, max_degree=args.max_degree,
+                        freq_embedding_size=args.freq_embedding_size,
+                        degree_embedding_size=args.degree_embedding_size, output_dim=args.hidden_size,
+                        node_hidden_dim=args.hidden_size, edge_hidden_dim=args.hidden_size,
+                        num_layers=args.num_layer, num_step_set2set=args.set2set_iter,
+                        num_layer_set2set=args.set2set_lstm_layer, norm=args.norm, gnn_model=args.model,
+                        degree_input=True)
+
+
+def main_finetune(args, dataset=None):
+    """The --finetune branch of the reference's main (train.py:483-545,600-660,716-792): hyper-parameters come
+    from the pretraining checkpoint, 10-fold stratified split, BatchNorm running statistics reset, two Adam
+    optimisers, validation after the last epoch.  Returns the validation micro-F1."""
+    from sklearn.model_selection import StratifiedKFold
+
+    from gcc_b200.datasets.labeled import (GRAPH_CLASSIFICATION_DSETS, GraphClassificationDatasetLabeled,
+                                           NodeClassificationDatasetLabeled)
+    dev = torch.device("cuda", args.gpu[0] if isinstance(args.gpu, (list, tuple)) and args.gpu else (args.gpu or 0))
+    torch.cuda.set_device(dev)
+    np.random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    torch.cuda.manual_seed(args.seed)
+    checkpoint = None
+    if args.resume:
+        if os.path.isfile(args.resume):
+            print("=> loading checkpoint '{}'".format(args.resume))
+            checkpoint = torch.load(args.resume, map_location="cpu", weights_only=False)
+            pre = checkpoint["opt"]                        # train.py:491-504: the pretraining run's options win
+            for k in ("fold_idx", "gpu", "finetune", "resume", "cv", "dataset", "epochs", "num_workers", "batch_size"):
+                setattr(pre, k, getattr(args, k))
+            for k, v in vars(args).items():                # options this driver has and an older checkpoint lacks
+                if not hasattr(pre, k):
+                    setattr(pre, k, v)
+            args = pre
+        else:
+            print("=> no checkpoint found at '{}'".format(args.resume))
+    args = option_update(args)
+    if dataset is None:
+        kw = dict(dataset=args.dataset, rw_hops=args.rw_hops, subgraph_size=args.subgraph_size,
+                  restart_prob=args.restart_prob, positional_embedding_size=args.positional_embedding_size,
+                  device=dev, seed=args.seed, batch_size=args.batch_size)
+        dataset = (GraphClassificationDatasetLabeled(**kw) if args.dataset in GRAPH_CLASSIFICATION_DSETS
+                   else NodeClassificationDatasetLabeled(**kw))
+    labels = dataset.labels.tolist()
+    skf = StratifiedKFold(n_splits=10, shuffle=True, random_state=args.seed)
+    idx_list = list(skf.split(np.zeros(len(labels)), labels))
+    assert 0 <= args.fold_idx < 10, "fold_idx must be from 0 to 9."
+    train_idx, test_idx = idx_list[args.fold_idx]
+    train_loader = LabeledLoader(dataset, train_idx, args.batch_size, shuffle=True, seed=args.seed)
+    valid_loader = LabeledLoader(dataset, test_idx, args.batch_size, shuffle=False)
+    model = _make_encoder(args)
+    if checkpoint is not None:
+        model.load_state_dict(checkpoint["model"])
+    model = model.to(dev)
+    criterion = torch.nn.CrossEntropyLoss()
+    output_layer = torch.nn.Linear(in_features=args.hidden_size, out_features=dataset.num_classes).to(dev)
+    output_layer_optimizer = torch.optim.Adam(output_layer.parameters(), lr=args.learning_rate,
+                                              betas=(args.beta1, args.beta2), weight_decay=args.weight_decay)
+
+    def clear_bn(m):                                       # train.py:648-653
+        if m.__class__.__name__.find("BatchNorm") != -1:
+            m.reset_running_stats()
+
+    model.apply(clear_bn)
+    optimizer = torch.optim.Adam(model.parameters(), lr=args.learning_rate, betas=(args.beta1, args.beta2),
+                                 weight_decay=args.weight_decay)
+    sw = None
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+        sw = SummaryWriter(args.tb_folder)
+    except Exception:
+        sw = None
+    epoch = 0
+    for epoch in range(1, args.epochs + 1):
+        t0 = time.time()
+        loss, _ = train_finetune(epoch, train_loader, model, output_layer, criterion, optimizer,
+                                 output_layer_optimizer, sw, args)
+        print("epoch {}, loss {:.4f}, total time {:.2f}".format(epoch, loss, time.time() - t0))
+        state = {"opt": args, "model": model.state_dict(), "optimizer": optimizer.state_dict(), "epoch": epoch}
+        torch.save(state, os.path.join(args.model_folder, "current.pth"))
+        if epoch % args.save_freq == 0:
+            torch.save(state, os.path.join(args.model_folder, "ckpt_epoch_{epoch}.pth".format(epoch=epoch)))
+    _, valid_f1 = test_finetune(epoch, valid_loader, model, output_layer, criterion, sw, args)
+    return valid_f1
+
+
 def main(args):
+    if getattr(args, "finetune", False):
+        return main_finetune(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", str(args.gpu[0] if args.gpu else 0)))
@@ -231,4 +430,15 @@ def main(args):
 
 
 if __name__ == "__main__":
-    main(parse_option())
+    _args = parse_option()
+    if _args.cv and _args.finetune:                         # train.py:801-816
+        import copy
+        f1 = []
+        for fold_idx in range(10):
+            a = copy.deepcopy(_args)
+            a.fold_idx = fold_idx
+            f1.append(main(a))
+        print(f1)
+        print(f"Mean = {np.mean(f1)}; Std = {np.std(f1)}")
+    else:
+        main(_args)
