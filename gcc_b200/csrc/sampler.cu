@@ -67,6 +67,9 @@ __device__ __forceinline__ bool adj_find(const int32_t* __restrict__ indices, in
                                // vertices, ~1e5..1e6 neighbour probes) are the tail of these kernels
 #endif
 #define GCCB_SW (GCCB_ST / 32)
+#ifndef GCCB_SCAN_UNROLL
+#define GCCB_SCAN_UNROLL 4     // 32-element chunks of a neighbour list loaded before the first is searched
+#endif
 #define GCCB_HIT_STAGE 128     // hits of one row parked in shared memory before their pool slot is known
 
 // Pass 1: walk + sort/unique + induced-degree count.  grid = 2B, block = GCCB_ST.
@@ -222,17 +225,28 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
           w += __popc(hit);
         }
       } else {
-        for (int64_t e0 = beg; e0 < end; e0 += 32) {
-          const int64_t e = e0 + lane;
-          int j = -1;
-          if (e < end) j = local_id(keys, n, seed, indices[e]);
-          const unsigned hit = __ballot_sync(0xffffffffu, j >= 0);
-          if (j >= 0) {
-            const int q = w + __popc(hit & lt_mask);
-            if (round == 1) pool[pos + q] = j;
-            else if (q < GCCB_HIT_STAGE) wstage[q] = j;
+        // four independent 128-byte loads in flight per warp before the first search: the scan of a cold
+        // neighbour list is bound by memory-level parallelism (one load per warp at a time reached ~500 GB/s
+        // on the RMAT sweep), not by the searches
+        for (int64_t e0 = beg; e0 < end; e0 += 32 * GCCB_SCAN_UNROLL) {
+          int u[GCCB_SCAN_UNROLL];
+#pragma unroll
+          for (int k = 0; k < GCCB_SCAN_UNROLL; ++k) {
+            const int64_t e = e0 + 32 * k + lane;
+            u[k] = e < end ? indices[e] : -1;
           }
-          w += __popc(hit);
+#pragma unroll
+          for (int k = 0; k < GCCB_SCAN_UNROLL; ++k) {
+            if (e0 + 32 * k >= end) break;                  // warp-uniform
+            const int j = u[k] >= 0 ? local_id(keys, n, seed, u[k]) : -1;
+            const unsigned hit = __ballot_sync(0xffffffffu, j >= 0);
+            if (j >= 0) {
+              const int q = w + __popc(hit & lt_mask);
+              if (round == 1) pool[pos + q] = j;
+              else if (q < GCCB_HIT_STAGE) wstage[q] = j;
+            }
+            w += __popc(hit);
+          }
         }
       }
       if (round == 1) break;

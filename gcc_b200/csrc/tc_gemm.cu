@@ -244,6 +244,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       float* outf = g.out_f32 ? g.out_f32 + (size_t)split * g.M_cap * g.ldo : nullptr;
+      const bool wide_f32 = outf && ((((uintptr_t)outf) | ((size_t)g.ldo * 4)) & 31) == 0;
+      const bool wide_bf16 = g.out_bf16 && ((((uintptr_t)g.out_bf16) | ((size_t)g.ldo * 2)) & 31) == 0;
       if (g.colstats) {                                     // per-warp column accumulators (n_tiles == 1 with statistics)
         for (int i = lane; i < COLS; i += 32) {               // own columns only: the warps of a lane group share a row
           stage_t[ew * (2 * BN) + part * COLS + i] = 0.f;
@@ -293,26 +295,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
           }
-          // a TMEM lane holds one ROW: each lane stores its 32 columns as 16-byte pieces (measured faster than
-          // staging the block in shared memory for row-contiguous warp stores)
           if (row_ok) {
+            // a TMEM lane holds one ROW: each lane stores its 32 columns itself.  256-bit stores (sm_100) when the
+            // row pitch allows: every store fills whole 32-byte sectors, half the store instructions
             if (outf) {
-              float4* dst = reinterpret_cast<float4*>(outf + (size_t)row * g.ldo + col0);
+              float* dst = outf + (size_t)row * g.ldo + col0;
+              if (wide_f32) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 4; ++j)
+                  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j),
+                               "f"(v[8 * j]), "f"(v[8 * j + 1]), "f"(v[8 * j + 2]), "f"(v[8 * j + 3]), "f"(v[8 * j + 4]),
+                               "f"(v[8 * j + 5]), "f"(v[8 * j + 6]), "f"(v[8 * j + 7])
+                               : "memory");
+              } else {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
             }
             if (g.out_bf16) {
-              uint4* dst = reinterpret_cast<uint4*>(g.out_bf16 + (size_t)row * g.ldo + col0);
+              uint32_t pk[16];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-                u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-                dst[j] = u;
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&p2);
+              }
+              __nv_bfloat16* dst = g.out_bf16 + (size_t)row * g.ldo + col0;
+              if (wide_bf16) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * j),
+                               "r"(pk[8 * j]), "r"(pk[8 * j + 1]), "r"(pk[8 * j + 2]), "r"(pk[8 * j + 3]), "r"(pk[8 * j + 4]),
+                               "r"(pk[8 * j + 5]), "r"(pk[8 * j + 6]), "r"(pk[8 * j + 7])
+                               : "memory");
+              } else {
+                uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
               }
             }
           }
