@@ -383,11 +383,13 @@ def run_ours(args, cfg):
                 "frac": achieved / peak_gbs, "traffic": None,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_step": alg_bytes, "ms_per_launch_group": samp_ms,
-                "note": "latency-bound at 512 ego-nets/step (tens of MB per launch group); see DESIGN.md"}
+                "note": "latency-bound at %d ego-nets/step (tens of MB per launch group); see DESIGN.md" % (2 * B)}
     try:
-        roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[
-            "sampler_group_dram_bytes_per_step"]
-        roofline["traffic_source"] = "profiles/r01_sampler_ncu_full.csv (one ncu --set full capture)"
+        if args.config != "c2":
+            raise KeyError("the ncu capture is of the C2 workload")
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = tr["sampler_group_dram_bytes_per_step"]
+        roofline["traffic_source"] = tr.get("source", "profiles/traffic.json")
     except Exception:
         pass
     eig = eigensolver_report(eng.cur_buf, eig_ms)
@@ -405,22 +407,30 @@ def run_ours(args, cfg):
     done = [torch.cuda.Event() for _ in range(4)]
     NSEED = 2 * (args.prefetch + 2)             # a slot is rewritten long after the sampler that reads it has run
     seeds_ring = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(NSEED)]
-    for i in range(2):
-        seeds_ring[i % NSEED].copy_(host_seeds[i], non_blocking=True)
+    # untimed e2e steps: every data stream (one per batch in flight) must have run the host-seed variant of the
+    # data path once -- its first use allocates from that stream's pool of the caching allocator (a cudaMalloc)
+    E2E_WARM = args.prefetch + 2
+    for i in range(E2E_WARM):
+        seeds_ring[i % NSEED].copy_(host_seeds[i % 2], non_blocking=True)
         eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[i % NSEED])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_losses = []
     LAG = 2                                    # < ring depth 4
+    host_t = np.zeros((n_e2e, 3))
     for i in range(n_e2e):
-        seeds_ring[(i + 2) % NSEED].copy_(host_seeds[2 + i], non_blocking=True)   # seeds of the batch prepared this step
-        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[(i + 2) % NSEED])
+        host_t[i, 0] = time.perf_counter()
+        slot = (i + E2E_WARM) % NSEED
+        seeds_ring[slot].copy_(host_seeds[2 + i], non_blocking=True)     # seeds of the batch prepared this step
+        eng.step(lr=lr_at(eng.global_step), seeds=seeds_ring[slot])
         loss_ring[i & 3].copy_(eng.stats, non_blocking=True)            # D2H of this step's loss / prob / grad norm
         done[i & 3].record()
+        host_t[i, 1] = time.perf_counter()
         if i >= LAG:        # the reference's .item() per step (train.py:420-422), read LAG steps late so that the
             done[(i - LAG) & 3].synchronize()                           # host enqueues ahead while those steps run
             e2e_losses.append(float(loss_ring[(i - LAG) & 3][0]))
+        host_t[i, 2] = time.perf_counter()
     for i in range(max(n_e2e - LAG, 0), n_e2e):
         done[i & 3].synchronize()
         e2e_losses.append(float(loss_ring[i & 3][0]))
@@ -431,6 +441,13 @@ def run_ours(args, cfg):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = 2.0 * B * world * n_e2e / (float(t2.item()) / 1e3)
+    enq, wait = (host_t[:, 1] - host_t[:, 0]) * 1e3, (host_t[:, 2] - host_t[:, 1]) * 1e3
+    worst = int(np.argmax(enq + wait))
+    e2e_host = {"enqueue_p50": float(np.median(enq)), "enqueue_max": float(enq.max()), "wait_p50": float(np.median(wait)),
+                "wait_max": float(wait.max()), "slowest_step": worst, "slowest_enqueue": float(enq[worst]),
+                "slowest_wait": float(wait[worst]),
+                "note": "host wall time per e2e step: enqueue = seed copy + PretrainEngine.step + stats copy; wait = "
+                        "blocking read of the result two steps back"}
 
     line = {"metric": METRIC, "value": value, "unit": "subgraphs/sec", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -447,7 +464,7 @@ def run_ours(args, cfg):
                        "avg_nodes_per_egonet": n_sum / (2 * B), "avg_edges_per_egonet": m_sum / (2 * B)},
             "pairs_per_sec": value / 2.0,
             "e2e": {"value": e2e_value, "unit": "subgraphs/sec", "h2d_bytes_per_step": B * 8,
-                    "d2h_bytes_per_step": 16, "steps": n_e2e,
+                    "d2h_bytes_per_step": 16, "steps": n_e2e, "host_step_ms": e2e_host,
                     "path": "host np seed draw -> pinned -> H2D -> PretrainEngine.step (trains batch t, prepares a later batch from these seeds) -> stats D2H every step, the host reads each step's copy two steps later"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "step_time": step_dist, "mode": args.mode, "rank_skew": rank_skew,

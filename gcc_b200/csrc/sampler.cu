@@ -70,6 +70,7 @@ __device__ __forceinline__ bool adj_find(const int32_t* __restrict__ indices, in
 #ifndef GCCB_SCAN_UNROLL
 #define GCCB_SCAN_UNROLL 4     // 32-element chunks of a neighbour list loaded before the first is searched
 #endif
+#define GCCB_HUB_LIST 1024     // hub rows per ego-net handled CTA-wide (further ones fall back to one warp each)
 #define GCCB_HIT_STAGE 128     // hits of one row parked in shared memory before their pool slot is known
 
 // Pass 1: walk + sort/unique + induced-degree count.  grid = 2B, block = GCCB_ST.
@@ -88,6 +89,8 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
   __shared__ int stage[GCCB_SW][GCCB_HIT_STAGE];      // per-warp parking of one row's hits
   __shared__ int s_tstar, s_m;
   __shared__ unsigned long long s_sumdeg;
+  __shared__ int s_nhub, s_pos;
+  __shared__ int hub_rows[GCCB_HUB_LIST];             // hub rows of this ego-net: probed by the whole CTA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = blockIdx.x;            // view-major: slot = view * B + g
   const int view = slot / B, g = slot - view * B;
@@ -198,7 +201,75 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
     while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < seed) lo = mid + 1; else hi = mid; }
     sr = lo - 1;
   }
+  // Hub rows first, with the whole CTA: a reverse probe is a chain of ~log2(deg) dependent global loads per key, so
+  // one warp needs n/32 such chains back to back for ONE row (a 326k-neighbour RMAT hub in a 400-vertex ego-net:
+  // ~120 us, and hub-rich ego-nets hold dozens of them); 1024 threads probe all keys of the row at once.
+  if (tid == 0) s_nhub = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += GCCB_ST) {
+    const int64_t v = keys[i];
+    int mark = -3;
+    if (indptr[v + 1] - indptr[v] > (int64_t)GCCB_REVERSE_FACTOR * n) {
+      const int idx = atomicAdd(&s_nhub, 1);
+      if (idx < GCCB_HUB_LIST) { hub_rows[idx] = i; mark = -2; }
+    }
+    rowstart[i] = mark;                                  // -2: handled below, not by the warp loop
+  }
+  __syncthreads();
+  const int n_hub = min(s_nhub, GCCB_HUB_LIST);
+  for (int h = 0; h < n_hub; ++h) {
+    const int i = hub_rows[h];
+    const int64_t v = keys[i];
+    const int64_t beg = indptr[v], end = indptr[v + 1];
+    int cnt = 0, my_j = -1, my_ex = 0;
+    for (int t0 = 0; t0 < n; t0 += GCCB_ST) {            // count (ascending parent id, the seed spliced in at rank sr)
+      const int t = t0 + tid;
+      int j = -1;
+      if (t < n) {
+        const int loc = t < sr ? t + 1 : (t == sr ? 0 : t);
+        if (adj_find(indices, beg, end, keys[loc])) j = loc;
+      }
+      int tot;
+      const int ex = block_scan_excl(j >= 0 ? 1 : 0, scan_scratch, &tot);
+      if (t0 == 0) { my_j = j; my_ex = ex; }
+      cnt += tot;
+    }
+    if (tid == 0) {
+      int pos = cnt > 0 ? atomicAdd(pool_counter, cnt) : 0;
+      if (pos + cnt > pool_cap) pos = -1;                  // pool exhausted: the fill kernel looks again itself
+      s_pos = pos;
+    }
+    __syncthreads();
+    const int pos = s_pos;
+    if (pos >= 0) {
+      if (n <= GCCB_ST) {
+        if (my_j >= 0) pool[pos + my_ex] = my_j;
+      } else {
+        int w = 0;
+        for (int t0 = 0; t0 < n; t0 += GCCB_ST) {
+          const int t = t0 + tid;
+          int j = -1;
+          if (t < n) {
+            const int loc = t < sr ? t + 1 : (t == sr ? 0 : t);
+            if (adj_find(indices, beg, end, keys[loc])) j = loc;
+          }
+          int tot;
+          const int ex = block_scan_excl(j >= 0 ? 1 : 0, scan_scratch, &tot);
+          if (j >= 0) pool[pos + w + ex] = j;
+          w += tot;
+        }
+      }
+    }
+    if (tid == 0) {
+      subdeg[i] = cnt;
+      rowstart[i] = pos;
+      m_local += cnt;
+      sumdeg_local += (unsigned long long)(end - beg);
+    }
+    __syncthreads();                                     // s_pos / scan_scratch are reused by the next hub row
+  }
   for (int i = warp; i < n; i += GCCB_SW) {
+    if (rowstart[i] != -3) continue;                     // a hub row: done above
     const int64_t v = keys[i];
     const int64_t beg = indptr[v], end = indptr[v + 1];
     const bool reverse = end - beg > (int64_t)GCCB_REVERSE_FACTOR * n;

@@ -31,7 +31,14 @@ def _run(g, B, rw_hops, key, first=0, node_cap=None, edge_cap=None):
     return b, views, want
 
 
-@pytest.mark.parametrize("name,B,hops", [("er", 5, 24), ("star", 3, 16), ("cl", 4, 40), ("hub", 4, 16), ("bigstar", 2, 400)])
+def _three_centres(leaves):
+    src = np.repeat(np.arange(3), leaves)
+    dst = 3 + np.tile(np.arange(leaves), 3)
+    return synthetic.from_pairs(src, dst, leaves + 3, "k3_%d" % leaves)
+
+
+@pytest.mark.parametrize("name,B,hops", [("er", 5, 24), ("star", 3, 16), ("cl", 4, 40), ("hub", 4, 16), ("bigstar", 2, 400),
+                                         ("k3", 2, 8000)])
 def test_sampler_matches_oracle(name, B, hops):
     g = {"er": lambda: synthetic.erdos_renyi(300, 1200, seed=2),
          "star": lambda: synthetic.star_graph(40),
@@ -40,9 +47,14 @@ def test_sampler_matches_oracle(name, B, hops):
          "bigstar": lambda: synthetic.star_graph(700),
          "cl": lambda: synthetic.chung_lu(2000, 12000, seed=3),
          # hub degree >> ego-net size: exercises the reverse-probe induction path
-         "hub": lambda: synthetic.chung_lu(6000, 60000, exponent=0.9, seed=5)}[name]()
+         "hub": lambda: synthetic.chung_lu(6000, 60000, exponent=0.9, seed=5),
+         # ego-nets of more than 1024 vertices whose three centre rows (degree 30000 > 16 n) take the CTA-wide
+         # reverse probe in several chunks of keys
+         "k3": lambda: _three_centres(30000)}[name]()
     b, views, want = _run(g, B, hops, key=0xABCDEF12345)
     assert b.flags[0] == 0
+    if name == "k3":
+        assert max(s_["n"] for v_ in views for s_ in v_) > 1024
     for v in (0, 1):
         got = b.view_graphs(v)
         assert b.node_off[v, B] == sum(s["n"] for s in views[v])
