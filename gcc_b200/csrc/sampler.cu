@@ -82,7 +82,7 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
                        const int64_t* __restrict__ sample_ids, int B, int cap_n,
                        int32_t* __restrict__ subv_scratch, int32_t* __restrict__ subdeg_scratch,
                        int32_t* __restrict__ rowstart_scratch, int32_t* __restrict__ pool, int pool_cap,
-                       int32_t* __restrict__ pool_counter,
+                       unsigned long long* __restrict__ pool_counter,
                        int64_t* __restrict__ counters, int32_t* __restrict__ flags) {
   GCCB_DYN_SMEM(int, keys);
   __shared__ int scan_scratch[33];
@@ -235,9 +235,8 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
       cnt += tot;
     }
     if (tid == 0) {
-      int pos = cnt > 0 ? atomicAdd(pool_counter, cnt) : 0;
-      if (pos + cnt > pool_cap) pos = -1;                  // pool exhausted: the fill kernel looks again itself
-      s_pos = pos;
+      const unsigned long long p64 = cnt > 0 ? atomicAdd(pool_counter, (unsigned long long)cnt) : 0ull;
+      s_pos = p64 + (unsigned long long)cnt > (unsigned long long)pool_cap ? -1 : (int)p64;   // exhausted: the fill kernel looks again itself
     }
     __syncthreads();
     const int pos = s_pos;
@@ -323,8 +322,9 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
       if (round == 1) break;
       cnt = w;
       if (lane == 0) {
-        pos = cnt > 0 ? atomicAdd(pool_counter, cnt) : 0;
-        if (pos + cnt > pool_cap) pos = -1;               // pool exhausted: the fill kernel looks again itself
+        // (64-bit counter: a launch of 65,536 hub-rich ego-nets parks more than 2^31 hits' worth of requests)
+        const unsigned long long p64 = cnt > 0 ? atomicAdd(pool_counter, (unsigned long long)cnt) : 0ull;
+        pos = p64 + (unsigned long long)cnt > (unsigned long long)pool_cap ? -1 : (int)p64;   // exhausted: the fill kernel looks again itself
       }
       pos = __shfl_sync(0xffffffffu, pos, 0);
       if (pos < 0) break;
@@ -530,10 +530,13 @@ extern "C" int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds
   int32_t* subv = (int32_t*)workspace;
   int32_t* subdeg = subv + (size_t)2 * B * cap_n;
   int32_t* rowstart = subdeg + (size_t)2 * B * cap_n;
-  int32_t* pool_counter = rowstart + (size_t)2 * B * cap_n;
-  int32_t* pool = pool_counter + 16;
-  const int pool_cap = 2 * batch->edge_cap;
-  cudaMemsetAsync(pool_counter, 0, sizeof(int32_t), (cudaStream_t)stream);
+  unsigned long long* pool_counter = (unsigned long long*)(rowstart + (size_t)2 * B * cap_n);   // 16 ints reserved, 8-byte aligned
+  int32_t* pool = (int32_t*)pool_counter + 16;
+  // pool positions are stored per row as int32: the pool is capped below 2^31 entries (2 * edge_cap overflows
+  // an int for edge_cap > 2^30 -- the 65,536-ego-net sweep of config 5)
+  const long long want_cap = 2ll * (long long)batch->edge_cap;
+  const int pool_cap = (int)(want_cap < 0x7fff0000ll ? want_cap : 0x7fff0000ll);
+  cudaMemsetAsync(pool_counter, 0, sizeof(unsigned long long), (cudaStream_t)stream);
   auto k1 = rwr_walk_unique_kernel;
   auto k3 = induce_fill_kernel;
   if (smem > 48 * 1024) {
