@@ -43,8 +43,10 @@ StreamKit* stream_kit(cudaStream_t caller, int family, bool lowest_priority) {
   static int nkits = 0;
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
-  for (int i = 0; i < nkits; ++i)
-    if (kits[i].key == caller && kits[i].family == family) return &kits[i];
+  int dev = 0;
+  cudaGetDevice(&dev);                                    // streams belong to a device: the legacy stream (0) of two
+  for (int i = 0; i < nkits; ++i)                         // devices must not share side streams
+    if (kits[i].key == caller && kits[i].family == family && kits[i].dev == dev) return &kits[i];
   StreamKit* k;
   if (nkits < 16) {
     k = &kits[nkits++];
@@ -55,6 +57,7 @@ StreamKit* stream_kit(cudaStream_t caller, int family, bool lowest_priority) {
   }
   k->key = caller;
   k->family = family;
+  k->dev = dev;
   return k;
 }
 #endif

@@ -1,5 +1,6 @@
 // common.cuh -- shared device/host helpers for libgccb200 (sm_100a).
 #pragma once
+#include <mutex>
 #include <stdint.h>
 
 #ifdef GCCB_EMU
@@ -25,6 +26,7 @@ namespace gccb {
 struct StreamKit {
   cudaStream_t key;
   int family;
+  int dev;
   cudaStream_t side[5];
   cudaEvent_t ev[24];
 };
@@ -35,22 +37,28 @@ StreamKit* stream_kit(cudaStream_t caller, int family, bool lowest_priority = fa
 namespace gccb {
 // Opt a kernel into `bytes` of dynamic shared memory.  The driver call costs microseconds, so the
 // largest value already granted is remembered per kernel and the call is skipped afterwards
-// (benign race: concurrent first calls set the same attribute twice).
+// (per device; guarded by a mutex).
 template <class K>
 inline void ensure_dyn_smem(K kern, size_t bytes) {
-  struct Slot { const void* fn; size_t bytes; };
-  static Slot slots[128];
+  // the attribute is per device: one table per (kernel pointer, device ordinal); guarded, because ctypes callers
+  // run without the GIL and two host threads may make their first call together
+  struct Slot { const void* fn; int dev; size_t bytes; };
+  static Slot slots[256];
   static int nslots = 0;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
   const void* key = (const void*)kern;
+  std::lock_guard<std::mutex> lock(mu);
   for (int i = 0; i < nslots; ++i)
-    if (slots[i].fn == key) {
+    if (slots[i].fn == key && slots[i].dev == dev) {
       if (slots[i].bytes >= bytes) return;
       slots[i].bytes = bytes;
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
       return;
     }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (nslots < 128) { slots[nslots].fn = key; slots[nslots].bytes = bytes; ++nslots; }
+  if (nslots < 256) { slots[nslots].fn = key; slots[nslots].dev = dev; slots[nslots].bytes = bytes; ++nslots; }
 }
 }  // namespace gccb
 

@@ -464,7 +464,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& 
 }
 
 // Internal entry used by the GIN / MoCo tensor-core paths and by gccb_tc_gemm_bf16.
-// splits > 1: `scratch` must hold splits * M_cap * ldo floats; the partial sums are reduced in a fixed order.
+// splits > 1 (or an accumulating / narrow / oddly pitched output): `scratch` must hold splits * M_cap * N floats; the partial sums are reduced in a fixed order.
 int gemm_bf16(const void* A, const void* B, int M_cap, int N, int K, const int32_t* m_dev, const float* bias,
               float alpha, float* out_f32, void* out_bf16, int ldo, double* colstats, int splits, float* scratch,
               cudaStream_t stream, float beta, int n_out) {

@@ -237,8 +237,9 @@ int gccb_sum_ranks(const float* gathered, int32_t world, int64_t stride, int64_t
  * m_dev (optional): device int with the number of valid rows (<= M_cap), so the row count of a sampled
  * batch never comes back to the host.  out_f32 / out_bf16: [M_cap][ldo] (either may be NULL).
  * colstats (optional): double [2][N], += column sums / sums of squares of the stored values over the
- * valid rows.  splits > 1: split-K over CTAs; scratch must hold splits * M_cap * ldo floats (partials are
- * added in a fixed order); colstats must be NULL.                                                  */
+ * valid rows.  splits > 1: split-K over CTAs; the partial products go to `scratch`, which must hold
+ * splits * M_cap * N floats (row pitch N), and are added in a fixed order; colstats must be NULL.  A row
+ * pitch ldo that is not a multiple of 8 also goes through `scratch` (M_cap * N floats, splits = 1).    */
 int gccb_tc_gemm_bf16(const void* A, const void* B, int32_t M_cap, int32_t N, int32_t K,
                       const int32_t* m_dev, const float* bias, float alpha, float* out_f32,
                       void* out_bf16, int32_t ldo, double* colstats, int32_t splits, float* scratch,
