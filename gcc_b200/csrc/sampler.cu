@@ -16,9 +16,10 @@
 // list is read ONCE: the local ids of the hits are parked in a scratch pool while the induced
 // degrees are counted, the per-view scan fixes the (deterministic) output layout, and the fill
 // kernel only copies pool -> batched CSR.  Hits wait in a per-warp shared-memory stage until their row's
-// count is known; a row that outgrows the stage (more than 128 induced neighbours) claims min(deg, n) pool
-// entries on the spot and writes the rest directly.  Hub rows (degree > 16 n) are not streamed: the ego-net's
-// vertices are looked up in the hub's sorted list, by the whole CTA at once.
+// count is known (rows with more than 128 induced neighbours are the exception: counted first, recorded on a
+// second look).  A one-hash membership filter of the frontier rejects most scanned neighbours with one shared-
+// memory load.  Hub rows (degree > 16 n) are not streamed: the ego-net's vertices are looked up in the hub's
+// sorted list, by the whole CTA at once.
 #include "common.cuh"
 
 namespace gccb {
@@ -74,6 +75,9 @@ __device__ __forceinline__ bool adj_find(const int32_t* __restrict__ indices, in
 #define GCCB_SW (GCCB_ST / 32)
 #ifndef GCCB_SCAN_UNROLL
 #define GCCB_SCAN_UNROLL 4     // 32-element chunks of a neighbour list loaded before the first is searched
+#endif
+#ifndef GCCB_BLOOM
+#define GCCB_BLOOM 1           // A/B switches (profiles/build_variant.py)
 #endif
 #define GCCB_BLOOM_WORDS 2048   // 65,536 bits: 0.6 % false positives at n = 400, 7 % at n = 5,000
 #define GCCB_HUB_LIST 1024     // hub rows per ego-net handled CTA-wide (further ones fall back to one warp each)
@@ -287,88 +291,74 @@ rwr_walk_unique_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
     const int64_t v = keys[i];
     const int64_t beg = indptr[v], end = indptr[v + 1];
     const bool reverse = end - beg > (int64_t)GCCB_REVERSE_FACTOR * n;
-    // Hits are parked in the warp's shared-memory stage until the row's count is known.  A row that outgrows the
-    // stage claims min(deg, n) pool entries on the spot (an upper bound of its count: the slack is scratch),
-    // moves the parked hits there and writes the rest directly -- still ONE look at the list.  (Rows of more
-    // than 128 induced neighbours are the long rows of a dense ego-net: scanning them twice, as an earlier
-    // version did, doubled the dominant cost of the RMAT sweep.)
-    int pos = -1, w = 0;
-    bool direct = false, tried = false;
+    // Hits are parked in the warp's shared-memory stage until the row's count is known, then moved to a pool
+    // slot claimed with one atomic.  A row with more hits than the stage holds (> 128 induced neighbours) is
+    // counted first and recorded on a second look.  (Claiming an upper bound min(deg, n) on the spot instead --
+    // one look -- was measured on the RMAT sweep: the slack exhausts the pool and costs more than the re-scan.)
+    int pos = 0, w = 0, round = 0;
     auto emit = [&](int j) {                             // called by all lanes; j < 0: no hit on this lane
       const unsigned hit = __ballot_sync(0xffffffffu, j >= 0);
-      const int c = __popc(hit);
-      if (!direct && !tried && w + c > GCCB_HIT_STAGE) {
-        tried = true;
-        const int64_t ub64 = end - beg < (int64_t)n ? end - beg : (int64_t)n;
-        const int ub = (int)ub64;
-        int p = -1;
-        if (lane == 0) {
-          const unsigned long long p64 = atomicAdd(pool_counter, (unsigned long long)ub);
-          p = p64 + (unsigned long long)ub > (unsigned long long)pool_cap ? -1 : (int)p64;
-        }
-        p = __shfl_sync(0xffffffffu, p, 0);
-        if (p >= 0) {
-          __syncwarp();
-          for (int q = lane; q < w; q += 32) pool[p + q] = wstage[q];
-          pos = p;
-          direct = true;
-        }
-      }
       if (j >= 0) {
         const int q = w + __popc(hit & lt_mask);
-        if (direct) pool[pos + q] = j;
+        if (round == 1) pool[pos + q] = j;
         else if (q < GCCB_HIT_STAGE) wstage[q] = j;
       }
-      w += c;
+      w += __popc(hit);
     };
-    if (reverse) {
-      // hub row (beyond the CTA-wide list): probe adj(v) for every ego-net vertex in ascending parent id (= the
-      // order a scan of adj(v) would meet them): keys[1..n) is ascending, the seed (local id 0) is spliced in at rank sr
-      for (int t0 = 0; t0 < n; t0 += 32) {
-        const int t = t0 + lane;
-        int j = -1;
-        if (t < n) {
-          const int loc = t < sr ? t + 1 : (t == sr ? 0 : t);
-          if (adj_find(indices, beg, end, keys[loc])) j = loc;
-        }
-        emit(j);
-      }
-    } else {
-      // four independent 128-byte loads in flight per warp before the first search: the scan of a cold
-      // neighbour list is bound by memory-level parallelism, not by the searches (-18 % on the RMAT sweep)
-      for (int64_t e0 = beg; e0 < end; e0 += 32 * GCCB_SCAN_UNROLL) {
-        int u[GCCB_SCAN_UNROLL];
-#pragma unroll
-        for (int k = 0; k < GCCB_SCAN_UNROLL; ++k) {
-          const int64_t e = e0 + 32 * k + lane;
-          u[k] = e < end ? indices[e] : -1;
-        }
-#pragma unroll
-        for (int k = 0; k < GCCB_SCAN_UNROLL; ++k) {
-          if (e0 + 32 * k >= end) break;                  // warp-uniform
+    auto scan_row = [&]() {
+      w = 0;
+      if (reverse) {
+        // hub row (beyond the CTA-wide list): probe adj(v) for every ego-net vertex in ascending parent id (= the
+        // order a scan of adj(v) would meet them): keys[1..n) is ascending, the seed (local id 0) is spliced in at rank sr
+        for (int t0 = 0; t0 < n; t0 += 32) {
+          const int t = t0 + lane;
           int j = -1;
-          if (u[k] >= 0) {
-            const unsigned b = bloom_bit(u[k]);
-            if ((bloom[b >> 5] >> (b & 31u)) & 1u) j = local_id(keys, n, seed, u[k]);
+          if (t < n) {
+            const int loc = t < sr ? t + 1 : (t == sr ? 0 : t);
+            if (adj_find(indices, beg, end, keys[loc])) j = loc;
           }
           emit(j);
         }
-      }
-    }
-    const int cnt = w;
-    if (!direct) {
-      if (cnt <= GCCB_HIT_STAGE) {
-        if (lane == 0) {
-          const unsigned long long p64 = cnt > 0 ? atomicAdd(pool_counter, (unsigned long long)cnt) : 0ull;
-          pos = p64 + (unsigned long long)cnt > (unsigned long long)pool_cap ? -1 : (int)p64;
-        }
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (pos >= 0) {
-          __syncwarp();
-          for (int q = lane; q < cnt; q += 32) pool[pos + q] = wstage[q];
-        }
       } else {
-        pos = -1;                                         // pool exhausted mid-row: the fill kernel looks again itself
+        // four independent 128-byte loads in flight per warp before the first search: the scan of a cold
+        // neighbour list is bound by memory-level parallelism, not by the searches (-18 % on the RMAT sweep)
+        for (int64_t e0 = beg; e0 < end; e0 += 32 * GCCB_SCAN_UNROLL) {
+          int u[GCCB_SCAN_UNROLL];
+#pragma unroll
+          for (int k = 0; k < GCCB_SCAN_UNROLL; ++k) {
+            const int64_t e = e0 + 32 * k + lane;
+            u[k] = e < end ? indices[e] : -1;
+          }
+#pragma unroll
+          for (int k = 0; k < GCCB_SCAN_UNROLL; ++k) {
+            if (e0 + 32 * k >= end) break;                  // warp-uniform
+            int j = -1;
+            if (u[k] >= 0) {
+#if GCCB_BLOOM
+              const unsigned b = bloom_bit(u[k]);
+              if ((bloom[b >> 5] >> (b & 31u)) & 1u)
+#endif
+                j = local_id(keys, n, seed, u[k]);
+            }
+            emit(j);
+          }
+        }
+      }
+    };
+    scan_row();
+    const int cnt = w;
+    if (lane == 0) {
+      const unsigned long long p64 = cnt > 0 ? atomicAdd(pool_counter, (unsigned long long)cnt) : 0ull;
+      pos = p64 + (unsigned long long)cnt > (unsigned long long)pool_cap ? -1 : (int)p64;   // exhausted: the fill kernel looks again itself
+    }
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (pos >= 0) {
+      if (cnt <= GCCB_HIT_STAGE) {
+        __syncwarp();
+        for (int q = lane; q < cnt; q += 32) pool[pos + q] = wstage[q];
+      } else {
+        round = 1;
+        scan_row();
       }
     }
     __syncwarp();                                          // wstage is reused by the next row
