@@ -24,6 +24,10 @@ timeout 300 python profiles/eig_diag.py > ${P}_eig_diag.log 2>&1
 timeout 300 python profiles/timeline.py 4 ${P}_timeline_c2.json.gz c2 > ${P}_tl_c2.log 2>&1 && python profiles/timeline_read.py ${P}_timeline_c2.json.gz x > ${P}_tl_c2_summary.txt 2>&1
 timeout 300 python profiles/timeline.py 4 ${P}_timeline_c4.json.gz c4 > ${P}_tl_c4.log 2>&1 && python profiles/timeline_read.py ${P}_timeline_c4.json.gz x > ${P}_tl_c4_summary.txt 2>&1
 { timeout 300 python profiles/data_alone.py 4; timeout 300 python profiles/data_alone.py 1; timeout 300 python profiles/train_alone.py; } 2>&1 | grep -E "data path|train part" > ${P}_alone.log
+timeout 900 python profiles/sampler_sweep.py 24 200000000 32768 0 64,128,256,512 3 > ${P}_sweep_c5.json 2> ${P}_sweep_c5.err
+timeout 900 ncu --set full --clock-control none -k regex:"rwr_walk_unique_kernel|induce_fill_kernel" -s 4 -c 2 -o ${P}_prof_c5 \
+    python profiles/sampler_sweep.py 24 200000000 32768 0 256 1 > ${P}_ncu_c5.json 2> ${P}_ncu_c5.err
 tail -3 ${P}_tests.log | cut -c1-300; cat ${P}_smoke.log | tail -2
+grep -o "'rw_hops': [0-9]*, 'ms_per_launch_group': [0-9.]*, 'egonets_per_sec': [0-9.]*" ${P}_sweep_c5.err
 for v in bench_c2 bench_ref bench_c4_tc bench_c4_simt bench_e2emode; do head -c 300 ${P}_$v.json | cut -c1-300; echo; done
 cat ${P}_alone.log
