@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """GPU diagnostic: the training part of the step alone (no sampler / eigensolver in flight), on the
-whole GPU or inside a green-context partition of N SMs."""
+whole GPU.  usage: train_alone.py [config=c2]"""
 import contextlib
 import os
 import sys
@@ -15,7 +15,7 @@ from gcc_b200.datasets.graph_dataset import LoadBalanceGraphDataset  # noqa: E40
 from gcc_b200.engine import PretrainEngine  # noqa: E402
 from gcc_b200.models import GraphEncoder  # noqa: E402
 
-cfg = bench.CONFIGS["c2"]
+cfg = bench.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
 dev = torch.device("cuda")
 g = bench.make_graph_device(cfg, dev)
 B, L, H, K = cfg["batch"], cfg["layers"], cfg["hidden"], cfg["K"]
