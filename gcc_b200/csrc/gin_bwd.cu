@@ -154,52 +154,53 @@ gin_bwd_dh_kernel(const int32_t* __restrict__ node_off_v, int B, const int32_t* 
                   const float* __restrict__ dpool_j, int DW, const float* __restrict__ da, int has_da,
                   float* __restrict__ dh) {
   __shared__ float scratch[8 * W];
-  __shared__ int hub_rows[GCCB_TILE_ROWS];
+  __shared__ int hub_rows[GCCB_HUB_QUEUE];
   __shared__ int n_hub;
   const int N = node_off_v[B];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int PER = (W + 31) / 32;
-  // 64-row tiles, warps independent inside a tile; hub rows (split across the CTA) after the tile: two
-  // barriers per 64 rows
-  for (int row0 = blockIdx.x * GCCB_TILE_ROWS; row0 < N; row0 += gridDim.x * GCCB_TILE_ROWS) {
-    if (tid == 0) n_hub = 0;
-    __syncthreads();
-    for (int rr = warp; rr < GCCB_TILE_ROWS; rr += 8) {
-      const int r = row0 + rr;
-      if (r >= N) break;
-      const int beg = indptr[r], end = indptr[r + 1];
-      if (has_da && end - beg > GCCB_HUB_DEG) {
-        if (lane == 0) hub_rows[atomicAdd(&n_hub, 1)] = r;   // deferred: split across the CTA below
+  constexpr int V4 = W / 4, PERV = (V4 + 31) / 32;
+  // one warp per row, round-robin over the grid's warps, no barrier in the loop; hub rows are queued per CTA and
+  // gathered by its 8 warps together afterwards (see gin_agg_cast_kernel)
+  if (tid == 0) n_hub = 0;
+  __syncthreads();
+  for (int r = blockIdx.x * 8 + warp; r < N; r += gridDim.x * 8) {
+    const int beg = indptr[r], end = indptr[r + 1];
+    if (has_da && end - beg > GCCB_HUB_DEG) {
+      int slot = GCCB_HUB_QUEUE;
+      if (lane == 0) slot = atomicAdd(&n_hub, 1);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (slot < GCCB_HUB_QUEUE) {
+        if (lane == 0) hub_rows[slot] = r;
         continue;
       }
-      const int g = graph_id[r];
-      float acc[PER];
+    }
+    const int g = graph_id[r];
+    float4 acc[PERV];
 #pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        int c = lane + 32 * j;
-        acc[j] = c < W ? dpool_j[(size_t)g * DW + c] : 0.f;
-      }
-      if (has_da) {
-#pragma unroll
-        for (int j = 0; j < PER; ++j) {
-          int c = lane + 32 * j;
-          if (c < W) acc[j] += da[(size_t)r * W + c];
+    for (int j = 0; j < PERV; ++j) {
+      const int v = lane + 32 * j;
+      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < V4) {
+        acc[j] = *reinterpret_cast<const float4*>(dpool_j + (size_t)g * DW + 4 * v);
+        if (has_da) {
+          const float4 x = *reinterpret_cast<const float4*>(da + (size_t)r * W + 4 * v);
+          acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
         }
-        gather_range<W>(da, indices, beg, end, lane, acc);
       }
+    }
+    if (has_da) gather_range4<W>(da, indices, beg, end, lane, acc);
 #pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        int c = lane + 32 * j;
-        if (c < W) dh[(size_t)r * W + c] = acc[j];
-      }
+    for (int j = 0; j < PERV; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V4) *reinterpret_cast<float4*>(dh + (size_t)r * W + 4 * v) = acc[j];
     }
-    __syncthreads();
-    for (int hi = 0; hi < n_hub; ++hi) {
-      const int rh = hub_rows[hi];
-      const float s = gather_hub<W>(da, indices, indptr[rh], indptr[rh + 1], scratch);
-      if (tid < W) dh[(size_t)rh * W + tid] = dpool_j[(size_t)graph_id[rh] * DW + tid] + da[(size_t)rh * W + tid] + s;
-    }
-    __syncthreads();
+  }
+  __syncthreads();
+  const int nh = min(n_hub, GCCB_HUB_QUEUE);
+  for (int hi = 0; hi < nh; ++hi) {
+    const int rh = hub_rows[hi];
+    const float s = gather_hub<W>(da, indices, indptr[rh], indptr[rh + 1], scratch);
+    if (tid < W) dh[(size_t)rh * W + tid] = dpool_j[(size_t)graph_id[rh] * DW + tid] + da[(size_t)rh * W + tid] + s;
   }
 }
 
@@ -684,7 +685,7 @@ static int run_backward(const BwdArgs& a) {
     double* rB = red + (size_t)(l * 3 + 2) * 2 * H;
     // dh_j = dpool_j broadcast + (I + A) da_{j}   (da of the layer above; none for the top)
     auto kdh = gin_bwd_dh_kernel<H>;
-    GCCB_LAUNCH(kdh, grid, 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id,
+    GCCB_LAUNCH(kdh, (tiles < 1184 ? tiles : 1184), 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id,
                 (const float*)(dpool + (size_t)j * B * DW), DW, (const float*)da, j < d.L - 1 ? 1 : 0, dh);
     auto kred = gin_bwd_reduce_kernel<H>;
     GCCB_LAUNCH(kred, grid, 256, 0, a.stream, 0, node_off_v, B, z2, (const float*)dh, sa, P + a.lay.bna_w[l],
@@ -748,7 +749,7 @@ static int run_backward(const BwdArgs& a) {
   }
   // layer-0 input gradient -> degree embedding
   auto kdh0 = gin_bwd_dh_kernel<GCCB_DINP>;
-  GCCB_LAUNCH(kdh0, grid, 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id, (const float*)dpool, DW,
+  GCCB_LAUNCH(kdh0, (tiles < 1184 ? tiles : 1184), 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id, (const float*)dpool, DW,
               (const float*)da, 1, dh);
   {
     size_t sm = (size_t)(d.maxdeg + 1) * d.D * sizeof(float);
@@ -1018,7 +1019,7 @@ static int run_backward_tc(const BwdArgs& a) {
     const __nv_bfloat16* w2t = w1t + (size_t)KW * H;
     float* c1 = coef1 + (size_t)l * 2 * H;
     auto kdh = gin_bwd_dh_kernel<H>;
-    GCCB_LAUNCH(kdh, grid, 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id,
+    GCCB_LAUNCH(kdh, (tiles < 1184 ? tiles : 1184), 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id,
                 (const float*)(dpool + (size_t)j * B * DW), DW, (const float*)da, j < d.L - 1 ? 1 : 0, dh);
     auto kred = gin_bwd_reduce_kernel<H>;
     GCCB_LAUNCH(kred, grid, 256, 0, a.stream, 0, node_off_v, B, z2, (const float*)dh, sa, P + a.lay.bna_w[l],
@@ -1062,7 +1063,7 @@ static int run_backward_tc(const BwdArgs& a) {
     cudaEventRecord(ev_side[l], side);
   }
   auto kdh0 = gin_bwd_dh_kernel<GCCB_DINP>;
-  GCCB_LAUNCH(kdh0, grid, 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id, (const float*)dpool, DW,
+  GCCB_LAUNCH(kdh0, (tiles < 1184 ? tiles : 1184), 256, 0, a.stream, node_off_v, B, indptr, indices, graph_id, (const float*)dpool, DW,
               (const float*)da, 1, dh);
   {
     size_t sm = (size_t)(d.maxdeg + 1) * d.D * sizeof(float);

@@ -159,6 +159,7 @@ __device__ __forceinline__ void bn_prepare(const double* __restrict__ sums, int 
 #ifndef GCCB_HUB_DEG
 #define GCCB_HUB_DEG 256      // rows with more neighbours are split across the warps of the CTA
 #endif
+#define GCCB_HUB_QUEUE 64     // hub rows a CTA of the barrier-free gather kernels defers to its cooperative pass
 template <int W>
 __device__ __forceinline__ void gather_range(const float* __restrict__ src, const int32_t* __restrict__ indices,
                                              int beg, int end, int lane, float (&acc)[(W + 31) / 32]) {
@@ -185,6 +186,43 @@ __device__ __forceinline__ void gather_range(const float* __restrict__ src, cons
     for (int j = 0; j < PER; ++j) {
       const int c = lane + 32 * j;
       if (c < W) acc[j] += src[(size_t)u * W + c];
+    }
+  }
+}
+
+// 128-bit variant for the barrier-free gather kernels: lane owns the float4 slots v = lane + 32 j of a row of W
+// floats (a warp reads 512 contiguous bytes per instruction); four neighbour rows in flight.
+template <int W>
+__device__ __forceinline__ void gather_range4(const float* __restrict__ src, const int32_t* __restrict__ indices,
+                                              int beg, int end, int lane, float4 (&acc)[(W / 4 + 31) / 32]) {
+  constexpr int V4 = W / 4, PERV = (V4 + 31) / 32;
+  int e = beg;
+  for (; e + 3 < end; e += 4) {
+    const int u0 = indices[e], u1 = indices[e + 1], u2 = indices[e + 2], u3 = indices[e + 3];
+#pragma unroll
+    for (int j = 0; j < PERV; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V4) {
+        const float4 x0 = *reinterpret_cast<const float4*>(src + (size_t)u0 * W + 4 * v);
+        const float4 x1 = *reinterpret_cast<const float4*>(src + (size_t)u1 * W + 4 * v);
+        const float4 x2 = *reinterpret_cast<const float4*>(src + (size_t)u2 * W + 4 * v);
+        const float4 x3 = *reinterpret_cast<const float4*>(src + (size_t)u3 * W + 4 * v);
+        acc[j].x += (x0.x + x1.x) + (x2.x + x3.x);
+        acc[j].y += (x0.y + x1.y) + (x2.y + x3.y);
+        acc[j].z += (x0.z + x1.z) + (x2.z + x3.z);
+        acc[j].w += (x0.w + x1.w) + (x2.w + x3.w);
+      }
+    }
+  }
+  for (; e < end; ++e) {
+    const int u = indices[e];
+#pragma unroll
+    for (int j = 0; j < PERV; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V4) {
+        const float4 x = *reinterpret_cast<const float4*>(src + (size_t)u * W + 4 * v);
+        acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
+      }
     }
   }
 }
