@@ -159,6 +159,7 @@ __device__ __forceinline__ void bn_prepare(const double* __restrict__ sums, int 
 #ifndef GCCB_HUB_DEG
 #define GCCB_HUB_DEG 256      // rows with more neighbours are split across the warps of the CTA
 #endif
+#define GCCB_GPB 8            // graphs per CTA of the pooled prediction heads (one warp per graph at the end)
 #define GCCB_HUB_QUEUE 64     // hub rows a CTA of the barrier-free gather kernels defers to its cooperative pass
 template <int W>
 __device__ __forceinline__ void gather_range(const float* __restrict__ src, const int32_t* __restrict__ indices,

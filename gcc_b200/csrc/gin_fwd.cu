@@ -298,28 +298,38 @@ gin_pool_kernel(int L, const int32_t* __restrict__ node_off_v, int B, const int3
     if (tid < GCCB_TILE_ROWS) gid[tid] = row0 + tid < N ? graph_id[row0 + tid] : -1;
     __syncthreads();
     for (int l = 0; l < L; ++l) {
+      // thread = (row group, float4 column): 128-bit loads, GCCB_TILE_ROWS / RG rows each, all of them in flight
+      // (a scalar column per thread with 64 dependent-issue loads ran this pass at 0.9 TB/s at hidden 256)
       const int W = l == 0 ? GCCB_DINP : H;
       const float* src = l == 0 ? x0 : h_layers[l - 1];
-      const int RG = 256 / W > 0 ? 256 / W : 1;          // row groups; threads beyond RG*W idle
-      const int c = tid % W, rg = tid / W;
+      const int VW = W >> 2;                                // float4 columns (W is a multiple of 4)
+      const int RG = 256 / VW < GCCB_TILE_ROWS ? 256 / VW : GCCB_TILE_ROWS;
+      const int v = tid % VW, rg = tid / VW;
       if (rg >= RG) continue;
       const int per = GCCB_TILE_ROWS / RG;
       const int rb = rg * per;
       int g_run = gid[rb];
-      float acc = 0.f;
-#pragma unroll 4
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto flush = [&](int g) {
+        double* dst = &pool_acc[((size_t)l * B + g) * PW + 4 * v];
+        atomicAdd(dst, (double)acc.x);
+        atomicAdd(dst + 1, (double)acc.y);
+        atomicAdd(dst + 2, (double)acc.z);
+        atomicAdd(dst + 3, (double)acc.w);
+      };
+#pragma unroll 8
       for (int k = 0; k < per; ++k) {
         const int g = gid[rb + k];
         if (g < 0) break;
-        const float v = src[(size_t)(row0 + rb + k) * W + c];
+        const float4 x = *reinterpret_cast<const float4*>(src + (size_t)(row0 + rb + k) * W + 4 * v);
         if (g != g_run) {
-          atomicAdd(&pool_acc[((size_t)l * B + g_run) * PW + c], (double)acc);
-          acc = 0.f;
+          flush(g_run);
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
           g_run = g;
         }
-        acc += v;
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
       }
-      if (g_run >= 0) atomicAdd(&pool_acc[((size_t)l * B + g_run) * PW + c], (double)acc);
+      if (g_run >= 0) flush(g_run);
     }
   }
 }
@@ -336,19 +346,22 @@ gin_pool_predict_kernel(GinDims d, const int32_t* __restrict__ node_off_v, int B
                         uint64_t drop_step, int drop_layer_base, uint32_t keep_thresh,
                         float* __restrict__ pooled, float* __restrict__ score_out,
                         float* __restrict__ feat_out, float* __restrict__ pooled_user) {
+  // GCCB_GPB graphs per CTA: a head weight row is read once and used for all of them (one graph per CTA re-read
+  // the L x H x H weights from L2 for every graph: 1.3 GB per launch at hidden 256 / batch 1024)
   constexpr int MAXW = H > GCCB_DINP ? H : GCCB_DINP;
-  __shared__ float pl[MAXW];
-  __shared__ float score[H];
-  __shared__ float red_s[8];
-  const int g = blockIdx.x, tid = threadIdx.x;
+  constexpr int G = GCCB_GPB;
+  __shared__ float pl[G][MAXW];
+  __shared__ float score[G][H];
+  const int g0 = blockIdx.x * G, tid = threadIdx.x;
+  const int ng = min(G, B - g0);
   if (node_off_v[B] < 0) {                               // view published empty: defined (zero) outputs, the
-    for (int o = tid; o < H; o += 256) {                 // optimiser / enqueue skip the step (gccb200.h)
-      score_out[(size_t)g * H + o] = 0.f;
-      feat_out[(size_t)g * H + o] = 0.f;
+    for (int i = tid; i < ng * H; i += 256) {            // optimiser / enqueue skip the step (gccb200.h)
+      score_out[(size_t)g0 * H + i] = 0.f;
+      feat_out[(size_t)g0 * H + i] = 0.f;
     }
     return;
   }
-  for (int o = tid; o < H; o += 256) score[o] = 0.f;
+  for (int i = tid; i < G * H; i += 256) (&score[0][0])[i] = 0.f;
   __syncthreads();
   for (int l = 0; l < d.L; ++l) {
     const int W = l == 0 ? GCCB_DINP : H;                 // stored width
@@ -356,50 +369,68 @@ gin_pool_predict_kernel(GinDims d, const int32_t* __restrict__ node_off_v, int B
     const float* Wp = params + wp_off[l];
     const float* bp = params + bp_off[l];
     __syncthreads();
-    for (int cc = tid; cc < W; cc += 256) {
-      const float s = (float)pool_acc[((size_t)l * B + g) * PW + cc];
-      pl[cc] = s;
-      pooled[((size_t)l * B + g) * PW + cc] = s;
-      if (pooled_user && l > 0) pooled_user[((size_t)(l - 1) * B + g) * H + cc] = s;   // all_outputs[1:]
+    for (int i = tid; i < G * W; i += 256) {
+      const int gi = i / W, cc = i - gi * W;
+      float s = 0.f;
+      if (gi < ng) {
+        const int g = g0 + gi;
+        s = (float)pool_acc[((size_t)l * B + g) * PW + cc];
+        pooled[((size_t)l * B + g) * PW + cc] = s;
+        if (pooled_user && l > 0) pooled_user[((size_t)(l - 1) * B + g) * H + cc] = s;   // all_outputs[1:]
+      }
+      pl[gi][cc] = s;
     }
     __syncthreads();
-    // head GEMV straight from L2 (16 KB per layer, read once per CTA): four lanes share an output,
-    // lane q takes k = q, q+4, ... (the four reads of a step are 16 contiguous bytes)
+    // head GEMV: four lanes share an output, lane q takes k = q, q+4, ... (the four weight reads of a step are
+    // 16 contiguous bytes); every weight is used for the G graphs of the CTA
     for (int o0 = 0; o0 < H; o0 += 64) {
       const int o = o0 + (tid >> 2), kq = tid & 3;
-      float s = 0.f;
+      float sg[G];
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) sg[gi] = 0.f;
       const float* wrow = Wp + (size_t)(o < H ? o : 0) * inf;
       if (o < H) {
-#pragma unroll 8
-        for (int k = kq; k < inf; k += 4) s = fmaf(pl[k], wrow[k], s);
+#pragma unroll 4
+        for (int k = kq; k < inf; k += 4) {
+          const float w = wrow[k];
+#pragma unroll
+          for (int gi = 0; gi < G; ++gi) sg[gi] = fmaf(pl[gi][k], w, sg[gi]);
+        }
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+        sg[gi] += __shfl_xor_sync(0xffffffffu, sg[gi], 1);
+        sg[gi] += __shfl_xor_sync(0xffffffffu, sg[gi], 2);
+      }
       if (kq != 0 || o >= H) continue;
-      s += bp[o];
-      if (drop_layer_base >= 0) {                          // Dropout(p) in train mode, Philox mask
-        const uint32_t e = (uint32_t)(g * H + o);
-        u32x4 w = philox_at(drop_key, drop_step, e >> 2, 0, (uint32_t)(drop_layer_base + l),
-                            GCCB_TAG_DROPOUT);
-        const uint32_t word = (e & 3u) == 0 ? w.x : (e & 3u) == 1 ? w.y : (e & 3u) == 2 ? w.z : w.w;
-        s = word < keep_thresh ? s / (1.0f - d.drop_p) : 0.f;
+      const float bias = bp[o];
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+        if (gi >= ng) break;
+        float sv = sg[gi] + bias;
+        if (drop_layer_base >= 0) {                        // Dropout(p) in train mode, Philox mask
+          const uint32_t e = (uint32_t)((g0 + gi) * H + o);
+          u32x4 w = philox_at(drop_key, drop_step, e >> 2, 0, (uint32_t)(drop_layer_base + l),
+                              GCCB_TAG_DROPOUT);
+          const uint32_t word = (e & 3u) == 0 ? w.x : (e & 3u) == 1 ? w.y : (e & 3u) == 2 ? w.z : w.w;
+          sv = word < keep_thresh ? sv / (1.0f - d.drop_p) : 0.f;
+        }
+        score[gi][o] += sv;
       }
-      score[o] += s;
     }
     __syncthreads();
   }
-  // F.normalize(x, p=2, dim=-1, eps): x / max(||x||, eps)
-  float ss = 0.f;
-  for (int o = tid; o < H; o += 256) ss = fmaf(score[o], score[o], ss);
-  ss = warp_sum(ss);
-  if ((tid & 31) == 0) red_s[tid >> 5] = ss;
-  __syncthreads();
-  float tot = 0.f;
-  for (int j = 0; j < 8; ++j) tot += red_s[j];
-  const float nrm = fmaxf(sqrtf(tot), d.norm_eps);
-  for (int o = tid; o < H; o += 256) {
-    score_out[(size_t)g * H + o] = score[o];
-    feat_out[(size_t)g * H + o] = d.norm ? score[o] / nrm : score[o];
+  // F.normalize(x, p=2, dim=-1, eps): x / max(||x||, eps) -- one warp per graph
+  for (int gi = tid >> 5; gi < ng; gi += 8) {
+    const int lane = tid & 31;
+    float ss = 0.f;
+    for (int o = lane; o < H; o += 32) ss = fmaf(score[gi][o], score[gi][o], ss);
+    ss = warp_sum(ss);
+    const float nrm = fmaxf(sqrtf(ss), d.norm_eps);
+    for (int o = lane; o < H; o += 32) {
+      score_out[(size_t)(g0 + gi) * H + o] = score[gi][o];
+      feat_out[(size_t)(g0 + gi) * H + o] = d.norm ? score[gi][o] / nrm : score[gi][o];
+    }
   }
 }
 
@@ -498,7 +529,7 @@ static int run_forward(const FwdArgs& a) {
   GCCB_LAUNCH(kpl, grid, 256, 0, a.stream, d.L, node_off_v, B, graph_id, (const float*)x0, a.d_hptrs, a.al.PW,
               pool_acc);
   auto kp = gin_pool_predict_kernel<H>;
-  GCCB_LAUNCH(kp, B, 256, 0, a.stream, d, node_off_v, B, (const double*)pool_acc, a.params, a.d_offs, a.d_offs + 8,
+  GCCB_LAUNCH(kp, (B + GCCB_GPB - 1) / GCCB_GPB, 256, 0, a.stream, d, node_off_v, B, (const double*)pool_acc, a.params, a.d_offs, a.d_offs + 8,
               a.al.PW, a.drop_key, a.drop_step, a.drop_base, keep, (float*)(a.acts + a.al.pooled),
               (float*)(a.acts + a.al.score), a.feat, a.pooled_user);
   return check_launch("gccb_gin_forward");
@@ -711,7 +742,7 @@ static int run_forward_tc(const FwdArgs& a) {
   GCCB_LAUNCH(kpl, grid, 256, 0, a.stream, d.L, node_off_v, B, graph_id, (const float*)x0, a.d_hptrs, a.al.PW,
               pool_acc);
   auto kp = gin_pool_predict_kernel<H>;
-  GCCB_LAUNCH(kp, B, 256, 0, a.stream, d, node_off_v, B, (const double*)pool_acc, a.params, a.d_offs, a.d_offs + 8,
+  GCCB_LAUNCH(kp, (B + GCCB_GPB - 1) / GCCB_GPB, 256, 0, a.stream, d, node_off_v, B, (const double*)pool_acc, a.params, a.d_offs, a.d_offs + 8,
               a.al.PW, a.drop_key, a.drop_step, a.drop_base, keep, (float*)(a.acts + a.al.pooled),
               (float*)(a.acts + a.al.score), a.feat, a.pooled_user);
   return check_launch("gccb_gin_forward (tensor cores)");
