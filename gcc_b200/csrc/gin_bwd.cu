@@ -72,54 +72,72 @@ gin_pool_predict_bwd_kernel(GinDims d, const int32_t* __restrict__ node_off_v, i
                             uint64_t drop_key, uint64_t drop_step, int drop_layer_base,
                             uint32_t keep_thresh, int DW, float* __restrict__ dS,
                             float* __restrict__ dpool) {
-  __shared__ float ds[H];
-  __shared__ float dsl[H];
-  __shared__ float red_s[2][8];
-  const int g = blockIdx.x, tid = threadIdx.x;
+  // GCCB_GPB graphs per CTA, like the forward heads: every head weight is read once for all of them
+  constexpr int G = GCCB_GPB;
+  __shared__ float ds[G][H];
+  __shared__ float dsl[G][H];
+  const int g0 = blockIdx.x * G, tid = threadIdx.x, lane = tid & 31;
+  const int ng = min(G, B - g0);
   if (node_off_v[B] < 0) return;
-  // F.normalize backward: y = x / max(||x||, eps)
-  float ss = 0.f, dot = 0.f;
-  for (int o = tid; o < H; o += 256) {
-    float x = score[(size_t)g * H + o];
-    ss = fmaf(x, x, ss);
-    dot = fmaf(x, dfeat[(size_t)g * H + o], dot);
-  }
-  ss = warp_sum(ss);
-  dot = warp_sum(dot);
-  if ((tid & 31) == 0) { red_s[0][tid >> 5] = ss; red_s[1][tid >> 5] = dot; }
-  __syncthreads();
-  float tss = 0.f, tdot = 0.f;
-  for (int j = 0; j < 8; ++j) { tss += red_s[0][j]; tdot += red_s[1][j]; }
-  const float nrm = sqrtf(tss);
-  for (int o = tid; o < H; o += 256) {
-    float x = score[(size_t)g * H + o], gy = dfeat[(size_t)g * H + o];
-    float dx;
-    if (!d.norm) dx = gy;
-    else if (nrm > d.norm_eps) dx = (gy - x * (tdot / (nrm * nrm))) / nrm;   // d/dx [x/||x||]
-    else dx = gy / d.norm_eps;                                                // clamped branch
-    ds[o] = dx;
+  // F.normalize backward: y = x / max(||x||, eps) -- one warp per graph
+  for (int gi = tid >> 5; gi < G; gi += 8) {
+    if (gi >= ng) {
+      for (int o = lane; o < H; o += 32) ds[gi][o] = 0.f;
+      continue;
+    }
+    const int g = g0 + gi;
+    float ss = 0.f, dot = 0.f;
+    for (int o = lane; o < H; o += 32) {
+      const float x = score[(size_t)g * H + o];
+      ss = fmaf(x, x, ss);
+      dot = fmaf(x, dfeat[(size_t)g * H + o], dot);
+    }
+    ss = warp_sum(ss);
+    dot = warp_sum(dot);
+    const float nrm = sqrtf(ss);
+    for (int o = lane; o < H; o += 32) {
+      const float x = score[(size_t)g * H + o], gy = dfeat[(size_t)g * H + o];
+      float dx;
+      if (!d.norm) dx = gy;
+      else if (nrm > d.norm_eps) dx = (gy - x * (dot / (nrm * nrm))) / nrm;   // d/dx [x/||x||]
+      else dx = gy / d.norm_eps;                                              // clamped branch
+      ds[gi][o] = dx;
+    }
   }
   __syncthreads();
   for (int l = 0; l < d.L; ++l) {
     const int inf = l == 0 ? d.din : H;
-    for (int o = tid; o < H; o += 256) {
-      float v = ds[o];
-      if (drop_layer_base >= 0) {
-        const uint32_t e = (uint32_t)(g * H + o);
-        u32x4 w = philox_at(drop_key, drop_step, e >> 2, 0, (uint32_t)(drop_layer_base + l), GCCB_TAG_DROPOUT);
-        const uint32_t word = (e & 3u) == 0 ? w.x : (e & 3u) == 1 ? w.y : (e & 3u) == 2 ? w.z : w.w;
-        v = word < keep_thresh ? v / (1.0f - d.drop_p) : 0.f;
+    for (int i = tid; i < G * H; i += 256) {
+      const int gi = i / H, o = i - gi * H;
+      float v = ds[gi][o];
+      if (gi < ng) {
+        if (drop_layer_base >= 0) {
+          const uint32_t e = (uint32_t)((g0 + gi) * H + o);
+          u32x4 w = philox_at(drop_key, drop_step, e >> 2, 0, (uint32_t)(drop_layer_base + l), GCCB_TAG_DROPOUT);
+          const uint32_t word = (e & 3u) == 0 ? w.x : (e & 3u) == 1 ? w.y : (e & 3u) == 2 ? w.z : w.w;
+          v = word < keep_thresh ? v / (1.0f - d.drop_p) : 0.f;
+        }
+        dS[((size_t)l * B + g0 + gi) * H + o] = v;
       }
-      dsl[o] = v;
-      dS[((size_t)l * B + g) * H + o] = v;
+      dsl[gi][o] = v;
     }
     __syncthreads();
     const float* Wp = params + lay.wp[l];
     for (int k = tid; k < DW; k += 256) {
-      float s = 0.f;
-      if (k < inf)
-        for (int o = 0; o < H; ++o) s = fmaf(dsl[o], Wp[(size_t)o * inf + k], s);
-      dpool[((size_t)l * B + g) * DW + k] = s;
+      float sg[G];
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) sg[gi] = 0.f;
+      if (k < inf) {
+#pragma unroll 4
+        for (int o = 0; o < H; ++o) {
+          const float w = Wp[(size_t)o * inf + k];
+#pragma unroll
+          for (int gi = 0; gi < G; ++gi) sg[gi] = fmaf(dsl[gi][o], w, sg[gi]);
+        }
+      }
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi)
+        if (gi < ng) dpool[((size_t)l * B + g0 + gi) * DW + k] = sg[gi];
     }
     __syncthreads();
   }
@@ -658,7 +676,7 @@ static int run_backward(const BwdArgs& a) {
 #endif
   cudaMemsetAsync(red, 0, (size_t)(d.L - 1) * 3 * 2 * H * sizeof(double), (cudaStream_t)a.stream);
   auto kpb = gin_pool_predict_bwd_kernel<H>;
-  GCCB_LAUNCH(kpb, B, 256, 0, a.stream, d, node_off_v, B, P, a.lay, (const float*)(a.acts + a.al.score),
+  GCCB_LAUNCH(kpb, (B + GCCB_GPB - 1) / GCCB_GPB, 256, 0, a.stream, d, node_off_v, B, P, a.lay, (const float*)(a.acts + a.al.score),
               a.dfeat, a.drop_key, a.drop_step, a.drop_base, keep, DW, dS, dpool);
 #ifndef GCCB_EMU
   cudaEventRecord(ev_head, main_s);
@@ -990,7 +1008,7 @@ static int run_backward_tc(const BwdArgs& a) {
   cudaEvent_t ev_head = kit->ev[16], ev_join = kit->ev[17];
   cudaMemsetAsync(red, 0, (size_t)(d.L - 1) * 3 * 2 * H * sizeof(double), main_s);
   auto kpb = gin_pool_predict_bwd_kernel<H>;
-  GCCB_LAUNCH(kpb, B, 256, 0, a.stream, d, node_off_v, B, P, a.lay, (const float*)(a.acts + a.al.score),
+  GCCB_LAUNCH(kpb, (B + GCCB_GPB - 1) / GCCB_GPB, 256, 0, a.stream, d, node_off_v, B, P, a.lay, (const float*)(a.acts + a.al.score),
               a.dfeat, a.drop_key, a.drop_step, a.drop_base, keep, DW, dS, dpool);
   cudaEventRecord(ev_head, main_s);
   cudaStreamWaitEvent(side, ev_head, 0);

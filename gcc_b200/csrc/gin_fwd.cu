@@ -302,6 +302,30 @@ gin_pool_kernel(int L, const int32_t* __restrict__ node_off_v, int B, const int3
       // (a scalar column per thread with 64 dependent-issue loads ran this pass at 0.9 TB/s at hidden 256)
       const int W = l == 0 ? GCCB_DINP : H;
       const float* src = l == 0 ? x0 : h_layers[l - 1];
+      if (W < 128) {
+        // narrow rows: one column per thread, 256 / W row groups (fewer, longer runs = fewer atomics)
+        const int RGs = 256 / W > 0 ? 256 / W : 1;
+        const int c = tid % W, rgs = tid / W;
+        if (rgs >= RGs) continue;
+        const int pers = GCCB_TILE_ROWS / RGs;
+        const int rbs = rgs * pers;
+        int g_run = gid[rbs];
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < pers; ++k) {
+          const int g = gid[rbs + k];
+          if (g < 0) break;
+          const float x = src[(size_t)(row0 + rbs + k) * W + c];
+          if (g != g_run) {
+            atomicAdd(&pool_acc[((size_t)l * B + g_run) * PW + c], (double)acc);
+            acc = 0.f;
+            g_run = g;
+          }
+          acc += x;
+        }
+        if (g_run >= 0) atomicAdd(&pool_acc[((size_t)l * B + g_run) * PW + c], (double)acc);
+        continue;
+      }
       const int VW = W >> 2;                                // float4 columns (W is a multiple of 4)
       const int RG = 256 / VW < GCCB_TILE_ROWS ? 256 / VW : GCCB_TILE_ROWS;
       const int v = tid % VW, rg = tid / VW;
