@@ -486,7 +486,9 @@ def eigensolver_report(buf, eig_ms):
     an fp32 FLOP estimate against the CUDA-core peak.  Per ChFSI iteration on an n-node, m-edge
     ego-net with a 48-column block: filter deg*(2(m+n)+3n)*48, Gram-Schmidt 2n*48^2 (one pass),
     H = Q^T L Q 2(m+n)*48 + 2n*48^2, 48x48 Jacobi ~6 sweeps * 47 rounds * 14e3, X = QW 2n*48^2,
-    residual 2(m+n)*48 + 6n*48; direct Jacobi (n <= 64): sweeps * 4 n^3."""
+    residual 2(m+n)*48 + 6n*48; direct Jacobi (n <= 64): sweeps * 4 n^3; dense tridiagonal solver (n <= 228,
+    reported with 0 iterations): 4/3 n^3 (Householder) + 4*32 n^2 (back-transformation) + 2*2*32^2 n (two
+    Gram-Schmidt passes) + 3*32*8n (inverse iterations) + 7*NT*5n (Sturm counts)."""
     import numpy as np
     it, res = buf.eig_debug()
     it, res = it.cpu().numpy().astype(np.int64), res.cpu().numpy()
@@ -495,13 +497,15 @@ def eigensolver_report(buf, eig_ms):
     ch = it > 0
     deg_sum = np.where(it >= 1, 4, 0) + 8 * np.maximum(it - 1, 0)
     per_iter = 2 * n * 48 ** 2 * 3 + (2 * (m + n) * 48) * 2 + 6 * n * 48 + 6 * 47 * 14e3
-    flops = np.where(ch, deg_sum * (2 * (m + n) + 3 * n) * 48 + it * per_iter, -it * 4.0 * n ** 3)
+    dense = 4.0 / 3.0 * n ** 3 + 128.0 * n ** 2 + 4096.0 * n + 768.0 * n + 7 * 256 * 5.0 * n
+    flops = np.where(ch, deg_sum * (2 * (m + n) + 3 * n) * 48 + it * per_iter, np.where(it < 0, -it * 4.0 * n ** 3, dense))
     total = float(flops.sum())
     peak = 148 * 128 * 2 * 1.965e9 / 1e12                   # fp32 FMA on the CUDA cores at 1965 MHz
     ach = total / (eig_ms / 1e3) / 1e12
     return {"bound": "fp32 CUDA-core FMA + shared-memory/barrier latency (neither HBM nor tensor; SURVEY 8d)",
             "k": 32, "block": 48, "egonets": int(len(n)), "mean_n": float(n.mean()), "max_n": int(n.max()),
             "mean_iterations_chfsi": float(it[ch].mean()) if ch.any() else 0.0,
+            "egonets_dense_solver": int((it == 0).sum()), "egonets_chfsi": int(ch.sum()),
             "max_iterations": int(it.max()), "max_residual": float(res.max()),
             "est_flop_per_batch": total, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak, "ms_per_batch": eig_ms, "egonets_per_sec": len(n) / (eig_ms / 1e3)}

@@ -30,6 +30,8 @@
 // deterministic run to run (no floating-point atomics on the results).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace gccb {
 
 #define GCCB_EIG_SMALL 64          // largest n solved by the dense Jacobi kernel
@@ -87,6 +89,15 @@ namespace gccb {
 #ifndef GCCB_CAP_MID2
 #define GCCB_CAP_MID2 (148 * 2)     // persistent grid of the n <= 160 class (2 CTAs per SM)
 #endif
+#ifndef GCCB_CAP_DN_A
+#define GCCB_CAP_DN_A (148 * 4)     // persistent grids of the dense classes
+#endif
+#ifndef GCCB_CAP_DN_B
+#define GCCB_CAP_DN_B (148 * 2)
+#endif
+#ifndef GCCB_CAP_DN_C
+#define GCCB_CAP_DN_C 148
+#endif
 #ifndef GCCB_BIG_NT
 #define GCCB_BIG_NT 512            // threads of the large-ego-net CTAs: 512 x 64 registers leave half of
 #endif                             // the SM's register file to concurrent kernels (these CTAs live for ms)
@@ -113,28 +124,40 @@ __device__ __forceinline__ int eig_class(int n) {
 }
 
 // Work lists: worklist[c][i] = slot.  One CTA, deterministic order.  grid = 1, block = 256.
+// Ego-nets up to `dense_max` vertices go to the dense tridiagonal solver instead (lists dense_list[3][2B], classes
+// n <= dn_a / dn_b / larger; dense_max = 0: none).
 __global__ void __launch_bounds__(256)
 posenc_classify_kernel(const int64_t* __restrict__ counters, const int32_t* __restrict__ node_off,
-                       int B, int32_t* __restrict__ worklist, int32_t* __restrict__ counts) {
+                       int B, int32_t* __restrict__ worklist, int32_t* __restrict__ counts,
+                       int dense_max, int dn_a, int dn_b, int32_t* __restrict__ dense_list,
+                       int32_t* __restrict__ dense_counts) {
   __shared__ int scan_scratch[33];
   const int tid = threadIdx.x;
-  int base[GCCB_EIG_NCLASS] = {0};
+  constexpr int NC = GCCB_EIG_NCLASS + 3;
+  int base[NC] = {0};
   for (int s0 = 0; s0 < 2 * B; s0 += 256) {
     int slot = s0 + tid;
     int cls = -1;
     if (slot < 2 * B) {
       int view = slot / B;
-      if (node_off[view * (B + 1) + B] >= 0) cls = eig_class((int)counters[(size_t)slot * 4]);
+      if (node_off[view * (B + 1) + B] >= 0) {
+        const int n = (int)counters[(size_t)slot * 4];
+        cls = n <= dense_max ? GCCB_EIG_NCLASS + (n <= dn_a ? 0 : n <= dn_b ? 1 : 2) : eig_class(n);
+      }
     }
 #pragma unroll
-    for (int c = 0; c < GCCB_EIG_NCLASS; ++c) {
+    for (int c = 0; c < NC; ++c) {
       int tot;
       int ex = block_scan_excl(cls == c ? 1 : 0, scan_scratch, &tot);
-      if (cls == c) worklist[(size_t)c * 2 * B + base[c] + ex] = slot;
+      if (cls == c) {
+        if (c < GCCB_EIG_NCLASS) worklist[(size_t)c * 2 * B + base[c] + ex] = slot;
+        else dense_list[(size_t)(c - GCCB_EIG_NCLASS) * 2 * B + base[c] + ex] = slot;
+      }
       base[c] += tot;
     }
   }
   if (tid < GCCB_EIG_NCLASS) counts[tid] = base[tid];
+  if (tid < 3) dense_counts[tid] = base[GCCB_EIG_NCLASS + tid];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1505,6 +1528,465 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
   }
 }
 
+// ---- solver (0): dense tridiagonal path, n <= GCCB_DN_C ------------------------------------------------
+// Ego-nets are small (C2 workload: mean 104 vertices, 97 % below 230): the whole normalised adjacency matrix fits
+// in the shared memory of one CTA, and the textbook dense symmetric eigensolver is both cheaper and more accurate
+// in fp32 than any subspace iteration (measured on the fp32 model of this kernel, C2 ego-nets and the degenerate
+// test graphs: eigenvalues to 4e-7, residuals to 5e-6, orthonormality to 1e-6, the reference's own simple-spectrum
+// goldens elementwise to 2e-6; ChFSI: 2e-5 / 4e-5 / 1e-4):
+//
+//   1. Householder tridiagonalisation Q^T L Q = T, unblocked, full symmetric storage (row stride = 4 mod 32, two
+//      threads per row reading 64-bit words: conflict-free), TWO barriers per column: the product S v is taken
+//      from the raw column x (v = scale * (x - beta e1), so S v = scale * (S x - beta S e1)) and overlaps the
+//      norm of x, every warp computes the scalars redundantly, w = p - gamma v is formed on the fly inside the
+//      rank-2 update, and the update hands the next column over in contiguous form;
+//   2. the k <= 32 largest eigenvalues of T by multisection on Sturm counts (all threads: a first cut of the
+//      Gershgorin interval into NT + 1 pieces, then NT / 32 points per eigenvalue and round; 6 / 4 rounds);
+//   3. eigenvectors of T by inverse iteration, one lane per eigenvalue (Gaussian elimination with partial
+//      pivoting; pivot rows that were swapped are original matrix entries, so two floats per row describe the
+//      factor -- kept in the L2-resident workspace, written coalesced, read back with one block prefetched), three
+//      iterations from a counter-based pseudo-random start, close eigenvalues separated by 6e-7 like LAPACK's sstein;
+//   4. modified Gram-Schmidt over the k vectors (lanes = columns: conflict-free; degenerate clusters -- the null
+//      space of a near-tree reaches multiplicity 30+ -- come out as an orthonormal basis), one pass after the second
+//      and one after the third inverse iteration (see the comment at the loop);
+//   5. back-transformation X = Q Z: every warp applies all n - 2 reflectors to its own columns held in registers
+//      (no barriers);
+//   6. a residual check against the sparse matrix (reported per ego-net; NOCONV above GCCB_DN_RES_FLAG).
+//
+// Z (n x 32) lives in the dead upper-right corner of the matrix (rows < n - 32, columns >= n - 32) plus a 32 x 32 tail.
+#define GCCB_DN_A 96
+#define GCCB_DN_B 144
+#define GCCB_DN_C 228
+#ifndef GCCB_DN_INVIT
+#define GCCB_DN_INVIT 3
+#endif
+#ifndef GCCB_DN_MGS
+#define GCCB_DN_MGS 2
+#endif
+#define GCCB_DN_PIVMIN 1.0e-30f
+#define GCCB_DN_GUARD 1.0e-9f      // smallest pivot of the inverse iteration (a perturbation far below eps * ||T||)
+#define GCCB_DN_SEP 6.0e-7f        // separation forced between close eigenvalues before the inverse iteration
+#define GCCB_DN_RES_FLAG 1.0e-3f
+
+
+#ifdef GCCB_EMU_DEBUG_DN
+#define DN_DEBUG(tag) do { __syncthreads(); if (tid == 0 && getenv("GCCB_DN_DEBUG")) { \
+    fprintf(stderr, "DN %s n=%d:", tag, n); \
+    for (int c = 0; c < k; ++c) { double rs = 0, nn = 0; \
+      for (int i = 0; i < n; ++i) { double y = (double)d[i] * zrow(i)[c] + (i > 0 ? (double)e[i-1] * zrow(i-1)[c] : 0.0) + (i + 1 < n ? (double)e[i] * zrow(i+1)[c] : 0.0) - (double)lam[c] * zrow(i)[c]; rs += y * y; nn += (double)zrow(i)[c] * zrow(i)[c]; } \
+      fprintf(stderr, " %.1e", sqrt(rs / nn)); } fprintf(stderr, "\n"); } __syncthreads(); } while (0)
+#else
+#define DN_DEBUG(tag)
+#endif
+__host__ __device__ constexpr int dn_ld(int n) { return ((n + 27) / 32) * 32 + 4; }
+
+// number of eigenvalues of T below x
+__device__ __forceinline__ int dn_sturm(const float* __restrict__ d, const float* __restrict__ e2, int n, float x) {
+  float q = d[0] - x;
+  if (fabsf(q) < GCCB_DN_PIVMIN) q = -GCCB_DN_PIVMIN;
+  int c = q < 0.f ? 1 : 0;
+  for (int i = 1; i < n; ++i) {
+    q = (d[i] - x) - __fdividef(e2[i - 1], q);
+    if (fabsf(q) < GCCB_DN_PIVMIN) q = -GCCB_DN_PIVMIN;
+    c += q < 0.f ? 1 : 0;
+  }
+  return c;
+}
+
+template <int NMAX, int NT>
+__device__ __forceinline__ void posenc_dense_item(const int slot, int B, int node_cap, int edge_cap,
+                    const int32_t* __restrict__ node_off, const int32_t* __restrict__ b_indptr,
+                    const int32_t* __restrict__ b_indices, const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
+                    float* __restrict__ blocks, float* __restrict__ pos, float* __restrict__ eigvals,
+                    int32_t* __restrict__ flags, int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res,
+                    long long* __restrict__ dbg_phase) {
+  constexpr int NW = NT / 32, NP = ((NMAX + 3) & ~3) + 4, NR = (NMAX + 31) / 32, CPW = 32 / NW;
+  static_assert(NT >= 2 * NMAX && NW <= 32 && 32 % NW == 0, "two threads per matrix row");
+  GCCB_DYN_SMEM(float, A);                              // n x ld, row-major
+  // (64-bit accesses to vbuf / pbuf / xbuf: every array gets its own aligned declaration)
+  __align__(16) __shared__ float d[NP];
+  __align__(16) __shared__ float e[NP];
+  __align__(16) __shared__ float e2[NP];
+  __align__(16) __shared__ float taus[NP];
+  __align__(16) __shared__ float vbuf[NP];
+  __align__(16) __shared__ float pbuf[NP];
+  __align__(16) __shared__ float xbuf[NP];
+  __align__(16) __shared__ float dinv[NP];
+  __shared__ float ztail[32 * 32];
+  __shared__ float lam[32], lamp[32], lo[32], hi[32], sgn[32];
+  __shared__ int cnt[NT];
+  __shared__ float part[NW * 32];
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = GCCB_CLK();
+  const int view = slot / B, g = slot - view * B;
+  const int noff = node_off[view * (B + 1) + g];
+  const int n = node_off[view * (B + 1) + g + 1] - noff;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = min(n - 2, pos_dim);
+  float* out = pos + ((size_t)view * node_cap + noff) * pos_dim;
+  if (k <= 0) {                                         // data_util.py:243-244
+    for (int i = tid; i < n * pos_dim; i += NT) out[i] = 0.f;
+    if (eigvals)
+      for (int i = tid; i < pos_dim; i += NT) eigvals[(size_t)slot * pos_dim + i] = 0.f;
+    if (tid == 0) { dbg_iters[slot] = 0; dbg_res[slot] = 0.f; }
+    return;
+  }
+  const int ld = dn_ld(n);
+  const int zb = n > 32 ? n - 32 : 0;                   // rows below zb keep their Z row inside the matrix
+  auto zrow = [&](int i) -> float* { return i < zb ? A + (size_t)i * ld + (n - 32) : ztail + (i - zb) * 32; };
+  const int32_t* v_indptr = b_indptr + (size_t)view * (node_cap + 1);
+  const int32_t* v_indices = b_indices + (size_t)view * edge_cap;
+  const int32_t* v_deg = sub_deg + (size_t)view * node_cap;
+  // factor rows of the inverse iteration: two n x 32 arrays in this ego-net's part of the L2 workspace
+  float* U0 = blocks + ((size_t)view * node_cap + noff) * (GCCB_CF_B + 1);
+  float* U1 = U0 + (size_t)2 * node_cap * (GCCB_CF_B + 1);
+  // ---- the matrix ---------------------------------------------------------------------------------------------
+  for (int i = tid; i < NP; i += NT) { d[i] = 0.f; e[i] = 0.f; e2[i] = 0.f; taus[i] = 0.f; vbuf[i] = 0.f; pbuf[i] = 0.f; xbuf[i] = 0.f; }
+  for (int i = tid; i < n; i += NT) {
+    int dg = v_deg[noff + i];
+    dinv[i] = 1.0f / sqrtf((float)(dg < 1 ? 1 : dg));  // in_degrees().clip(1) ** -0.5
+  }
+  {
+    float4* A4 = reinterpret_cast<float4*>(A);
+    for (int i = tid; i < n * ld / 4; i += NT) A4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  for (int i = warp; i < n; i += NW) {                  // row i <- its in-neighbours j (multi-edges add up)
+    const int beg = v_indptr[noff + i], end = v_indptr[noff + i + 1];
+    const float di = dinv[i];
+    for (int ed = beg + lane; ed < end; ed += 32) {
+      int j = v_indices[ed] - noff;
+      atomicAdd(&A[(size_t)j * ld + i], di * dinv[j]);  // shared-memory adds of exact products
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += NT) xbuf[i] = i >= 1 ? A[(size_t)i * ld] : 0.f;
+  __syncthreads();
+  GCCB_TICK(0);
+  // ---- 1. Householder tridiagonalisation -------------------------------------------------------------------------
+  {
+    const int r = tid >> 1, h = tid & 1;
+    float* row = A + (size_t)r * ld;
+    for (int kk = 0; kk + 2 < n; ++kk) {
+      const int c0 = (kk + 1) & ~3;
+      const bool mine = r > kk && r < n;
+      float y = 0.f;
+      if (mine) {                                       // y = (S x)_r over this thread's half of the row
+        float y0 = 0.f, y1 = 0.f;
+        for (int c = c0 + 2 * h; c < n; c += 4) {
+          const float2 a = *reinterpret_cast<const float2*>(row + c);
+          const float2 x = *reinterpret_cast<const float2*>(xbuf + c);
+          y0 = fmaf(a.x, x.x, y0);
+          y1 = fmaf(a.y, x.y, y1);
+        }
+        y = y0 + y1;
+      }
+      y += __shfl_xor_sync(0xffffffffu, y, 1);
+      float s = 0.f;                                    // every warp: ||x(kk+2:)||^2
+      for (int i = kk + 2 + lane; i < n; i += 32) { const float t = xbuf[i]; s = fmaf(t, t, s); }
+      s = warp_sum(s);
+      const float alpha = xbuf[kk + 1];
+      float tau = 0.f, beta = alpha, scale = 0.f;
+      if (s > 1.0e-30f) {
+        beta = -copysignf(sqrtf(fmaf(alpha, alpha, s)), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0f / (alpha - beta);
+      }
+      if (mine && h == 0) {
+        const float vr = r == kk + 1 ? 1.0f : xbuf[r] * scale;
+        vbuf[r] = vr;
+        pbuf[r] = tau * scale * (y - beta * row[kk + 1]);
+        row[kk] = vr;                                   // the reflector stays in column kk for step 5
+      }
+      if (tid == 2 * kk) { vbuf[kk] = 0.f; pbuf[kk] = 0.f; }
+      if (tid == 0) { d[kk] = A[(size_t)kk * ld + kk]; e[kk] = beta; taus[kk] = tau; }
+      __syncthreads();
+      if (tau != 0.f) {
+        float gs = 0.f;                                 // every warp: gamma = tau/2 * p.v
+        for (int i = kk + 1 + lane; i < n; i += 32) gs = fmaf(pbuf[i], vbuf[i], gs);
+        const float gam = 0.5f * tau * warp_sum(gs);
+        if (mine) {
+          const float vr = vbuf[r], wr = fmaf(-gam, vr, pbuf[r]);
+          for (int c = c0 + 2 * h; c < n; c += 4) {     // S -= v w^T + w v^T, w = p - gamma v
+            float2 a = *reinterpret_cast<float2*>(row + c);
+            const float2 v2 = *reinterpret_cast<const float2*>(vbuf + c);
+            const float2 p2 = *reinterpret_cast<const float2*>(pbuf + c);
+            const float w0 = fmaf(-gam, v2.x, p2.x), w1 = fmaf(-gam, v2.y, p2.y);
+            a.x -= fmaf(vr, w0, wr * v2.x);
+            a.y -= fmaf(vr, w1, wr * v2.y);
+            *reinterpret_cast<float2*>(row + c) = a;
+          }
+        }
+      }
+      // the next column in contiguous form, from the thread that owns that element of its row
+      if (r > kk + 1 && r < n && h == (((kk + 1) >> 1) & 1)) xbuf[r] = row[kk + 1];
+      if (tid == 0) xbuf[kk + 1] = 0.f;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      d[n - 2] = A[(size_t)(n - 2) * ld + n - 2];
+      d[n - 1] = A[(size_t)(n - 1) * ld + n - 1];
+      e[n - 2] = A[(size_t)(n - 1) * ld + n - 2];
+    }
+    __syncthreads();
+    for (int i = tid; i + 1 < n; i += NT) e2[i] = e[i] * e[i];
+    __syncthreads();
+  }
+  GCCB_TICK(1);
+  // ---- 2. the k largest eigenvalues of T: multisection on Sturm counts -------------------------------------------
+  {
+    float gl = 3.0e38f, gu = -3.0e38f;                    // Gershgorin interval (every warp)
+    for (int i = lane; i < n; i += 32) {
+      const float rad = (i > 0 ? fabsf(e[i - 1]) : 0.f) + (i + 1 < n ? fabsf(e[i]) : 0.f);
+      gl = fminf(gl, d[i] - rad);
+      gu = fmaxf(gu, d[i] + rad);
+    }
+    gl = -warp_max(-gl); gu = warp_max(gu);
+    { const float pad = 1.0e-5f * fmaxf(fabsf(gl), fabsf(gu)) + 1.0e-6f; gl -= pad; gu += pad; }
+    const float w0 = (gu - gl) / (float)(NT + 1);
+    cnt[tid] = dn_sturm(d, e2, n, gl + (float)(tid + 1) * w0);
+    __syncthreads();
+    if (tid < k) {                                        // eigenvalue number n - k + tid (ascending, 0-based)
+      const int want = n - k + tid + 1;
+      int a = 0, b = NT;                                  // first point whose count reaches `want`
+      while (a < b) { const int mid = (a + b) >> 1; if (cnt[mid] >= want) b = mid; else a = mid + 1; }
+      hi[tid] = a < NT ? gl + (float)(a + 1) * w0 : gu;
+      lo[tid] = a > 0 ? gl + (float)a * w0 : gl;
+    }
+    __syncthreads();
+    constexpr int P = NT / 32;                            // points per eigenvalue and round
+    constexpr int ROUNDS = P >= 16 ? 4 : 6;
+    const int j = tid / P, p = tid % P;
+    const int want = n - k + j + 1;
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      float l = 0.f, wd = 0.f;
+      int ok = 0;
+      if (j < k) {
+        l = lo[j];
+        wd = (hi[j] - l) / (float)(P + 1);
+        ok = dn_sturm(d, e2, n, l + (float)(p + 1) * wd) >= want;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      const unsigned grp = (bal >> (lane & ~(P - 1))) & ((1u << P) - 1u);
+      __syncwarp();
+      if (j < k && p == 0) {
+        const int first = grp ? __ffs((int)grp) - 1 : P;  // first point at or above the eigenvalue
+        if (first < P) hi[j] = l + (float)(first + 1) * wd;
+        if (first > 0) lo[j] = l + (float)first * wd;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (tid < 32) lam[tid] = tid < k ? 0.5f * (lo[tid] + hi[tid]) : 0.f;
+    __syncthreads();
+    if (tid == 0) {                                       // sstein: close eigenvalues are pushed apart
+      lamp[0] = lam[0];
+      for (int c = 1; c < k; ++c) lamp[c] = fmaxf(lam[c], lamp[c - 1] + GCCB_DN_SEP);
+    }
+    // pseudo-random start vectors (counter-based: deterministic), columns >= k stay zero
+    for (int i = tid; i < n * 32; i += NT) {
+      const int r_ = i >> 5, c_ = i & 31;
+      float v = 0.f;
+      if (c_ < k) {
+        u32x4 w = philox4x32_10((uint32_t)i, (uint32_t)n, 0x51ED270Bu, 7u, 0xC0FFEEu, 0x5EEDu);
+        v = (float)(int32_t)w.x * (1.0f / 2147483648.0f);
+      }
+      zrow(r_)[c_] = v;
+    }
+    __syncthreads();
+  }
+  GCCB_TICK(2);
+  // ---- 3. + 4. inverse iteration (lane = eigenvalue) and modified Gram-Schmidt, in two stages ------------------------
+  // Inside a degenerate cluster the iterates are W_j P b_j (P: projector on the eigenspace, W_j: weights 1/(lambda_i -
+  // shift_j) that differ by the fp32 spread of the cluster): independent, but with condition numbers up to ~1e3, and
+  // Gram-Schmidt then amplifies the out-of-cluster contamination of a single-precision solve (eps / gap ~ 1e-4) by
+  // that factor (measured: residual 2.8e-4 on the first member of a 15-fold cluster).  So: two iterations from the
+  // random start, ONE Gram-Schmidt pass, a third iteration from the orthonormal vectors -- it damps the amplified
+  // contamination by (shift distance / gap) ~ 1e-3 and leaves the cluster members nearly orthonormal, because they
+  // all scale by ~1/(shift distance) -- and the final, now well-conditioned, Gram-Schmidt pass.
+  for (int stage = 0; stage < 2; ++stage) {
+  if (warp == 0 && lane < k) {
+    const int j = lane;
+    const float lj = lamp[j];
+    float bscale = 1.0f;
+    const int nit = stage == 0 ? GCCB_DN_INVIT - 1 : 1;
+    for (int it = 0; it < nit; ++it) {
+      // forward elimination with partial pivoting of T - lj I, applied to the right-hand side in place
+      float cd = d[0] - lj, cu = e[0];
+      float bi = zrow(0)[j] * bscale;
+      for (int i = 0; i + 1 < n; ++i) {
+        const float sub = e[i], nd = d[i + 1] - lj, nu = e[i + 1];   // e[n-1] = 0
+        const float bn = zrow(i + 1)[j] * bscale;
+        float s0, s1;
+        if (fabsf(cd) >= fabsf(sub)) {
+          if (fabsf(cd) < GCCB_DN_GUARD) cd = copysignf(GCCB_DN_GUARD, cd);
+          const float m = sub / cd;
+          s0 = cd; s1 = cu;
+          cd = fmaf(-m, cu, nd); cu = nu;
+          zrow(i)[j] = bi;
+          bi = fmaf(-m, bi, bn);
+        } else {                                          // rows swapped: the pivot row is (e[i], d[i+1]-lj, e[i+1])
+          const float m = cd / sub;
+          s0 = 0.f; s1 = 0.f;
+          cd = fmaf(-m, nd, cu); cu = -m * nu;
+          zrow(i)[j] = bn;
+          bi = fmaf(-m, bn, bi);
+        }
+        U0[(size_t)i * 32 + j] = s0;
+        U1[(size_t)i * 32 + j] = s1;
+      }
+      if (fabsf(cd) < GCCB_DN_GUARD) cd = copysignf(GCCB_DN_GUARD, cd);
+      // back substitution, factor rows prefetched one block of four ahead
+      float x1 = bi / cd, x2 = 0.f, mx = fabsf(x1);
+      zrow(n - 1)[j] = x1;
+      float f0[4], f1[4], g0[4], g1[4];
+      int ib = n - 2;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int i = ib - q; f0[q] = i >= 0 ? U0[(size_t)i * 32 + j] : 1.f; f1[q] = i >= 0 ? U1[(size_t)i * 32 + j] : 0.f; }
+      while (ib >= 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int i = ib - 4 - q; g0[q] = i >= 0 ? U0[(size_t)i * 32 + j] : 1.f; g1[q] = i >= 0 ? U1[(size_t)i * 32 + j] : 0.f; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = ib - q;
+          if (i >= 0) {
+            float u0 = f0[q], u1 = f1[q], u2 = 0.f;
+            if (u0 == 0.f) { u0 = e[i]; u1 = d[i + 1] - lj; u2 = e[i + 1]; }
+            const float x = (zrow(i)[j] - u1 * x1 - u2 * x2) / u0;
+            zrow(i)[j] = x;
+            mx = fmaxf(mx, fabsf(x));
+            x2 = x1; x1 = x;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { f0[q] = g0[q]; f1[q] = g1[q]; }
+        ib -= 4;
+      }
+      if (!(mx > 0.f && mx < 3.0e38f)) {                  // overflow / breakdown: never seen; keep a valid vector
+        for (int i = 0; i < n; ++i) zrow(i)[j] = i == (j % n) ? 1.f : 0.f;
+        mx = 1.f;
+        atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
+      }
+      bscale = 1.0f / mx;
+    }
+    for (int i = 0; i < n; ++i) zrow(i)[j] *= bscale;
+  }
+  __syncthreads();
+  DN_DEBUG("invit");
+  GCCB_TICK(3);
+  // modified Gram-Schmidt (right-looking), lanes = columns
+  for (int pass = 0; pass < (stage == 0 ? 1 : GCCB_DN_MGS - 1); ++pass)
+    for (int j = k - 1; j >= 0; --j) {
+      float acc = 0.f;
+      for (int i = warp; i < n; i += NW) { const float* zr = zrow(i); acc = fmaf(zr[j], zr[lane], acc); }
+      part[warp * 32 + lane] = acc;
+      __syncthreads();
+      float dot = 0.f, nn = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { dot += part[w * 32 + lane]; nn += part[w * 32 + j]; }
+      nn = fmaxf(nn, 1.0e-30f);
+      const float inv = 1.0f / sqrtf(nn), coef = dot / nn;
+      for (int i = warp; i < n; i += NW) {
+        float* zr = zrow(i);
+        const float zj = zr[j], zc = zr[lane];
+        __syncwarp();
+        if (lane == j) zr[lane] = zj * inv;
+        else if (lane < j) zr[lane] = fmaf(-coef, zj, zc);
+      }
+      __syncthreads();
+    }
+  DN_DEBUG("mgs");
+  GCCB_TICK(4);
+  }
+  // ---- 5. X = Q Z: all reflectors on this warp's columns, in registers --------------------------------------------
+  {
+    float xr[CPW][NR];
+#pragma unroll
+    for (int t = 0; t < NR; ++t) {
+      const int rr = lane + 32 * t;
+#pragma unroll
+      for (int q = 0; q < CPW; ++q) xr[q][t] = rr < n ? zrow(rr)[warp * CPW + q] : 0.f;
+    }
+    for (int kk = n - 3; kk >= 0; --kk) {
+      const float tau = taus[kk];
+      if (tau == 0.f) continue;
+      float vv[NR];
+#pragma unroll
+      for (int t = 0; t < NR; ++t) {
+        const int rr = lane + 32 * t;
+        vv[t] = (rr > kk && rr < n) ? A[(size_t)rr * ld + kk] : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < CPW; ++q) {
+        float dt = 0.f;
+#pragma unroll
+        for (int t = 0; t < NR; ++t) dt = fmaf(vv[t], xr[q][t], dt);
+        dt = tau * warp_sum(dt);
+#pragma unroll
+        for (int t = 0; t < NR; ++t) xr[q][t] = fmaf(-dt, vv[t], xr[q][t]);
+      }
+    }
+    __syncthreads();                                      // every warp has read its Z columns
+#pragma unroll
+    for (int t = 0; t < NR; ++t) {
+      const int rr = lane + 32 * t;
+      if (rr < n) {
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) zrow(rr)[warp * CPW + q] = xr[q][t];
+      }
+    }
+    __syncthreads();
+  }
+  GCCB_TICK(5);
+  // ---- 6. residuals ||L x - lambda x|| against the sparse matrix -----------------------------------------------------
+  {
+    float acc = 0.f;
+    const float lc = lam[lane];
+    for (int i = warp; i < n; i += NW) {
+      const int beg = v_indptr[noff + i], end = v_indptr[noff + i + 1];
+      float yv = 0.f;
+      for (int ed = beg; ed < end; ++ed) {
+        const int jn = v_indices[ed] - noff;
+        yv = fmaf(dinv[jn], zrow(jn)[lane], yv);
+      }
+      const float rs = fmaf(dinv[i], yv, -lc * zrow(i)[lane]);
+      acc = fmaf(rs, rs, acc);
+    }
+    part[warp * 32 + lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) tot += part[w * 32 + lane];
+      tot = lane < k ? tot : 0.f;
+      tot = sqrtf(warp_max(tot));
+      if (lane == 0) {
+        dbg_iters[slot] = 0; dbg_res[slot] = tot;
+        if (!(tot < GCCB_DN_RES_FLAG)) atomicOr(flags, (int)GCCB_FLAG_EIG_NOCONV);
+        for (int i = 0; i < 8; ++i) dbg_phase[(size_t)slot * 8 + i] = ph[i];
+      }
+    }
+  }
+  // eigsh(which='LA') returns ascending eigenvalues (data_util.py:251): column c <-> lam[c]
+  if (eigvals)
+    for (int c = tid; c < pos_dim; c += NT) eigvals[(size_t)slot * pos_dim + c] = c < k ? lam[c] : 0.f;
+  write_features(n, k, pos_dim, normalize, sgn, out, [&](int c, int r_) { return zrow(r_)[c]; });
+}
+
+template <int NMAX, int NT>
+__global__ void __launch_bounds__(NT, 65536 / 64 / NT)
+posenc_dense_kernel(const int32_t* __restrict__ worklist /* this class */, const int32_t* __restrict__ count,
+                    int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
+                    const int32_t* __restrict__ b_indptr, const int32_t* __restrict__ b_indices,
+                    const int32_t* __restrict__ sub_deg, int pos_dim, int normalize, float* __restrict__ blocks,
+                    float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags,
+                    int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res, long long* __restrict__ dbg_phase) {
+  for (int item = blockIdx.x; item < count[0]; item += gridDim.x) {
+    posenc_dense_item<NMAX, NT>(worklist[item], B, node_cap, edge_cap, node_off, b_indptr, b_indices, sub_deg, pos_dim,
+                                normalize, blocks, pos, eigvals, flags, dbg_iters, dbg_res, dbg_phase);
+    __syncthreads();
+  }
+}
+
 }  // namespace gccb
 
 using namespace gccb;
@@ -1517,7 +1999,17 @@ static size_t posenc_ws_ints(int B) {
 extern "C" size_t gccb_posenc_workspace(int32_t batch, int32_t node_cap) {
   return posenc_ws_ints(batch) * sizeof(int32_t) +
          ((size_t)2 * batch + (size_t)2 * node_cap + (size_t)2 * 2 * node_cap * (GCCB_CF_B + 1)) * sizeof(float) +
-         (size_t)2 * batch * 8 * sizeof(long long) + 64;
+         (size_t)2 * batch * 8 * sizeof(long long) + 64 +
+         ((size_t)3 * 2 * batch + 4) * sizeof(int32_t);        // work lists + counts of the dense solver (tail)
+}
+
+// largest ego-net handed to the dense tridiagonal solver: GCCB200_DENSE_MAX (0 = ChFSI / Jacobi for every size;
+// read on every call so that a test can compare both solvers in one process)
+static int posenc_dense_max() {
+  const char* e = getenv("GCCB200_DENSE_MAX");
+  int v = GCCB_DN_C;
+  if (e && e[0]) v = atoi(e);
+  return v < 0 ? 0 : v > GCCB_DN_C ? GCCB_DN_C : v;
 }
 
 extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t normalize,
@@ -1540,7 +2032,11 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   float* blocks = dinv + (size_t)2 * batch->node_cap;
   // diagnostics tail: per-slot phase cycle counters (8-byte aligned)
   long long* dbg_phase = (long long*)(((uintptr_t)(blocks + (size_t)2 * 2 * batch->node_cap * (GCCB_CF_B + 1)) + 15) & ~(uintptr_t)15);
-  GCCB_LAUNCH(posenc_classify_kernel, 1, 256, 0, stream, batch->counters, batch->node_off, B, worklist, counts);
+  int32_t* dense_list = (int32_t*)(dbg_phase + (size_t)2 * B * 8);
+  int32_t* dense_counts = dense_list + (size_t)3 * 2 * B;
+  const int dense_max = posenc_dense_max();
+  GCCB_LAUNCH(posenc_classify_kernel, 1, 256, 0, stream, batch->counters, batch->node_off, B, worklist, counts,
+              dense_max, GCCB_DN_A, GCCB_DN_B, dense_list, dense_counts);
   auto kgiant = posenc_chfsi_kernel<0, 1024>;
 #ifndef GCCB_EMU
   constexpr int CLUSTER = 8;
@@ -1608,12 +2104,33 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
                 eigvals, batch->flags, dbg_iters, dbg_res, dbg_phase);
 #endif
   }
+  if (dense_max > 0) {
+    // dense classes: n <= 96 (256 threads, 48 KB: four CTAs per SM), n <= 144 (512 threads, 108 KB: two per SM),
+    // n <= 228 (512 threads, 224 KB: one per SM); on the streams of the ChFSI classes they replace
+    auto kd_a = posenc_dense_kernel<GCCB_DN_A, 256>;
+    auto kd_b = posenc_dense_kernel<GCCB_DN_B, 512>;
+    auto kd_c = posenc_dense_kernel<GCCB_DN_C, 512>;
+    const size_t sd_a = (size_t)GCCB_DN_A * dn_ld(GCCB_DN_A) * sizeof(float);
+    const size_t sd_b = (size_t)GCCB_DN_B * dn_ld(GCCB_DN_B) * sizeof(float);
+    const size_t sd_c = (size_t)GCCB_DN_C * dn_ld(GCCB_DN_C) * sizeof(float);
+    gccb::ensure_dyn_smem(kd_a, sd_a);
+    gccb::ensure_dyn_smem(kd_b, sd_b);
+    gccb::ensure_dyn_smem(kd_c, sd_c);
+#define GCCB_DN_ARGS(c) dense_list + (size_t)(c) * 2 * B, dense_counts + (c), B, batch->node_cap, batch->edge_cap, \
+    batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, pos, eigvals, \
+    batch->flags, dbg_iters, dbg_res, dbg_phase
+    GCCB_LAUNCH(kd_c, capped(GCCB_CAP_DN_C), 512, sd_c, s_big, GCCB_DN_ARGS(2));
+    GCCB_LAUNCH(kd_b, capped(GCCB_CAP_DN_B), 512, sd_b, s_mid2, GCCB_DN_ARGS(1));
+    GCCB_LAUNCH(kd_a, capped(GCCB_CAP_DN_A), 256, sd_a, s_mid1, GCCB_DN_ARGS(0));
+  }
   GCCB_LAUNCH(kbig, capped(148), GCCB_BIG_NT, s_c, s_big, GCCB_PE_ARGS(3));
-  GCCB_LAUNCH(kmid, capped(GCCB_CAP_MID2), 256, s_b, s_mid2, GCCB_PE_ARGS(2));
-  GCCB_LAUNCH(kmid, capped(GCCB_CAP_MID1), 256, s_a, s_mid1, GCCB_PE_ARGS(1));
-  GCCB_LAUNCH(ksmall, capped(148), 256, 0, s_small, worklist, counts, B, batch->node_cap, batch->edge_cap,
-              batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, pos, eigvals,
-              batch->flags, dbg_iters, dbg_res);
+  // classes the dense solver covers completely have empty lists: not launched
+  if (dense_max < GCCB_CF_NSM) GCCB_LAUNCH(kmid, capped(GCCB_CAP_MID2), 256, s_b, s_mid2, GCCB_PE_ARGS(2));
+  if (dense_max < GCCB_CF_NSM_A) GCCB_LAUNCH(kmid, capped(GCCB_CAP_MID1), 256, s_a, s_mid1, GCCB_PE_ARGS(1));
+  if (dense_max < GCCB_EIG_SMALL)
+    GCCB_LAUNCH(ksmall, capped(148), 256, 0, s_small, worklist, counts, B, batch->node_cap, batch->edge_cap,
+                batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, pos, eigvals,
+                batch->flags, dbg_iters, dbg_res);
 #ifndef GCCB_EMU
   for (int i = 0; i < 5; ++i) {
     cudaEventRecord(ev_join[i], side[i]);

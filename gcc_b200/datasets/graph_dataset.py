@@ -133,7 +133,8 @@ class BatchBuffers:
     def eig_debug(self):
         """(iterations, worst residual) per ego-net of the last gccb_posenc on these buffers, read
         from the debug area of its workspace (posenc.cu: worklist[7][2B] | counts[7] | iters[2B] |
-        pad to 64 ints | res[2B]).  Direct-Jacobi ego-nets report minus their sweep count."""
+        pad to 64 ints | res[2B]).  Direct-Jacobi ego-nets report minus their sweep count, ego-nets solved by
+        the dense tridiagonal solver (a direct method) report 0 iterations and their measured residual."""
         B, NC = self.B, 7
         ints = self.ws_posenc.view(torch.int32)
         o = NC * 2 * B + NC

@@ -1,6 +1,10 @@
-"""CPU: eigensolver kernel (gcc_b200/csrc/posenc.cu) under the fiber emulator --
+"""CPU: eigensolver kernels (gcc_b200/csrc/posenc.cu) under the fiber emulator --
 spectral parity with the oracle (dense float64 eigh) and with the reference's own
-outputs (tests/golden/posenc_golden.npz).  Kernel LOGIC only; see test_gpu_*."""
+outputs (tests/golden/posenc_golden.npz).  Kernel LOGIC only; see test_gpu_*.
+
+Two solver families share the size range n <= 228: the dense tridiagonal solver (default) and the
+Jacobi / Chebyshev-filtered subspace iteration classes (GCCB200_DENSE_MAX=0, read by gccb_posenc on every
+call); the `solver` fixture runs every test through both."""
 import ctypes as C
 import os
 
@@ -12,6 +16,15 @@ from gcc_b200.datasets import synthetic
 from oracle import posenc as opos
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(params=["dense", "iterative"])
+def solver(request, monkeypatch):
+    if request.param == "iterative":
+        monkeypatch.setenv("GCCB200_DENSE_MAX", "0")
+    else:
+        monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    return request.param
 
 
 def _sub(g):
@@ -46,7 +59,7 @@ def _check_spectral(sub, u, lam):
     assert np.allclose(theta, w_exact, atol=1e-5)
 
 
-def test_jacobi_spectral_parity_small_and_degenerate():
+def test_jacobi_spectral_parity_small_and_degenerate(solver):
     graphs = [synthetic.path_graph(2), synthetic.path_graph(3), synthetic.path_graph(9),
               synthetic.star_graph(20), synthetic.triangle_tail(4),
               synthetic.erdos_renyi(40, 90, seed=1), synthetic.star_graph(50),
@@ -61,7 +74,7 @@ def test_jacobi_spectral_parity_small_and_degenerate():
             _check_spectral(sub, pos[v, a:z], eig[v * b.B + gi])
 
 
-def test_jacobi_size_classes_and_normalisation():
+def test_jacobi_size_classes_and_normalisation(solver):
     g1 = synthetic.erdos_renyi(90, 240, seed=7)           # 64 < n <= 96: Chebyshev-filtered subspace iteration
     g2 = synthetic.star_graph(90)                         # extreme degeneracy (eigenvalue 0 x 89)
     g3 = synthetic.erdos_renyi(150, 420, seed=9)          # 96 < n <= 160: second shared-memory class
@@ -82,7 +95,7 @@ def test_jacobi_size_classes_and_normalisation():
         assert np.allclose(posn[v, :n], want, atol=1e-6)
 
 
-def test_posenc_matches_reference_golden():
+def test_posenc_matches_reference_golden(solver):
     z = np.load(os.path.join(G, "posenc_golden.npz"))
     subs = []
     for ci in range(int(z["num_cases"])):
@@ -120,7 +133,7 @@ def test_huge_egonet_one_block_in_shared_memory():
     _check_spectral(views[0][0], pos[0, :g.num_nodes], eig[0])
 
 
-def test_large_egonet_goes_through_chfsi():
+def test_large_egonet_goes_through_chfsi(solver):
     g = synthetic.chung_lu(260, 700, seed=3)              # hub-and-leaves: large degenerate cluster
     assert g.num_nodes > 200
     views = [[_sub(g)], [_sub(synthetic.path_graph(5))]]
@@ -128,3 +141,54 @@ def test_large_egonet_goes_through_chfsi():
     assert b.flags[0] == 0
     _check_spectral(views[0][0], pos[0, :g.num_nodes], eig[0])
     _check_spectral(views[1][0], pos[1, :5], eig[1])
+
+
+def test_dense_solver_class_boundaries_and_degenerate_spectra(monkeypatch):
+    """The dense tridiagonal solver at the edges of its three classes (96 / 144 / 228), on the smallest ego-nets
+    (k = 1, 2, 3), on exactly degenerate spectra (stars: eigenvalue 0 x 199; a disconnected union) and on paths
+    (the matrix is already tridiagonal: every reflector is the identity); tighter bars than the shared ones --
+    the fp32 model of the kernel measures eigenvalues to 5e-7 and residuals / orthonormality to 4e-6."""
+    monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    graphs = [synthetic.path_graph(3), synthetic.path_graph(4), synthetic.path_graph(5), synthetic.star_graph(33),
+              synthetic.path_graph(96), synthetic.chung_lu(100, 250, seed=1), synthetic.chung_lu(150, 400, seed=2),
+              synthetic.chung_lu(156, 420, seed=3), synthetic.path_graph(228), synthetic.star_graph(200),
+              synthetic.disjoint_union([synthetic.star_graph(30), synthetic.star_graph(30), synthetic.path_graph(20)]),
+              synthetic.erdos_renyi(228, 2000, seed=3), synthetic.chung_lu(240, 640, exponent=0.8, seed=5),
+              synthetic.erdos_renyi(34, 60, seed=2)]
+    sizes = [g.num_nodes for g in graphs]
+    assert max(sizes) <= 228 and any(96 < n <= 144 for n in sizes) and any(144 < n for n in sizes), sizes
+    half = len(graphs) // 2
+    views = [[_sub(g) for g in graphs[:half]], [_sub(g) for g in graphs[half:]]]
+    b, pos, eig = _posenc(views, normalize=0)
+    assert b.flags[0] == 0
+    for v in (0, 1):
+        for gi, sub in enumerate(views[v]):
+            a, z = b.node_off[v, gi], b.node_off[v, gi + 1]
+            u, lam = pos[v, a:z], eig[v * b.B + gi]
+            _check_spectral(sub, u, lam)
+            n = sub["n"]
+            k = min(n - 2, 32)
+            lap = opos.normalized_adjacency(sub["indptr"], sub["indices"], n).toarray()
+            w_exact, _ = opos.eig_topk_exact(lap, k)
+            theta, resid, ortho = opos.spectral_report(lap, u[:, :k].astype(np.float64))
+            assert np.abs(lam[:k] - w_exact).max() < 2e-6 and resid.max() < 2e-5 and ortho < 2e-5, (
+                n, np.abs(lam[:k] - w_exact).max(), resid.max(), ortho)
+
+
+def test_dense_solver_fifteen_fold_cluster_regression(monkeypatch):
+    """A sampled C2 ego-net (n = 173) whose 15-fold eigenvalue 1/sqrt 2 made the first cluster member come out of
+    Gram-Schmidt with a residual of 2.8e-4 when all inverse iterations ran before the orthogonalisation (the
+    iterates of a cluster get more collinear with every iteration); with the two-stage order it is 4e-7."""
+    monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    z = np.load(os.path.join(G, "egonet_cluster15.npz"))
+    ip, ix = z["indptr"].astype(np.int32), z["indices"].astype(np.int32)
+    n = len(ip) - 1
+    sub = dict(subv=np.arange(n, dtype=np.int32), indptr=ip, indices=ix, n=n, m=len(ix))
+    views = [[sub], [_sub(synthetic.path_graph(5))]]
+    b, pos, eig = _posenc(views, normalize=0)
+    assert b.flags[0] == 0
+    lap = opos.normalized_adjacency(ip, ix, n).toarray()
+    w = np.linalg.eigvalsh(lap)
+    assert np.sum(np.abs(w - 2 ** -0.5) < 1e-9) == 15
+    theta, resid, ortho = opos.spectral_report(lap, pos[0, :n, :32].astype(np.float64))
+    assert resid.max() < 2e-5 and ortho < 2e-5, (resid.max(), ortho)

@@ -25,6 +25,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 #   Inside that cluster (spread up to ~1e-3) WHICH members make the top-32 cut is not resolved either, so the
 #   eigenvalue bar for n > 160 is the cluster spread, 1e-3 (2e-5 everywhere else).
 RES_SMALL, RES_HUB, HUB_N, LAM_SMALL, LAM_HUB = 1e-4, 2.5e-3, 160, 2e-5, 1e-3
+# The dense tridiagonal solver (default for n <= 228; posenc.cu solver (0)) is a direct method: eigenvalues to 2e-6,
+# residuals and orthonormality to 2e-5 (measured on the fp32 model: 5e-7 / 4e-6 / 3e-6), hub-like ego-nets included.
+DENSE_N, RES_DENSE, LAM_DENSE = 228, 2e-5, 2e-6
+
+
+@pytest.fixture(params=["dense", "iterative"])
+def solver(request, monkeypatch):
+    """gccb_posenc reads GCCB200_DENSE_MAX on every call: 0 sends every size to the Jacobi / ChFSI classes."""
+    if request.param == "iterative":
+        monkeypatch.setenv("GCCB200_DENSE_MAX", "0")
+    else:
+        monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    return request.param
+
+
+def _bars(n, solver):
+    if solver == "dense" and n <= DENSE_N:
+        return RES_DENSE, LAM_DENSE
+    return (RES_HUB, LAM_HUB) if n > HUB_N else (RES_SMALL, LAM_SMALL)
 
 
 def _spectral(sub, u, lam, res_bar, tol_l):
@@ -52,9 +71,10 @@ def _posenc_raw(buf):
     return buf.pos.cpu().numpy().copy(), buf.eigvals.cpu().numpy().copy()
 
 
-def test_eigensolver_every_size_class():
+def test_eigensolver_every_size_class(solver):
     """One explicit ego-net per solver class: dense Jacobi (n 40), shared-memory ChFSI (90, 150, 300),
-    cluster ChFSI with 192- and 448-row slabs (520, 1500, 3300) and a 700-vertex star (eigenvalue 0 x 698)."""
+    cluster ChFSI with 192- and 448-row slabs (520, 1500, 3300) and a 700-vertex star (eigenvalue 0 x 698);
+    with the dense solver on, the first three go through its three classes (n <= 96 / 144 / 228)."""
     from gcc_b200.datasets import synthetic
     from gcc_b200.datasets.graph_dataset import BatchBuffers
     graphs = [synthetic.erdos_renyi(40, 90, seed=1), synthetic.chung_lu(95, 250, seed=2),
@@ -78,10 +98,47 @@ def test_eigensolver_every_size_class():
     report = []
     for i, s in enumerate(subs):
         v, gi = divmod(i, B)
-        bar = RES_SMALL if s["n"] <= HUB_N else RES_HUB
-        r, o = _spectral(s, raw[v, noff[v, gi]:noff[v, gi + 1]], eig[v * B + gi], bar, LAM_HUB if s["n"] > HUB_N else LAM_SMALL)
+        bar, lbar = _bars(s["n"], solver)
+        r, o = _spectral(s, raw[v, noff[v, gi]:noff[v, gi + 1]], eig[v * B + gi], bar, lbar)
         report.append((s["n"], int(it[v * B + gi]), r))
-    print("eigensolver classes (n, iterations, max residual):", report)
+    print("eigensolver classes [%s] (n, iterations, max residual):" % solver, report)
+
+
+def test_dense_eigensolver_class_boundaries(monkeypatch):
+    """The dense tridiagonal solver at the edges of its classes (96 / 144 / 228), on exactly degenerate spectra
+    (a 200-leaf star, a disconnected union), on paths (already tridiagonal), on k = 1..3, and on the sampled
+    ego-net with a 15-fold eigenvalue (tests/golden/egonet_cluster15.npz)."""
+    monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    from gcc_b200.datasets import synthetic
+    from gcc_b200.datasets.graph_dataset import BatchBuffers
+    graphs = [synthetic.path_graph(3), synthetic.path_graph(4), synthetic.path_graph(5), synthetic.star_graph(33),
+              synthetic.path_graph(96), synthetic.chung_lu(100, 250, seed=1), synthetic.chung_lu(150, 400, seed=2),
+              synthetic.chung_lu(156, 420, seed=3), synthetic.path_graph(228), synthetic.star_graph(200),
+              synthetic.disjoint_union([synthetic.star_graph(30), synthetic.star_graph(30), synthetic.path_graph(20)]),
+              synthetic.erdos_renyi(228, 2000, seed=3), synthetic.chung_lu(240, 640, exponent=0.8, seed=5)]
+    subs = [dict(indptr=g.indptr.astype(np.int32), indices=g.indices.astype(np.int32), n=g.num_nodes) for g in graphs]
+    z = np.load(os.path.join(ROOT, "tests", "golden", "egonet_cluster15.npz"))
+    subs.append(dict(indptr=z["indptr"].astype(np.int32), indices=z["indices"].astype(np.int32), n=len(z["indptr"]) - 1))
+    assert max(s["n"] for s in subs) <= DENSE_N
+    B = len(subs) // 2
+    views = [subs[:B], subs[B:]]
+    N = max(sum(s["n"] for s in v) for v in views)
+    E = max(sum(len(s["indices"]) for s in v) for v in views)
+    buf = BatchBuffers(B, N + 8, E + 8, 32, 64, "cuda")
+    _fill_batch(buf, views)
+    raw, eig = _posenc_raw(buf)
+    assert int(buf.flags.item()) == 0
+    noff = buf.node_off.cpu().numpy()
+    it, res = buf.eig_debug()
+    worst = 0.0
+    for i, s in enumerate(subs):
+        v, gi = divmod(i, B)
+        r, o = _spectral(s, raw[v, noff[v, gi]:noff[v, gi + 1]], eig[v * B + gi], RES_DENSE, LAM_DENSE)
+        assert o < 2e-5, (s["n"], o)
+        worst = max(worst, r)
+    print("dense eigensolver: worst residual %.2e (fp64 re-evaluation), kernel-side %.2e" % (worst, float(res.max())))
+    raw2, eig2 = _posenc_raw(buf)                          # deterministic run to run
+    assert np.array_equal(raw, raw2) and np.array_equal(eig, eig2)
 
 
 @pytest.fixture(scope="module")
@@ -125,7 +182,7 @@ def test_c2_batch_sampler_bit_exact(c2_batch):
     assert max(sizes) > 384                                # a hub ego-net (cluster eigensolver class) is present
 
 
-def test_c2_batch_posenc_spectral_every_egonet(c2_batch):
+def test_c2_batch_posenc_spectral_every_egonet(c2_batch, solver):
     """Spectral parity of ALL 512 ego-nets of the batch, with the residual bar of each solver class."""
     buf, B = c2_batch["buf"], c2_batch["B"]
     raw, eig = _posenc_raw(buf)
@@ -139,16 +196,17 @@ def test_c2_batch_posenc_spectral_every_egonet(c2_batch):
     for v in (0, 1):
         for gi, s in enumerate(_split(buf, v)):
             hub = s["n"] > HUB_N
-            r, _ = _spectral(s, raw[v, noff[v, gi]:noff[v, gi + 1]], eig[v * B + gi], RES_HUB if hub else RES_SMALL,
-                             LAM_HUB if hub else LAM_SMALL)
+            bar, lbar = _bars(s["n"], solver)
+            r, _ = _spectral(s, raw[v, noff[v, gi]:noff[v, gi + 1]], eig[v * B + gi], bar, lbar)
             if hub:
                 worst_hub, nhub = max(worst_hub, r), nhub + 1
             else:
                 worst_small = max(worst_small, r)
     ch = it > 0
-    print("C2 batch eigensolver: NOCONV flag %d; ChFSI iterations mean %.2f max %d; worst residual n<=160: %.2e, "
-          "n>160 (%d): %.2e; kernel-side residual max %.2e" % (
-              (flags >> 3) & 1, it[ch].mean(), it.max(), worst_small, nhub, worst_hub, res.max()))
+    print("C2 batch eigensolver [%s]: NOCONV flag %d; ChFSI ego-nets %d, iterations mean %.2f max %d; worst residual "
+          "n<=160: %.2e, n>160 (%d): %.2e; kernel-side residual max %.2e" % (
+              solver, (flags >> 3) & 1, int(ch.sum()), it[ch].mean() if ch.any() else 0.0, it.max(), worst_small, nhub,
+              worst_hub, res.max()))
 
 
 def test_c2_batch_engine_step_matches_oracle(c2_batch):
