@@ -1535,8 +1535,8 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
 // test graphs: eigenvalues to 4e-7, residuals to 5e-6, orthonormality to 1e-6, the reference's own simple-spectrum
 // goldens elementwise to 2e-6; ChFSI: 2e-5 / 4e-5 / 1e-4):
 //
-//   1. Householder tridiagonalisation Q^T L Q = T, unblocked, full symmetric storage (row stride = 4 mod 32, two
-//      threads per row reading 64-bit words: conflict-free), TWO barriers per column: the product S v is taken
+//   1. Householder tridiagonalisation Q^T L Q = T, unblocked, full symmetric storage (row stride = 8 mod 32, two
+//      threads per row reading 128-bit words: conflict-free), TWO barriers per column: the product S v is taken
 //      from the raw column x (v = scale * (x - beta e1), so S v = scale * (S x - beta S e1)) and overlaps the
 //      norm of x, every warp computes the scalars redundantly, w = p - gamma v is formed on the fly inside the
 //      rank-2 update, and the update hands the next column over in contiguous form;
@@ -1545,7 +1545,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
 //   3. eigenvectors of T by inverse iteration, one lane per eigenvalue (Gaussian elimination with partial
 //      pivoting; pivot rows that were swapped are original matrix entries, so two floats per row describe the
 //      factor -- kept in the L2-resident workspace, written coalesced, read back with one block prefetched), three
-//      iterations from a counter-based pseudo-random start, close eigenvalues separated by 6e-7 like LAPACK's sstein;
+//      iterations from a counter-based pseudo-random start, ONE common shift per multiple eigenvalue (see there);
 //   4. modified Gram-Schmidt over the k vectors (lanes = columns: conflict-free; degenerate clusters -- the null
 //      space of a near-tree reaches multiplicity 30+ -- come out as an orthonormal basis), one pass after the second
 //      and one after the third inverse iteration (see the comment at the loop);
@@ -1561,11 +1561,13 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
 #define GCCB_DN_INVIT 3
 #endif
 #ifndef GCCB_DN_MGS
-#define GCCB_DN_MGS 2
+#define GCCB_DN_MGS 1              // Gram-Schmidt passes after the LAST inverse iteration (one after each earlier one)
 #endif
 #define GCCB_DN_PIVMIN 1.0e-30f
 #define GCCB_DN_GUARD 1.0e-9f      // smallest pivot of the inverse iteration (a perturbation far below eps * ||T||)
-#define GCCB_DN_SEP 6.0e-7f        // separation forced between close eigenvalues before the inverse iteration
+#define GCCB_DN_TIGHT 2.0e-6f      // eigenvalues closer than this form a group with one common shift ...
+#define GCCB_DN_DELTA 4.0e-6f      // ... this far outside the group
+#define GCCB_DN_GAPTOL 1.0e-2f     // Gram-Schmidt links eigenvalues closer than this
 #define GCCB_DN_RES_FLAG 1.0e-3f
 
 
@@ -1578,7 +1580,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
 #else
 #define DN_DEBUG(tag)
 #endif
-__host__ __device__ constexpr int dn_ld(int n) { return ((n + 27) / 32) * 32 + 4; }
+__host__ __device__ constexpr int dn_ld(int n) { return ((n + 23) / 32) * 32 + 8; }   // >= n, = 8 mod 32
 
 // number of eigenvalues of T below x
 __device__ __forceinline__ int dn_sturm(const float* __restrict__ d, const float* __restrict__ e2, int n, float x) {
@@ -1603,7 +1605,7 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
   constexpr int NW = NT / 32, NP = ((NMAX + 3) & ~3) + 4, NR = (NMAX + 31) / 32, CPW = 32 / NW;
   static_assert(NT >= 2 * NMAX && NW <= 32 && 32 % NW == 0, "two threads per matrix row");
   GCCB_DYN_SMEM(float, A);                              // n x ld, row-major
-  // (64-bit accesses to vbuf / pbuf / xbuf: every array gets its own aligned declaration)
+  // (128-bit accesses to vbuf / pbuf / xbuf: every array gets its own aligned declaration)
   __align__(16) __shared__ float d[NP];
   __align__(16) __shared__ float e[NP];
   __align__(16) __shared__ float e2[NP];
@@ -1672,11 +1674,13 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
       float y = 0.f;
       if (mine) {                                       // y = (S x)_r over this thread's half of the row
         float y0 = 0.f, y1 = 0.f;
-        for (int c = c0 + 2 * h; c < n; c += 4) {
-          const float2 a = *reinterpret_cast<const float2*>(row + c);
-          const float2 x = *reinterpret_cast<const float2*>(xbuf + c);
+        for (int c = c0 + 4 * h; c < n; c += 8) {
+          const float4 a = *reinterpret_cast<const float4*>(row + c);
+          const float4 x = *reinterpret_cast<const float4*>(xbuf + c);
           y0 = fmaf(a.x, x.x, y0);
           y1 = fmaf(a.y, x.y, y1);
+          y0 = fmaf(a.z, x.z, y0);
+          y1 = fmaf(a.w, x.w, y1);
         }
         y = y0 + y1;
       }
@@ -1706,19 +1710,21 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
         const float gam = 0.5f * tau * warp_sum(gs);
         if (mine) {
           const float vr = vbuf[r], wr = fmaf(-gam, vr, pbuf[r]);
-          for (int c = c0 + 2 * h; c < n; c += 4) {     // S -= v w^T + w v^T, w = p - gamma v
-            float2 a = *reinterpret_cast<float2*>(row + c);
-            const float2 v2 = *reinterpret_cast<const float2*>(vbuf + c);
-            const float2 p2 = *reinterpret_cast<const float2*>(pbuf + c);
-            const float w0 = fmaf(-gam, v2.x, p2.x), w1 = fmaf(-gam, v2.y, p2.y);
-            a.x -= fmaf(vr, w0, wr * v2.x);
-            a.y -= fmaf(vr, w1, wr * v2.y);
-            *reinterpret_cast<float2*>(row + c) = a;
+          const float nvr = -vr, nwr = -wr;
+          for (int c = c0 + 4 * h; c < n; c += 8) {     // S -= v w^T + w v^T, w = p - gamma v
+            float4 a = *reinterpret_cast<float4*>(row + c);
+            const float4 v4 = *reinterpret_cast<const float4*>(vbuf + c);
+            const float4 p4 = *reinterpret_cast<const float4*>(pbuf + c);
+            a.x = fmaf(nwr, v4.x, fmaf(nvr, fmaf(-gam, v4.x, p4.x), a.x));
+            a.y = fmaf(nwr, v4.y, fmaf(nvr, fmaf(-gam, v4.y, p4.y), a.y));
+            a.z = fmaf(nwr, v4.z, fmaf(nvr, fmaf(-gam, v4.z, p4.z), a.z));
+            a.w = fmaf(nwr, v4.w, fmaf(nvr, fmaf(-gam, v4.w, p4.w), a.w));
+            *reinterpret_cast<float4*>(row + c) = a;
           }
         }
       }
       // the next column in contiguous form, from the thread that owns that element of its row
-      if (r > kk + 1 && r < n && h == (((kk + 1) >> 1) & 1)) xbuf[r] = row[kk + 1];
+      if (r > kk + 1 && r < n && h == 0) xbuf[r] = row[kk + 1];   // column kk+1 is in the first 4-column chunk
       if (tid == 0) xbuf[kk + 1] = 0.f;
       __syncthreads();
     }
@@ -1778,9 +1784,32 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
     __syncthreads();
     if (tid < 32) lam[tid] = tid < k ? 0.5f * (lo[tid] + hi[tid]) : 0.f;
     __syncthreads();
-    if (tid == 0) {                                       // sstein: close eigenvalues are pushed apart
-      lamp[0] = lam[0];
-      for (int c = 1; c < k; ++c) lamp[c] = fmaxf(lam[c], lamp[c - 1] + GCCB_DN_SEP);
+    if (tid == 0) {
+      // Shifts of the inverse iteration.  An eigenvalue resolved from its neighbours (spacing >= GCCB_DN_TIGHT) is its
+      // own shift.  A tight group (multiple eigenvalue: the members of T differ by the rounding of the reduction,
+      // ~3e-7) shares ONE shift, GCCB_DN_DELTA outside the group on the side of the wider gap: every member of the
+      // group's eigenspace is then amplified by the same factor (+-10 %), so the iterates stay as independent as their
+      // start vectors (random: condition ~50; orthonormal after the first Gram-Schmidt pass: ~1.1) and Gram-Schmidt
+      // does not amplify the out-of-group contamination of a single-precision solve.  With LAPACK's recipe (sstein:
+      // members pushed 10 eps apart) the members whose shifts end up on the same side of the group converge to the
+      // same eigenvector, the set degenerates (condition 1e3) and the last member that Gram-Schmidt reaches came out
+      // with residuals up to 3e-4 (measured on sampled ego-nets, 15-fold and 4-fold eigenvalues).
+      int c = 0;
+      while (c < k) {
+        int ce = c;
+        while (ce + 1 < k && lam[ce + 1] - lam[ce] < GCCB_DN_TIGHT) ++ce;
+        if (ce > c) {
+          const float below = c > 0 ? lam[c] - lam[c - 1] : 0.f;        // the next eigenvalue below lam[0] is unknown
+          const float above = ce + 1 < k ? lam[ce + 1] - lam[ce] : 1.0f;  // nothing above the largest one
+          const bool up = above >= below;
+          const float dl = fminf(GCCB_DN_DELTA, (up ? above : below) * (1.0f / 3.0f));
+          const float sh = up ? lam[ce] + dl : lam[c] - dl;
+          for (int q = c; q <= ce; ++q) lamp[q] = sh;
+        } else {
+          lamp[c] = lam[c];
+        }
+        c = ce + 1;
+      }
     }
     // pseudo-random start vectors (counter-based: deterministic), columns >= k stay zero
     for (int i = tid; i < n * 32; i += NT) {
@@ -1796,13 +1825,10 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
   }
   GCCB_TICK(2);
   // ---- 3. + 4. inverse iteration (lane = eigenvalue) and modified Gram-Schmidt, in two stages ------------------------
-  // Inside a degenerate cluster the iterates are W_j P b_j (P: projector on the eigenspace, W_j: weights 1/(lambda_i -
-  // shift_j) that differ by the fp32 spread of the cluster): independent, but with condition numbers up to ~1e3, and
-  // Gram-Schmidt then amplifies the out-of-cluster contamination of a single-precision solve (eps / gap ~ 1e-4) by
-  // that factor (measured: residual 2.8e-4 on the first member of a 15-fold cluster).  So: two iterations from the
-  // random start, ONE Gram-Schmidt pass, a third iteration from the orthonormal vectors -- it damps the amplified
-  // contamination by (shift distance / gap) ~ 1e-3 and leaves the cluster members nearly orthonormal, because they
-  // all scale by ~1/(shift distance) -- and the final, now well-conditioned, Gram-Schmidt pass.
+  // Two iterations from the random start, ONE Gram-Schmidt pass (the group iterates are projections of random vectors:
+  // condition ~50, so the pass amplifies the out-of-group contamination of the solve, eps / gap ~ 1e-4, to ~1e-2), a
+  // third iteration from the orthonormal vectors -- it damps that contamination by (shift distance / gap) ~ 1e-3 and,
+  // with the common shift, leaves the group members orthonormal to ~10 % -- and the final, well-conditioned pass.
   for (int stage = 0; stage < 2; ++stage) {
   if (warp == 0 && lane < k) {
     const int j = lane;
@@ -1819,8 +1845,9 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
         float s0, s1;
         if (fabsf(cd) >= fabsf(sub)) {
           if (fabsf(cd) < GCCB_DN_GUARD) cd = copysignf(GCCB_DN_GUARD, cd);
-          const float m = sub / cd;
-          s0 = cd; s1 = cu;
+          const float rinv = __fdividef(1.0f, cd);        // kept for the back substitution (never 0: |cd| < 4)
+          const float m = sub * rinv;
+          s0 = rinv; s1 = cu;
           cd = fmaf(-m, cu, nd); cu = nu;
           zrow(i)[j] = bi;
           bi = fmaf(-m, bi, bn);
@@ -1849,9 +1876,9 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
         for (int q = 0; q < 4; ++q) {
           const int i = ib - q;
           if (i >= 0) {
-            float u0 = f0[q], u1 = f1[q], u2 = 0.f;
-            if (u0 == 0.f) { u0 = e[i]; u1 = d[i + 1] - lj; u2 = e[i + 1]; }
-            const float x = (zrow(i)[j] - u1 * x1 - u2 * x2) / u0;
+            float ri = f0[q], u1 = f1[q], u2 = 0.f;
+            if (ri == 0.f) { ri = __fdividef(1.0f, e[i]); u1 = d[i + 1] - lj; u2 = e[i + 1]; }
+            const float x = (zrow(i)[j] - u1 * x1 - u2 * x2) * ri;
             zrow(i)[j] = x;
             mx = fmaxf(mx, fabsf(x));
             x2 = x1; x1 = x;
@@ -1873,9 +1900,12 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
   __syncthreads();
   DN_DEBUG("invit");
   GCCB_TICK(3);
-  // modified Gram-Schmidt (right-looking), lanes = columns
-  for (int pass = 0; pass < (stage == 0 ? 1 : GCCB_DN_MGS - 1); ++pass)
-    for (int j = k - 1; j >= 0; --j) {
+  // modified Gram-Schmidt (right-looking), lanes = columns.  Step j removes z_j from the columns below it; it is
+  // needed only when eigenvalue j has a lower neighbour within GCCB_DN_GAPTOL (eigenvectors of T further apart come
+  // out of the inverse iteration orthogonal to eps / gap < 1e-5).  Columns are normalised once, at the very end.
+  for (int pass = 0; pass < (stage == 0 ? 1 : GCCB_DN_MGS); ++pass)
+    for (int j = k - 1; j >= 1; --j) {
+      if (!(lam[j] - lam[j - 1] < GCCB_DN_GAPTOL)) continue;
       float acc = 0.f;
       for (int i = warp; i < n; i += NW) { const float* zr = zrow(i); acc = fmaf(zr[j], zr[lane], acc); }
       part[warp * 32 + lane] = acc;
@@ -1883,17 +1913,23 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
       float dot = 0.f, nn = 0.f;
 #pragma unroll
       for (int w = 0; w < NW; ++w) { dot += part[w * 32 + lane]; nn += part[w * 32 + j]; }
-      nn = fmaxf(nn, 1.0e-30f);
-      const float inv = 1.0f / sqrtf(nn), coef = dot / nn;
-      for (int i = warp; i < n; i += NW) {
-        float* zr = zrow(i);
-        const float zj = zr[j], zc = zr[lane];
-        __syncwarp();
-        if (lane == j) zr[lane] = zj * inv;
-        else if (lane < j) zr[lane] = fmaf(-coef, zj, zc);
-      }
+      const float coef = dot / fmaxf(nn, 1.0e-30f);
+      if (lane < j)
+        for (int i = warp; i < n; i += NW) { float* zr = zrow(i); zr[lane] = fmaf(-coef, zr[j], zr[lane]); }
       __syncthreads();
     }
+  if (stage == 1) {                                       // unit columns
+    float acc = 0.f;
+    for (int i = warp; i < n; i += NW) { const float t = zrow(i)[lane]; acc = fmaf(t, t, acc); }
+    part[warp * 32 + lane] = acc;
+    __syncthreads();
+    float nn = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) nn += part[w * 32 + lane];
+    const float inv = 1.0f / sqrtf(fmaxf(nn, 1.0e-30f));
+    for (int i = warp; i < n; i += NW) zrow(i)[lane] *= inv;
+    __syncthreads();
+  }
   DN_DEBUG("mgs");
   GCCB_TICK(4);
   }
@@ -2119,9 +2155,11 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
 #define GCCB_DN_ARGS(c) dense_list + (size_t)(c) * 2 * B, dense_counts + (c), B, batch->node_cap, batch->edge_cap, \
     batch->node_off, batch->indptr, batch->indices, batch->sub_deg, pos_dim, normalize, blocks, pos, eigvals, \
     batch->flags, dbg_iters, dbg_res, dbg_phase
-    GCCB_LAUNCH(kd_c, capped(GCCB_CAP_DN_C), 512, sd_c, s_big, GCCB_DN_ARGS(2));
-    GCCB_LAUNCH(kd_b, capped(GCCB_CAP_DN_B), 512, sd_b, s_mid2, GCCB_DN_ARGS(1));
-    GCCB_LAUNCH(kd_a, capped(GCCB_CAP_DN_A), 256, sd_a, s_mid1, GCCB_DN_ARGS(0));
+    // (diagnostics: GCCB200_DN_CAP_A / _B / _C override the persistent grid sizes, i.e. the CTAs per SM)
+    auto env_cap = [](const char* name, int dflt) { const char* e = getenv(name); const int v = e && e[0] ? atoi(e) : dflt; return v > 0 ? v : dflt; };
+    GCCB_LAUNCH(kd_c, capped(env_cap("GCCB200_DN_CAP_C", GCCB_CAP_DN_C)), 512, sd_c, s_big, GCCB_DN_ARGS(2));
+    GCCB_LAUNCH(kd_b, capped(env_cap("GCCB200_DN_CAP_B", GCCB_CAP_DN_B)), 512, sd_b, s_mid2, GCCB_DN_ARGS(1));
+    GCCB_LAUNCH(kd_a, capped(env_cap("GCCB200_DN_CAP_A", GCCB_CAP_DN_A)), 256, sd_a, s_mid1, GCCB_DN_ARGS(0));
   }
   GCCB_LAUNCH(kbig, capped(148), GCCB_BIG_NT, s_c, s_big, GCCB_PE_ARGS(3));
   // classes the dense solver covers completely have empty lists: not launched
