@@ -2039,11 +2039,15 @@ extern "C" size_t gccb_posenc_workspace(int32_t batch, int32_t node_cap) {
          ((size_t)3 * 2 * batch + 4) * sizeof(int32_t);        // work lists + counts of the dense solver (tail)
 }
 
-// largest ego-net handed to the dense tridiagonal solver: GCCB200_DENSE_MAX (0 = ChFSI / Jacobi for every size;
-// read on every call so that a test can compare both solvers in one process)
+// Largest ego-net handed to the dense tridiagonal solver.  Default: its first class, n <= 96 -- the only one that
+// beats the subspace iteration inside the running pipeline (C2 bench on one box, profiles/r02_dense_ab_c2.json:
+// 240.4k subgraphs/s without it, 265.4k with n <= 96, 256.8k with n <= 144, 244.6k with n <= 228: the larger
+// classes hold 108 / 224 KB of shared memory and 512 threads x 64 registers per CTA and crowd the training kernels
+// out of their SMs).  GCCB200_DENSE_MAX overrides (0 = ChFSI / Jacobi for every size, 228 = direct-method accuracy
+// for every ego-net up to 228 vertices); read on every call so that a test can compare the solvers in one process.
 static int posenc_dense_max() {
   const char* e = getenv("GCCB200_DENSE_MAX");
-  int v = GCCB_DN_C;
+  int v = GCCB_DN_A;
   if (e && e[0]) v = atoi(e);
   return v < 0 ? 0 : v > GCCB_DN_C ? GCCB_DN_C : v;
 }

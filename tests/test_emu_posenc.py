@@ -2,9 +2,9 @@
 spectral parity with the oracle (dense float64 eigh) and with the reference's own
 outputs (tests/golden/posenc_golden.npz).  Kernel LOGIC only; see test_gpu_*.
 
-Two solver families share the size range n <= 228: the dense tridiagonal solver (default) and the
-Jacobi / Chebyshev-filtered subspace iteration classes (GCCB200_DENSE_MAX=0, read by gccb_posenc on every
-call); the `solver` fixture runs every test through both."""
+Two solver families share the size range n <= 228: the dense tridiagonal solver (GCCB200_DENSE_MAX=228; the
+product default is 96) and the Jacobi / Chebyshev-filtered subspace iteration classes (GCCB200_DENSE_MAX=0); the
+variable is read by gccb_posenc on every call and the `solver` fixture runs every test through both."""
 import ctypes as C
 import os
 
@@ -20,10 +20,7 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 @pytest.fixture(params=["dense", "iterative"])
 def solver(request, monkeypatch):
-    if request.param == "iterative":
-        monkeypatch.setenv("GCCB200_DENSE_MAX", "0")
-    else:
-        monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    monkeypatch.setenv("GCCB200_DENSE_MAX", "0" if request.param == "iterative" else "228")
     return request.param
 
 
@@ -148,7 +145,7 @@ def test_dense_solver_class_boundaries_and_degenerate_spectra(monkeypatch):
     (k = 1, 2, 3), on exactly degenerate spectra (stars: eigenvalue 0 x 199; a disconnected union) and on paths
     (the matrix is already tridiagonal: every reflector is the identity); tighter bars than the shared ones --
     the fp32 model of the kernel measures eigenvalues to 5e-7 and residuals / orthonormality to 4e-6."""
-    monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    monkeypatch.setenv("GCCB200_DENSE_MAX", "228")
     graphs = [synthetic.path_graph(3), synthetic.path_graph(4), synthetic.path_graph(5), synthetic.star_graph(33),
               synthetic.path_graph(96), synthetic.chung_lu(100, 250, seed=1), synthetic.chung_lu(150, 400, seed=2),
               synthetic.chung_lu(156, 420, seed=3), synthetic.path_graph(228), synthetic.star_graph(200),
@@ -179,7 +176,7 @@ def test_dense_solver_fifteen_fold_cluster_regression(monkeypatch):
     """A sampled C2 ego-net (n = 173) whose 15-fold eigenvalue 1/sqrt 2 made the first cluster member come out of
     Gram-Schmidt with a residual of 2.8e-4 when all inverse iterations ran before the orthogonalisation (the
     iterates of a cluster get more collinear with every iteration); with the two-stage order it is 4e-7."""
-    monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    monkeypatch.setenv("GCCB200_DENSE_MAX", "228")
     z = np.load(os.path.join(G, "egonet_cluster15.npz"))
     ip, ix = z["indptr"].astype(np.int32), z["indices"].astype(np.int32)
     n = len(ip) - 1

@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 #   Inside that cluster (spread up to ~1e-3) WHICH members make the top-32 cut is not resolved either, so the
 #   eigenvalue bar for n > 160 is the cluster spread, 1e-3 (2e-5 everywhere else).
 RES_SMALL, RES_HUB, HUB_N, LAM_SMALL, LAM_HUB = 1e-4, 2.5e-3, 160, 2e-5, 1e-3
-# The dense tridiagonal solver (default for n <= 228; posenc.cu solver (0)) is a direct method: eigenvalues to 2e-6,
+# The dense tridiagonal solver (posenc.cu solver (0); GCCB200_DENSE_MAX=228 here, product default 96) is a direct method: eigenvalues to 2e-6,
 # residuals and orthonormality to 2e-5 (measured on the fp32 model: 5e-7 / 4e-6 / 3e-6), hub-like ego-nets included.
 DENSE_N, RES_DENSE, LAM_DENSE = 228, 2e-5, 2e-6
 
@@ -33,10 +33,7 @@ DENSE_N, RES_DENSE, LAM_DENSE = 228, 2e-5, 2e-6
 @pytest.fixture(params=["dense", "iterative"])
 def solver(request, monkeypatch):
     """gccb_posenc reads GCCB200_DENSE_MAX on every call: 0 sends every size to the Jacobi / ChFSI classes."""
-    if request.param == "iterative":
-        monkeypatch.setenv("GCCB200_DENSE_MAX", "0")
-    else:
-        monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    monkeypatch.setenv("GCCB200_DENSE_MAX", "0" if request.param == "iterative" else "228")
     return request.param
 
 
@@ -108,7 +105,7 @@ def test_dense_eigensolver_class_boundaries(monkeypatch):
     """The dense tridiagonal solver at the edges of its classes (96 / 144 / 228), on exactly degenerate spectra
     (a 200-leaf star, a disconnected union), on paths (already tridiagonal), on k = 1..3, and on the sampled
     ego-net with a 15-fold eigenvalue (tests/golden/egonet_cluster15.npz)."""
-    monkeypatch.delenv("GCCB200_DENSE_MAX", raising=False)
+    monkeypatch.setenv("GCCB200_DENSE_MAX", "228")
     from gcc_b200.datasets import synthetic
     from gcc_b200.datasets.graph_dataset import BatchBuffers
     graphs = [synthetic.path_graph(3), synthetic.path_graph(4), synthetic.path_graph(5), synthetic.star_graph(33),
