@@ -1541,7 +1541,7 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
 //      norm of x, every warp computes the scalars redundantly, w = p - gamma v is formed on the fly inside the
 //      rank-2 update, and the update hands the next column over in contiguous form;
 //   2. the k <= 32 largest eigenvalues of T by multisection on Sturm counts (all threads: a first cut of the
-//      Gershgorin interval into NT + 1 pieces, then NT / 32 points per eigenvalue and round; 6 / 4 rounds);
+//      Gershgorin interval into NT + 1 pieces, then NT / 32 points per eigenvalue and round; 5 / 4 rounds);
 //   3. eigenvectors of T by inverse iteration, one lane per eigenvalue (Gaussian elimination with partial
 //      pivoting; pivot rows that were swapped are original matrix entries, so two floats per row describe the
 //      factor -- kept in the L2-resident workspace, written coalesced, read back with one block prefetched), three
@@ -1595,7 +1595,7 @@ __device__ __forceinline__ int dn_sturm(const float* __restrict__ d, const float
   return c;
 }
 
-template <int NMAX, int NT>
+template <int NMAX, int NT, bool USM>
 __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int node_cap, int edge_cap,
                     const int32_t* __restrict__ node_off, const int32_t* __restrict__ b_indptr,
                     const int32_t* __restrict__ b_indices, const int32_t* __restrict__ sub_deg, int pos_dim, int normalize,
@@ -1618,6 +1618,7 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
   __shared__ float lam[32], lamp[32], lo[32], hi[32], sgn[32];
   __shared__ int cnt[NT];
   __shared__ float part[NW * 32];
+  __shared__ float ufac[USM ? 2 * 32 * NMAX : 1];        // factor rows of the inverse iteration (USM: else in L2)
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = GCCB_CLK();
   const int view = slot / B, g = slot - view * B;
   const int noff = node_off[view * (B + 1) + g];
@@ -1639,8 +1640,8 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
   const int32_t* v_indices = b_indices + (size_t)view * edge_cap;
   const int32_t* v_deg = sub_deg + (size_t)view * node_cap;
   // factor rows of the inverse iteration: two n x 32 arrays in this ego-net's part of the L2 workspace
-  float* U0 = blocks + ((size_t)view * node_cap + noff) * (GCCB_CF_B + 1);
-  float* U1 = U0 + (size_t)2 * node_cap * (GCCB_CF_B + 1);
+  float* U0 = USM ? ufac : blocks + ((size_t)view * node_cap + noff) * (GCCB_CF_B + 1);
+  float* U1 = USM ? ufac + 32 * NMAX : U0 + (size_t)2 * node_cap * (GCCB_CF_B + 1);
   // ---- the matrix ---------------------------------------------------------------------------------------------
   for (int i = tid; i < NP; i += NT) { d[i] = 0.f; e[i] = 0.f; e2[i] = 0.f; taus[i] = 0.f; vbuf[i] = 0.f; pbuf[i] = 0.f; xbuf[i] = 0.f; }
   for (int i = tid; i < n; i += NT) {
@@ -1671,6 +1672,11 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
     for (int kk = 0; kk + 2 < n; ++kk) {
       const int c0 = (kk + 1) & ~3;
       const bool mine = r > kk && r < n;
+      if (warp * 16 + 15 <= kk || warp * 16 >= n) {        // no live row in this warp (rows 16 w .. 16 w + 15)
+        __syncthreads();
+        __syncthreads();
+        continue;
+      }
       float y = 0.f;
       if (mine) {                                       // y = (S x)_r over this thread's half of the row
         float y0 = 0.f, y1 = 0.f;
@@ -1701,8 +1707,10 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
         pbuf[r] = tau * scale * (y - beta * row[kk + 1]);
         row[kk] = vr;                                   // the reflector stays in column kk for step 5
       }
-      if (tid == 2 * kk) { vbuf[kk] = 0.f; pbuf[kk] = 0.f; }
-      if (tid == 0) { d[kk] = A[(size_t)kk * ld + kk]; e[kk] = beta; taus[kk] = tau; }
+      if (tid == 2 * (kk + 1)) {                          // row kk + 1 is always live
+        vbuf[kk] = 0.f; pbuf[kk] = 0.f;
+        d[kk] = A[(size_t)kk * ld + kk]; e[kk] = beta; taus[kk] = tau;
+      }
       __syncthreads();
       if (tau != 0.f) {
         float gs = 0.f;                                 // every warp: gamma = tau/2 * p.v
@@ -1725,7 +1733,7 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
       }
       // the next column in contiguous form, from the thread that owns that element of its row
       if (r > kk + 1 && r < n && h == 0) xbuf[r] = row[kk + 1];   // column kk+1 is in the first 4-column chunk
-      if (tid == 0) xbuf[kk + 1] = 0.f;
+      if (tid == 2 * (kk + 1)) xbuf[kk + 1] = 0.f;
       __syncthreads();
     }
     if (tid == 0) {
@@ -1760,7 +1768,7 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
     }
     __syncthreads();
     constexpr int P = NT / 32;                            // points per eigenvalue and round
-    constexpr int ROUNDS = P >= 16 ? 4 : 6;
+    constexpr int ROUNDS = P >= 16 ? 4 : 5;               // final interval 5e-8 / 1.3e-7: the fp32 spacing of the eigenvalues
     const int j = tid / P, p = tid % P;
     const int want = n - k + j + 1;
     for (int rd = 0; rd < ROUNDS; ++rd) {
@@ -2008,7 +2016,7 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
   write_features(n, k, pos_dim, normalize, sgn, out, [&](int c, int r_) { return zrow(r_)[c]; });
 }
 
-template <int NMAX, int NT>
+template <int NMAX, int NT, bool USM>
 __global__ void __launch_bounds__(NT, 65536 / 64 / NT)
 posenc_dense_kernel(const int32_t* __restrict__ worklist /* this class */, const int32_t* __restrict__ count,
                     int B, int node_cap, int edge_cap, const int32_t* __restrict__ node_off,
@@ -2017,7 +2025,7 @@ posenc_dense_kernel(const int32_t* __restrict__ worklist /* this class */, const
                     float* __restrict__ pos, float* __restrict__ eigvals, int32_t* __restrict__ flags,
                     int32_t* __restrict__ dbg_iters, float* __restrict__ dbg_res, long long* __restrict__ dbg_phase) {
   for (int item = blockIdx.x; item < count[0]; item += gridDim.x) {
-    posenc_dense_item<NMAX, NT>(worklist[item], B, node_cap, edge_cap, node_off, b_indptr, b_indices, sub_deg, pos_dim,
+    posenc_dense_item<NMAX, NT, USM>(worklist[item], B, node_cap, edge_cap, node_off, b_indptr, b_indices, sub_deg, pos_dim,
                                 normalize, blocks, pos, eigvals, flags, dbg_iters, dbg_res, dbg_phase);
     __syncthreads();
   }
@@ -2147,13 +2155,18 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   if (dense_max > 0) {
     // dense classes: n <= 96 (256 threads, 48 KB: four CTAs per SM), n <= 144 (512 threads, 108 KB: two per SM),
     // n <= 228 (512 threads, 224 KB: one per SM); on the streams of the ChFSI classes they replace
-    auto kd_a = posenc_dense_kernel<GCCB_DN_A, 256>;
-    auto kd_b = posenc_dense_kernel<GCCB_DN_B, 512>;
-    auto kd_c = posenc_dense_kernel<GCCB_DN_C, 512>;
+    // class A keeps the factor rows of the inverse iteration in shared memory (74 KB per CTA: three per SM;
+    // GCCB200_DN_USM=0: in the L2 workspace like the larger classes, 50 KB, four per SM)
+    const char* usm_e = getenv("GCCB200_DN_USM");
+    const bool usm = !(usm_e && usm_e[0] == '0');
+    auto kd_a = usm ? posenc_dense_kernel<GCCB_DN_A, 256, true> : posenc_dense_kernel<GCCB_DN_A, 256, false>;
+    auto kd_b = posenc_dense_kernel<GCCB_DN_B, 512, false>;
+    auto kd_c = posenc_dense_kernel<GCCB_DN_C, 512, false>;
     const size_t sd_a = (size_t)GCCB_DN_A * dn_ld(GCCB_DN_A) * sizeof(float);
     const size_t sd_b = (size_t)GCCB_DN_B * dn_ld(GCCB_DN_B) * sizeof(float);
     const size_t sd_c = (size_t)GCCB_DN_C * dn_ld(GCCB_DN_C) * sizeof(float);
-    gccb::ensure_dyn_smem(kd_a, sd_a);
+    gccb::ensure_dyn_smem(posenc_dense_kernel<GCCB_DN_A, 256, true>, sd_a);
+    gccb::ensure_dyn_smem(posenc_dense_kernel<GCCB_DN_A, 256, false>, sd_a);
     gccb::ensure_dyn_smem(kd_b, sd_b);
     gccb::ensure_dyn_smem(kd_c, sd_c);
 #define GCCB_DN_ARGS(c) dense_list + (size_t)(c) * 2 * B, dense_counts + (c), B, batch->node_cap, batch->edge_cap, \
@@ -2163,7 +2176,7 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
     auto env_cap = [](const char* name, int dflt) { const char* e = getenv(name); const int v = e && e[0] ? atoi(e) : dflt; return v > 0 ? v : dflt; };
     GCCB_LAUNCH(kd_c, capped(env_cap("GCCB200_DN_CAP_C", GCCB_CAP_DN_C)), 512, sd_c, s_big, GCCB_DN_ARGS(2));
     GCCB_LAUNCH(kd_b, capped(env_cap("GCCB200_DN_CAP_B", GCCB_CAP_DN_B)), 512, sd_b, s_mid2, GCCB_DN_ARGS(1));
-    GCCB_LAUNCH(kd_a, capped(env_cap("GCCB200_DN_CAP_A", GCCB_CAP_DN_A)), 256, sd_a, s_mid1, GCCB_DN_ARGS(0));
+    GCCB_LAUNCH(kd_a, capped(env_cap("GCCB200_DN_CAP_A", usm ? 148 * 3 : GCCB_CAP_DN_A)), 256, sd_a, s_mid1, GCCB_DN_ARGS(0));
   }
   GCCB_LAUNCH(kbig, capped(148), GCCB_BIG_NT, s_c, s_big, GCCB_PE_ARGS(3));
   // classes the dense solver covers completely have empty lists: not launched
