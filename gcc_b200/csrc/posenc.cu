@@ -2155,10 +2155,12 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
   if (dense_max > 0) {
     // dense classes: n <= 96 (256 threads, 48 KB: four CTAs per SM), n <= 144 (512 threads, 108 KB: two per SM),
     // n <= 228 (512 threads, 224 KB: one per SM); on the streams of the ChFSI classes they replace
-    // class A keeps the factor rows of the inverse iteration in shared memory (74 KB per CTA: three per SM;
-    // GCCB200_DN_USM=0: in the L2 workspace like the larger classes, 50 KB, four per SM)
+    // GCCB200_DN_USM=1: class A keeps the factor rows of the inverse iteration in shared memory (74 KB per CTA, three
+    // per SM) instead of the L2 workspace (50 KB, four per SM).  Measured on the C2 bench (profiles/
+    // r02_dense_ab2_c2.json): 261.4k subgraphs/s against 265.2k -- the shorter inverse iteration does not pay for
+    // the larger footprint -- so it stays off.
     const char* usm_e = getenv("GCCB200_DN_USM");
-    const bool usm = !(usm_e && usm_e[0] == '0');
+    const bool usm = usm_e && usm_e[0] == '1';
     auto kd_a = usm ? posenc_dense_kernel<GCCB_DN_A, 256, true> : posenc_dense_kernel<GCCB_DN_A, 256, false>;
     auto kd_b = posenc_dense_kernel<GCCB_DN_B, 512, false>;
     auto kd_c = posenc_dense_kernel<GCCB_DN_C, 512, false>;

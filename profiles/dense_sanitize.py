@@ -19,6 +19,7 @@ from gcc_b200 import _capi  # noqa: E402
 from gcc_b200.datasets import synthetic  # noqa: E402
 from oracle import posenc as opos  # noqa: E402  (checker only)
 
+os.environ["GCCB200_DENSE_MAX"] = "228"                   # every dense class (the product default is n <= 96)
 rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
 rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
 rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
