@@ -113,7 +113,13 @@ int gccb_sample_batch(const gccb_graph_t* graph, const int64_t* seeds,
  * D^-1/2 A D^-1/2, ascending, row-L2 normalised, zero-padded to pos_dim.
  * pos: [2][node_cap][pos_dim]; eigvals (optional, may be NULL): [2B][pos_dim]
  * ascending top-k eigenvalues (padding = 0).  normalize=0 returns the raw unit
- * eigenvectors (used by the spectral parity tests).                                    */
+ * eigenvectors (used by the spectral parity tests).
+ * Solvers by ego-net size (device-built work lists, csrc/posenc.cu): a dense tridiagonal
+ * solver (Householder -> multisection -> inverse iteration; a direct method) for n <= 96,
+ * Chebyshev-filtered subspace iteration above.  The environment variable
+ * GCCB200_DENSE_MAX (0 .. 228, read on every call) moves that boundary: 0 = subspace
+ * iteration / Jacobi for every size, 228 = direct-method accuracy up to 228 vertices.
+ * Results are deterministic run to run for a given setting.                              */
 size_t gccb_posenc_workspace(int32_t batch, int32_t node_cap);
 int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t normalize, float* pos,
                 float* eigvals, void* workspace, size_t workspace_bytes,
