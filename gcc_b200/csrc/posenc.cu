@@ -2176,8 +2176,12 @@ extern "C" int gccb_posenc(const gccb_batch_t* batch, int32_t pos_dim, int32_t n
     batch->flags, dbg_iters, dbg_res, dbg_phase
     // (diagnostics: GCCB200_DN_CAP_A / _B / _C override the persistent grid sizes, i.e. the CTAs per SM)
     auto env_cap = [](const char* name, int dflt) { const char* e = getenv(name); const int v = e && e[0] ? atoi(e) : dflt; return v > 0 ? v : dflt; };
-    GCCB_LAUNCH(kd_c, capped(env_cap("GCCB200_DN_CAP_C", GCCB_CAP_DN_C)), 512, sd_c, s_big, GCCB_DN_ARGS(2));
-    GCCB_LAUNCH(kd_b, capped(env_cap("GCCB200_DN_CAP_B", GCCB_CAP_DN_B)), 512, sd_b, s_mid2, GCCB_DN_ARGS(1));
+    // classes above dense_max have empty lists: not launched (an idle CTA of theirs must still win 108 / 224 KB of
+    // shared memory to exit -- 40-170 us at the head of the streams of the ChFSI classes, CUPTI timeline)
+    if (dense_max > GCCB_DN_B)
+      GCCB_LAUNCH(kd_c, capped(env_cap("GCCB200_DN_CAP_C", GCCB_CAP_DN_C)), 512, sd_c, s_big, GCCB_DN_ARGS(2));
+    if (dense_max > GCCB_DN_A)
+      GCCB_LAUNCH(kd_b, capped(env_cap("GCCB200_DN_CAP_B", GCCB_CAP_DN_B)), 512, sd_b, s_mid2, GCCB_DN_ARGS(1));
     GCCB_LAUNCH(kd_a, capped(env_cap("GCCB200_DN_CAP_A", usm ? 148 * 3 : GCCB_CAP_DN_A)), 256, sd_a, s_mid1, GCCB_DN_ARGS(0));
   }
   GCCB_LAUNCH(kbig, capped(148), GCCB_BIG_NT, s_c, s_big, GCCB_PE_ARGS(3));
