@@ -7,16 +7,21 @@
 // k <= 0 -> zeros.  The reference runs ARPACK (scipy eigsh, float64, random v0)
 // per ego-net on a CPU worker: ~2.8 ms each, the dominant cost of its pipeline.
 //
-// Two device solvers, one CTA per ego-net, chosen by size through device-built work lists:
+// Three device solvers, one CTA (or one cluster) per ego-net, chosen by size through device-built work lists:
 //
-//  (1) n <= 64: dense one-sided (Hestenes) Jacobi.  G = L + 2I (SPD, spectrum in [1,3]) lives in
+//  (0) n <= 96 by default (up to 228 with GCCB200_DENSE_MAX): the dense tridiagonal solver -- Householder
+//      tridiagonalisation of the whole matrix in shared memory, multisection on Sturm counts, inverse iteration
+//      with one common shift per multiple eigenvalue, Gram-Schmidt inside clusters, back-transformation in
+//      registers.  A direct method: eigenvalues / residuals / orthonormality to 1e-6.  See its own comment below.
+//
+//  (1) n <= 64, only with solver (0) off: dense one-sided (Hestenes) Jacobi.  G = L + 2I (SPD, spectrum in [1,3]) lives in
 //      shared memory, column-major; plane rotations applied on the right orthogonalise its
 //      columns; because G is symmetric positive definite the converged columns are
 //      lambda_j' v_j, so the eigenvectors are the normalised columns and no V matrix is stored.
 //      A warp owns one column pair per step of a round-robin tournament; dot products by
 //      shuffle reduction, rotations in registers.
 //
-//  (2) n > 64: Chebyshev-filtered subspace iteration (ChFSI) on a block of 48 vectors, any n.
+//  (2) every larger n: Chebyshev-filtered subspace iteration (ChFSI) on a block of 48 vectors, any n.
 //      Ego-nets are star-like: their spectra have one huge degenerate cluster, so a degree-4/8
 //      Chebyshev filter on [-1, cut] followed by Rayleigh-Ritz converges in ~3 outer iterations
 //      (measured on the C2 workload).  Per iteration: 8 sparse products with the sub-CSR (fused
@@ -25,7 +30,7 @@
 //      an L2-resident workspace (2 blocks per ego-net), so shared memory does not bound n and
 //      8 CTAs fit per SM.  Cost is O(n * 48^2) instead of the O(n^3) of a dense solve.
 //
-// Both return an orthonormal basis of every eigenspace (degenerate clusters included), Ritz
+// All return an orthonormal basis of every eigenspace (degenerate clusters included), Ritz
 // values as Rayleigh quotients, a deterministic sign (largest-|.| component positive) and are
 // deterministic run to run (no floating-point atomics on the results).
 #include "common.cuh"
