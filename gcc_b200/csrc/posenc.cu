@@ -1685,7 +1685,22 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
       float y = 0.f;
       if (mine) {                                       // y = (S x)_r over this thread's half of the row
         float y0 = 0.f, y1 = 0.f;
-        for (int c = c0 + 4 * h; c < n; c += 8) {
+        int c = c0 + 4 * h;
+        for (; c + 8 < n; c += 16) {                      // two chunks per trip: four loads in flight
+          const float4 a = *reinterpret_cast<const float4*>(row + c);
+          const float4 x = *reinterpret_cast<const float4*>(xbuf + c);
+          const float4 a2 = *reinterpret_cast<const float4*>(row + c + 8);
+          const float4 x2 = *reinterpret_cast<const float4*>(xbuf + c + 8);
+          y0 = fmaf(a.x, x.x, y0);
+          y1 = fmaf(a.y, x.y, y1);
+          y0 = fmaf(a.z, x.z, y0);
+          y1 = fmaf(a.w, x.w, y1);
+          y0 = fmaf(a2.x, x2.x, y0);
+          y1 = fmaf(a2.y, x2.y, y1);
+          y0 = fmaf(a2.z, x2.z, y0);
+          y1 = fmaf(a2.w, x2.w, y1);
+        }
+        if (c < n) {
           const float4 a = *reinterpret_cast<const float4*>(row + c);
           const float4 x = *reinterpret_cast<const float4*>(xbuf + c);
           y0 = fmaf(a.x, x.x, y0);
@@ -1724,14 +1739,30 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
         if (mine) {
           const float vr = vbuf[r], wr = fmaf(-gam, vr, pbuf[r]);
           const float nvr = -vr, nwr = -wr;
-          for (int c = c0 + 4 * h; c < n; c += 8) {     // S -= v w^T + w v^T, w = p - gamma v
-            float4 a = *reinterpret_cast<float4*>(row + c);
-            const float4 v4 = *reinterpret_cast<const float4*>(vbuf + c);
-            const float4 p4 = *reinterpret_cast<const float4*>(pbuf + c);
+          auto upd = [&](float4& a, const float4& v4, const float4& p4) {   // S -= v w^T + w v^T, w = p - gamma v
             a.x = fmaf(nwr, v4.x, fmaf(nvr, fmaf(-gam, v4.x, p4.x), a.x));
             a.y = fmaf(nwr, v4.y, fmaf(nvr, fmaf(-gam, v4.y, p4.y), a.y));
             a.z = fmaf(nwr, v4.z, fmaf(nvr, fmaf(-gam, v4.z, p4.z), a.z));
             a.w = fmaf(nwr, v4.w, fmaf(nvr, fmaf(-gam, v4.w, p4.w), a.w));
+          };
+          int c = c0 + 4 * h;
+          for (; c + 8 < n; c += 16) {                    // two chunks per trip: six loads in flight, then the stores
+            float4 a = *reinterpret_cast<float4*>(row + c);
+            const float4 v4 = *reinterpret_cast<const float4*>(vbuf + c);
+            const float4 p4 = *reinterpret_cast<const float4*>(pbuf + c);
+            float4 a2 = *reinterpret_cast<float4*>(row + c + 8);
+            const float4 v42 = *reinterpret_cast<const float4*>(vbuf + c + 8);
+            const float4 p42 = *reinterpret_cast<const float4*>(pbuf + c + 8);
+            upd(a, v4, p4);
+            upd(a2, v42, p42);
+            *reinterpret_cast<float4*>(row + c) = a;
+            *reinterpret_cast<float4*>(row + c + 8) = a2;
+          }
+          if (c < n) {
+            float4 a = *reinterpret_cast<float4*>(row + c);
+            const float4 v4 = *reinterpret_cast<const float4*>(vbuf + c);
+            const float4 p4 = *reinterpret_cast<const float4*>(pbuf + c);
+            upd(a, v4, p4);
             *reinterpret_cast<float4*>(row + c) = a;
           }
         }
@@ -1849,56 +1880,65 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
     float bscale = 1.0f;
     const int nit = stage == 0 ? GCCB_DN_INVIT - 1 : 1;
     for (int it = 0; it < nit; ++it) {
-      // forward elimination with partial pivoting of T - lj I, applied to the right-hand side in place
+      // forward elimination with partial pivoting of T - lj I, applied to the right-hand side in place.  One
+      // branch-free path for both pivot choices (lanes differ), and the operands of row i + 2 are loaded before
+      // row i is stored: shared-memory loads cannot be moved across the store by the compiler.
       float cd = d[0] - lj, cu = e[0];
       float bi = zrow(0)[j] * bscale;
+      float sub = e[0], nd_raw = d[1], nu = e[1], bn_raw = zrow(1)[j];       // n >= 3
       for (int i = 0; i + 1 < n; ++i) {
-        const float sub = e[i], nd = d[i + 1] - lj, nu = e[i + 1];   // e[n-1] = 0
-        const float bn = zrow(i + 1)[j] * bscale;
-        float s0, s1;
-        if (fabsf(cd) >= fabsf(sub)) {
-          if (fabsf(cd) < GCCB_DN_GUARD) cd = copysignf(GCCB_DN_GUARD, cd);
-          const float rinv = __fdividef(1.0f, cd);        // kept for the back substitution (never 0: |cd| < 4)
-          const float m = sub * rinv;
-          s0 = rinv; s1 = cu;
-          cd = fmaf(-m, cu, nd); cu = nu;
-          zrow(i)[j] = bi;
-          bi = fmaf(-m, bi, bn);
-        } else {                                          // rows swapped: the pivot row is (e[i], d[i+1]-lj, e[i+1])
-          const float m = cd / sub;
-          s0 = 0.f; s1 = 0.f;
-          cd = fmaf(-m, nd, cu); cu = -m * nu;
-          zrow(i)[j] = bn;
-          bi = fmaf(-m, bn, bi);
-        }
-        U0[(size_t)i * 32 + j] = s0;
-        U1[(size_t)i * 32 + j] = s1;
+        const int i2 = i + 2 < n ? i + 2 : n - 1;
+        const float d_next = d[i + 2], e_next = e[i + 2], b_next = zrow(i2)[j];   // d, e are zero-padded past n
+        const float nd = nd_raw - lj, bn = bn_raw * bscale;
+        const bool sw = fabsf(cd) < fabsf(sub);           // rows swapped: the pivot row is (e[i], d[i+1]-lj, e[i+1])
+        const float cdg = fabsf(cd) < GCCB_DN_GUARD ? copysignf(GCCB_DN_GUARD, cd) : cd;
+        const float rinv = __fdividef(1.0f, sw ? sub : cdg);
+        const float m = (sw ? cd : sub) * rinv;
+        const float bs = sw ? bn : bi, bo = sw ? bi : bn;
+        zrow(i)[j] = bs;
+        U0[(size_t)i * 32 + j] = sw ? 0.f : rinv;          // 1 / pivot, kept for the back substitution (never 0: |cd| < 4)
+        U1[(size_t)i * 32 + j] = sw ? 0.f : cu;
+        cd = sw ? fmaf(-m, nd, cu) : fmaf(-m, cu, nd);
+        cu = sw ? -m * nu : nu;
+        bi = fmaf(-m, bs, bo);
+        sub = nu; nd_raw = d_next; nu = e_next; bn_raw = b_next;
       }
       if (fabsf(cd) < GCCB_DN_GUARD) cd = copysignf(GCCB_DN_GUARD, cd);
-      // back substitution, factor rows prefetched one block of four ahead
+      // back substitution: factor rows (L2) prefetched two blocks of four ahead, the shared-memory operands of a
+      // block loaded before its chain starts
       float x1 = bi / cd, x2 = 0.f, mx = fabsf(x1);
       zrow(n - 1)[j] = x1;
-      float f0[4], f1[4], g0[4], g1[4];
+      float f0[4], f1[4], g0[4], g1[4], h0[4], h1[4];
       int ib = n - 2;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const int i = ib - q; f0[q] = i >= 0 ? U0[(size_t)i * 32 + j] : 1.f; f1[q] = i >= 0 ? U1[(size_t)i * 32 + j] : 0.f; }
+      for (int q = 0; q < 4; ++q) {
+        const int i = ib - q, i4 = ib - 4 - q;
+        f0[q] = i >= 0 ? U0[(size_t)i * 32 + j] : 1.f; f1[q] = i >= 0 ? U1[(size_t)i * 32 + j] : 0.f;
+        g0[q] = i4 >= 0 ? U0[(size_t)i4 * 32 + j] : 1.f; g1[q] = i4 >= 0 ? U1[(size_t)i4 * 32 + j] : 0.f;
+      }
       while (ib >= 0) {
+        float eb[5], db[4], bb[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const int i = ib - 4 - q; g0[q] = i >= 0 ? U0[(size_t)i * 32 + j] : 1.f; g1[q] = i >= 0 ? U1[(size_t)i * 32 + j] : 0.f; }
+        for (int q = 0; q < 4; ++q) {
+          const int i8 = ib - 8 - q, i = ib - q >= 0 ? ib - q : 0;
+          h0[q] = i8 >= 0 ? U0[(size_t)i8 * 32 + j] : 1.f; h1[q] = i8 >= 0 ? U1[(size_t)i8 * 32 + j] : 0.f;
+          eb[q + 1] = e[i]; db[q] = d[i + 1]; bb[q] = zrow(i)[j];
+        }
+        eb[0] = e[ib + 1];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int i = ib - q;
           if (i >= 0) {
             float ri = f0[q], u1 = f1[q], u2 = 0.f;
-            if (ri == 0.f) { ri = __fdividef(1.0f, e[i]); u1 = d[i + 1] - lj; u2 = e[i + 1]; }
-            const float x = (zrow(i)[j] - u1 * x1 - u2 * x2) * ri;
+            if (ri == 0.f) { ri = __fdividef(1.0f, eb[q + 1]); u1 = db[q] - lj; u2 = eb[q]; }
+            const float x = (bb[q] - u1 * x1 - u2 * x2) * ri;
             zrow(i)[j] = x;
             mx = fmaxf(mx, fabsf(x));
             x2 = x1; x1 = x;
           }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { f0[q] = g0[q]; f1[q] = g1[q]; }
+        for (int q = 0; q < 4; ++q) { f0[q] = g0[q]; f1[q] = g1[q]; g0[q] = h0[q]; g1[q] = h1[q]; }
         ib -= 4;
       }
       if (!(mx > 0.f && mx < 3.0e38f)) {                  // overflow / breakdown: never seen; keep a valid vector
@@ -1920,7 +1960,18 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
     for (int j = k - 1; j >= 1; --j) {
       if (!(lam[j] - lam[j - 1] < GCCB_DN_GAPTOL)) continue;
       float acc = 0.f;
-      for (int i = warp; i < n; i += NW) { const float* zr = zrow(i); acc = fmaf(zr[j], zr[lane], acc); }
+      for (int i0 = warp; i0 < n; i0 += 4 * NW) {         // four rows per trip: eight loads in flight
+        float zj[4], zc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q * NW;
+          const float* zr = zrow(i < n ? i : i0);
+          zj[q] = i < n ? zr[j] : 0.f;
+          zc[q] = zr[lane];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc = fmaf(zj[q], zc[q], acc);
+      }
       part[warp * 32 + lane] = acc;
       __syncthreads();
       float dot = 0.f, nn = 0.f;
@@ -1928,7 +1979,21 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
       for (int w = 0; w < NW; ++w) { dot += part[w * 32 + lane]; nn += part[w * 32 + j]; }
       const float coef = dot / fmaxf(nn, 1.0e-30f);
       if (lane < j)
-        for (int i = warp; i < n; i += NW) { float* zr = zrow(i); zr[lane] = fmaf(-coef, zr[j], zr[lane]); }
+        for (int i0 = warp; i0 < n; i0 += 4 * NW) {       // loads of four rows, then their stores
+          float zj[4], zc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * NW;
+            const float* zr = zrow(i < n ? i : i0);
+            zj[q] = zr[j];
+            zc[q] = zr[lane];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * NW;
+            if (i < n) zrow(i)[lane] = fmaf(-coef, zj[q], zc[q]);
+          }
+        }
       __syncthreads();
     }
   if (stage == 1) {                                       // unit columns
