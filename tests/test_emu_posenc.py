@@ -239,3 +239,29 @@ def test_dense_solver_random_structures(monkeypatch):
             theta, resid, ortho = opos.spectral_report(lap, pos[v, a:z, :k].astype(np.float64))
             assert np.abs(eig[v * b.B + gi, :k] - w_exact).max() < 2e-6 and resid.max() < 2e-5 and ortho < 2e-5, (
                 n, np.abs(eig[v * b.B + gi, :k] - w_exact).max(), resid.max(), ortho)
+
+
+@pytest.mark.parametrize("pos_dim", [5, 16])
+def test_dense_solver_other_feature_widths(monkeypatch, pos_dim):
+    """positional_embedding_size below 32 (train.py:94 is a free parameter): k = min(n - 2, pos_dim) columns, the rest
+    zero; the top-k cut may fall inside a multiple eigenvalue (the star's 0 x 39)."""
+    monkeypatch.setenv("GCCB200_DENSE_MAX", "228")
+    views = [[_sub(synthetic.chung_lu(90, 240, seed=2)), _sub(synthetic.path_graph(7))],
+             [_sub(synthetic.star_graph(40)), _sub(synthetic.chung_lu(150, 400, seed=3))]]
+    L = lib()
+    b = NpBatch.from_subgraphs(views)
+    pos = np.full((2, b.node_cap, pos_dim), np.nan, np.float32)
+    eig = np.full((2 * b.B, pos_dim), np.nan, np.float32)
+    ws = np.zeros(L.gccb_posenc_workspace(b.B, b.node_cap), np.uint8)
+    assert L.gccb_posenc(C.byref(b.c), pos_dim, 0, ptr(pos), ptr(eig), ptr(ws), ws.nbytes, None) == 0
+    assert b.flags[0] == 0
+    for v in (0, 1):
+        for gi, sub in enumerate(views[v]):
+            a, z = b.node_off[v, gi], b.node_off[v, gi + 1]
+            n = sub["n"]
+            k = min(n - 2, pos_dim)
+            lap = opos.normalized_adjacency(sub["indptr"], sub["indices"], n).toarray()
+            w, _ = opos.eig_topk_exact(lap, k)
+            theta, resid, ortho = opos.spectral_report(lap, pos[v, a:z, :k].astype(np.float64))
+            assert np.all(pos[v, a:z, k:] == 0) and np.all(eig[v * b.B + gi, k:] == 0)
+            assert np.abs(eig[v * b.B + gi, :k] - w).max() < 2e-6 and resid.max() < 2e-5 and ortho < 2e-5
