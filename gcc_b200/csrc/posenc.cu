@@ -1576,15 +1576,6 @@ posenc_chfsi_cluster_kernel(const int32_t* __restrict__ worklist, const int32_t*
 #define GCCB_DN_RES_FLAG 1.0e-3f
 
 
-#ifdef GCCB_EMU_DEBUG_DN
-#define DN_DEBUG(tag) do { __syncthreads(); if (tid == 0 && getenv("GCCB_DN_DEBUG")) { \
-    fprintf(stderr, "DN %s n=%d:", tag, n); \
-    for (int c = 0; c < k; ++c) { double rs = 0, nn = 0; \
-      for (int i = 0; i < n; ++i) { double y = (double)d[i] * zrow(i)[c] + (i > 0 ? (double)e[i-1] * zrow(i-1)[c] : 0.0) + (i + 1 < n ? (double)e[i] * zrow(i+1)[c] : 0.0) - (double)lam[c] * zrow(i)[c]; rs += y * y; nn += (double)zrow(i)[c] * zrow(i)[c]; } \
-      fprintf(stderr, " %.1e", sqrt(rs / nn)); } fprintf(stderr, "\n"); } __syncthreads(); } while (0)
-#else
-#define DN_DEBUG(tag)
-#endif
 __host__ __device__ constexpr int dn_ld(int n) { return ((n + 23) / 32) * 32 + 8; }   // >= n, = 8 mod 32
 
 // number of eigenvalues of T below x
@@ -1951,7 +1942,6 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
     for (int i = 0; i < n; ++i) zrow(i)[j] *= bscale;
   }
   __syncthreads();
-  DN_DEBUG("invit");
   GCCB_TICK(3);
   // modified Gram-Schmidt (right-looking), lanes = columns.  Step j removes z_j from the columns below it; it is
   // needed only when eigenvalue j has a lower neighbour within GCCB_DN_GAPTOL (eigenvectors of T further apart come
@@ -2008,7 +1998,6 @@ __device__ __forceinline__ void posenc_dense_item(const int slot, int B, int nod
     for (int i = warp; i < n; i += NW) zrow(i)[lane] *= inv;
     __syncthreads();
   }
-  DN_DEBUG("mgs");
   GCCB_TICK(4);
   }
   // ---- 5. X = Q Z: all reflectors on this warp's columns, in registers --------------------------------------------
